@@ -1,0 +1,115 @@
+/* libpram_b200 -- C ABI of the B200-native (sm_100a) PRAM localization hot path.
+ *
+ * The reference (feixue94/pram) is 100 % Python/PyTorch and has no FFI of its own; its operator
+ * boundary is the Python API in nets/{sfd2,segnetvit,gml,adagml}.py and localization/matchers/*.py
+ * (SURVEY.md section 8b).  pram_b200 keeps that Python API and implements it on top of the entry
+ * points below, which a reference maintainer could equally bind with ctypes from the original modules
+ * (INTEGRATION.md shows the stubs).  Every entry point cites the reference code it replaces.
+ *
+ * Conventions: plain device pointers and sizes, no allocation and no host synchronisation inside,
+ * work is enqueued on the given cudaStream_t (passed as void*), return 0 on success or a negative
+ * PRAM_ERR_* code.  All floating-point buffers are fp32 unless stated; feature maps are NHWC.
+ */
+#ifndef PRAM_B200_H
+#define PRAM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRAM_OK 0
+#define PRAM_ERR_ARG (-1)
+#define PRAM_ERR_CUDA (-2)
+#define PRAM_ERR_WORKSPACE (-3)
+#define PRAM_ERR_UNSUPPORTED (-4)
+
+typedef void* pram_stream_t; /* cudaStream_t */
+
+int pram_version(void);
+unsigned long long pram_launch_count(void); /* kernels launched by this library so far */
+const char* pram_error_string(int code);
+const char* pram_last_cuda_error(void);
+
+/* K5: softmax(65) -> drop dustbin -> 8x8 pixel shuffle.  nets/sfd2.py:294-300.
+ * logits addressed as base + b*batch_stride + hc*y_stride + wc*x_stride + c*ch_stride (floats). */
+int pram_score_map(const float* logits, long long batch_stride, long long y_stride, long long x_stride,
+                   long long ch_stride, int B, int Hc, int Wc, float* score, pram_stream_t stream);
+
+/* K5b: bilinear resize, align_corners=True.  nets/sfd2.py:301-303. */
+int pram_resize_bilinear(const float* in, int B, int Hi, int Wi, float* out, int Ho, int Wo,
+                         pram_stream_t stream);
+
+/* K6: simple_nms(radius) + candidate emission.  nets/sfd2.py:20-35, 305-315.
+ * cand[B][cap] receives 64-bit keys (score bits << 32 | y*W+x) of survivors >= th_lo;
+ * cand_count[B] their number (may exceed cap: overflow), count_hi[B] the number >= th_hi.
+ * nms_out (optional) receives the dense NMS map. */
+int pram_nms_candidates(const float* score, int B, int H, int W, int radius, float th_lo, float th_hi,
+                        float* nms_out, unsigned long long* cand, int cap, int* cand_count, int* count_hi,
+                        pram_stream_t stream);
+
+/* K7: threshold fallback, border removal, top-k / row-major ordering, (x,y) float output.
+ * nets/sfd2.py:38-50, 306-329.  kpts[B][kpad][2], scores[B][kpad], n_out[B]. */
+int pram_select_keypoints(const unsigned long long* cand, int cap, const int* cand_count, const int* count_hi,
+                          const float* score, int B, int H, int W, float th_lo, float th_hi, int min_keypoints,
+                          int max_keypoints, int border, float* kpts, float* scores, int* n_out, int kpad,
+                          pram_stream_t stream);
+
+/* K8: bilinear sampling of an NHWC map at keypoints (+ optional L2 norm).  nets/sfd2.py:53-64, 348-363.
+ * fmap[B][h][w][C], kpts[B][kpad][2], counts[B] or NULL, out[B][kpad][C]. */
+int pram_sample_features(const float* fmap, int B, int C, int h, int w, const float* kpts, const int* counts,
+                         int kpad, int s, int normalize, float* out, pram_stream_t stream);
+
+/* score_map[b][(int)y][(int)x] gather.  nets/sfd2.py:367. */
+int pram_gather_scores(const float* score, int B, int H, int W, const float* kpts, const int* counts, int kpad,
+                       float* out, pram_stream_t stream);
+
+/* K9: normalize_keypoints + learnable Fourier encoding -> cos/sin [tokens][32].
+ * nets/utils.py:17-24, nets/segnetvit.py:35-40 (== nets/gml.py:69-74). */
+int pram_posenc(const float* kpts, int tokens, float width, float height, int prenormalized, const float* Wr,
+                float* cos_out, float* sin_out, pram_stream_t stream);
+
+/* K1-K4 (fp32 CUDA-core path): 3x3 / 1x1 convolution, NHWC, BN pre-folded, fused bias/residual/ReLU.
+ * nets/sfd2.py:141-170.  w[taps][Cin][Cout]. */
+int pram_conv_f32(const float* in, long long in_pix_stride, const float* w, const float* bias, const float* res,
+                  long long res_pix_stride, float* out, long long out_pix_stride, int B, int H, int W, int Cin,
+                  int Cout, int ksize, int stride, int relu, pram_stream_t stream);
+
+/* nn.Linear / batched A.B^T with row strides (concat-free MLPs).  nets/segnetvit.py:88-95,
+ * nets/gml.py:119-126, 152-159, 278-282. */
+int pram_linear_f32(const float* a, long long lda, const float* w, const float* bias, const float* res,
+                    long long ldres, float* out, long long ldo, long long rows, int K, int N, int relu, int batch,
+                    long long a_batch_stride, long long w_batch_stride, long long out_batch_stride,
+                    pram_stream_t stream);
+
+/* K2: grouped 3x3 convolution (32 groups x 8 channels) + bias + ReLU.  nets/sfd2.py:101. */
+int pram_gconv3x3_f32(const float* in, const float* w, const float* bias, float* out, int B, int H, int W,
+                      int groups, int relu, pram_stream_t stream);
+
+/* F.normalize over the channel axis of an NHWC map.  nets/sfd2.py:333. */
+int pram_l2norm_rows(const float* in, float* out, long long rows, int C, pram_stream_t stream);
+
+/* LayerNorm + exact GELU.  nets/segnetvit.py:92-93. */
+int pram_layernorm_gelu(const float* in, const float* gamma, const float* beta, float* out, long long rows, int C,
+                        int gelu, pram_stream_t stream);
+
+/* qkv split + rotary embedding -> q,k,v [B][heads][N][64].  nets/segnetvit.py:15-23, 98-103. */
+int pram_rotary_split(const float* qkv, int nparts, int B, int N, int heads, const float* cosb, const float* sinb,
+                      float scale_qk, float* q, float* k, float* v, pram_stream_t stream);
+
+/* K10/K12/K13: softmax(QK^T*scale)V without materialising the N x N matrix; optional per-key mean
+ * attention (AdaGML).  nets/segnetvit.py:73-76, nets/gml.py:175-181, nets/adagml.py:148. */
+int pram_attention_f32(const float* Q, const float* K, const float* V, int B, int heads, int Nq, int Nk,
+                       float scale, float* out, int out_stride, float* colmean, pram_stream_t stream);
+
+/* K15+K16: dustbin Sinkhorn (probability domain) + mutual arg-max matches in one launch.
+ * nets/gml.py:27-46, 304-319.  pws: pram_sinkhorn_workspace_floats() floats (holds P on return),
+ * iws: B*(M+N) ints, fws: B*M floats. */
+long long pram_sinkhorn_workspace_floats(int B, int M, int N);
+int pram_sinkhorn_match(const float* dist, int B, int M, int N, const float* bin_score, int iters,
+                        float threshold, float* pws, int* iws, float* fws, long long* matches0,
+                        long long* matches1, float* mscores0, float* mscores1, int cluster, pram_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRAM_B200_H */

@@ -1,0 +1,101 @@
+"""ctypes binding of ``csrc/libpram_b200.so`` (the C ABI declared in ``include/pram_b200.h``).
+
+There is no CPU fallback: if the shared library is missing or a call fails, this raises.
+PyTorch is used only to own device memory and streams; every argument crossing the boundary is a
+raw pointer / size / ``cudaStream_t``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / 'csrc' / 'libpram_b200.so'
+
+_P = C.c_void_p
+_I = C.c_int
+_L = C.c_longlong
+_F = C.c_float
+
+# name -> (restype, argtypes); mirrors include/pram_b200.h one to one
+SIGNATURES = {
+    'pram_version': (_I, []),
+    'pram_launch_count': (C.c_ulonglong, []),
+    'pram_error_string': (C.c_char_p, [_I]),
+    'pram_last_cuda_error': (C.c_char_p, []),
+    'pram_score_map': (_I, [_P, _L, _L, _L, _L, _I, _I, _I, _P, _P]),
+    'pram_resize_bilinear': (_I, [_P, _I, _I, _I, _P, _I, _I, _P]),
+    'pram_nms_candidates': (_I, [_P, _I, _I, _I, _I, _F, _F, _P, _P, _I, _P, _P, _P]),
+    'pram_select_keypoints': (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _F, _F, _I, _I, _I, _P, _P, _P, _I, _P]),
+    'pram_sample_features': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P]),
+    'pram_gather_scores': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P]),
+    'pram_posenc': (_I, [_P, _I, _F, _F, _I, _P, _P, _P, _P]),
+    'pram_conv_f32': (_I, [_P, _L, _P, _P, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'pram_linear_f32': (_I, [_P, _L, _P, _P, _P, _L, _P, _L, _L, _I, _I, _I, _I, _L, _L, _L, _P]),
+    'pram_gconv3x3_f32': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'pram_l2norm_rows': (_I, [_P, _P, _L, _I, _P]),
+    'pram_layernorm_gelu': (_I, [_P, _P, _P, _P, _L, _I, _I, _P]),
+    'pram_rotary_split': (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P, _P]),
+    'pram_attention_f32': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _P, _P]),
+    'pram_sinkhorn_workspace_floats': (_L, [_I, _I, _I]),
+    'pram_sinkhorn_match': (_I, [_P, _I, _I, _I, _P, _I, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+}
+
+_lib = None
+
+
+class PramError(RuntimeError):
+    pass
+
+
+def load(path: os.PathLike | None = None) -> C.CDLL:
+    """Load the shared library (once) and attach argument types.  Fails loudly."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path is not None else LIB_PATH
+    if not p.exists():
+        raise PramError(f'{p} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                        f'(nvcc, sm_100a). There is no CPU fallback.')
+    lib = C.CDLL(str(p))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def ptr(t: torch.Tensor | None):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def call(name: str, *args):
+    """Invoke an int-returning ABI function and raise on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.pram_error_string(rc).decode()
+        cuda = lib.pram_last_cuda_error().decode() if rc == -2 else ''
+        raise PramError(f'{name} failed: {msg} {cuda}')
+    return rc
+
+
+def launch_count() -> int:
+    return int(load().pram_launch_count())
+
+
+def require_cuda(t: torch.Tensor, what: str = 'tensor'):
+    if not t.is_cuda:
+        raise PramError(f'{what} must live on a CUDA device: pram_b200 has no CPU path '
+                        f'(the CPU oracle under oracle/ is test infrastructure only)')

@@ -1,0 +1,56 @@
+"""Build ``csrc/libpram_b200.so`` in-tree with nvcc for sm_100a (no JIT cache, no torch extension)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+CSRC = Path(__file__).resolve().parent / 'csrc'
+LIB = CSRC / 'libpram_b200.so'
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+              '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+
+
+def sources():
+    return sorted(CSRC.glob('*.cu'))
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh')) + list(CSRC.glob('*.h'))
+    return any(p.stat().st_mtime > t for p in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    objs = []
+    procs = []
+    bdir = CSRC / 'build'
+    bdir.mkdir(exist_ok=True)
+    for src in sources():
+        obj = bdir / (src.stem + '.o')
+        objs.append(obj)
+        cmd = [nvcc, *NVCC_FLAGS, '-c', str(src), '-o', str(obj)]
+        if verbose:
+            cmd.insert(1, '-Xptxas=-v')
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src.name}:\n{out}')
+    cmd = [nvcc, '-shared', '-o', str(LIB), *map(str, objs), '-lcuda']
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f'link failed:\n{r.stdout}')
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force=True, verbose=bool(os.environ.get('VERBOSE'))))

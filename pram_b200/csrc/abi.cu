@@ -1,0 +1,22 @@
+// Library-level entry points of libpram_b200.so.
+#include "common.cuh"
+
+unsigned long long g_pram_launches = 0;
+
+PRAM_API int pram_version(void) { return 100; }  // 0.1.0
+
+// Number of kernels this library has launched so far in this process (bench.py: gpu_launches).
+PRAM_API unsigned long long pram_launch_count(void) { return g_pram_launches; }
+
+PRAM_API const char* pram_error_string(int code) {
+    switch (code) {
+        case PRAM_OK: return "ok";
+        case PRAM_ERR_ARG: return "invalid argument";
+        case PRAM_ERR_CUDA: return "CUDA error";
+        case PRAM_ERR_WORKSPACE: return "workspace too small";
+        case PRAM_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return "unknown";
+    }
+}
+
+PRAM_API const char* pram_last_cuda_error(void) { return cudaGetErrorString(cudaGetLastError()); }

@@ -1,0 +1,44 @@
+// Shared device/host helpers for libpram_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+#define PRAM_OK 0
+#define PRAM_ERR_ARG (-1)
+#define PRAM_ERR_CUDA (-2)
+#define PRAM_ERR_WORKSPACE (-3)
+#define PRAM_ERR_UNSUPPORTED (-4)
+
+#define PRAM_API extern "C" __attribute__((visibility("default")))
+
+// Launch-counter: every kernel launch of this library goes through PRAM_LAUNCH so that
+// bench.py can report how many of OUR kernels ran inside the timed region (pram_launch_count()).
+extern unsigned long long g_pram_launches;
+
+#define PRAM_CHECK_LAUNCH()                                      \
+    do {                                                         \
+        ++g_pram_launches;                                       \
+        cudaError_t e__ = cudaPeekAtLastError();                 \
+        if (e__ != cudaSuccess) return PRAM_ERR_CUDA;            \
+    } while (0)
+
+#define PRAM_CUDA(call)                                          \
+    do {                                                         \
+        cudaError_t e__ = (call);                                \
+        if (e__ != cudaSuccess) return PRAM_ERR_CUDA;            \
+    } while (0)
+
+__host__ __device__ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

@@ -1,0 +1,523 @@
+// FP32 CUDA-core kernels: the exact-arithmetic path of the networks (and the on-device reference the
+// tcgen05 path is validated against).  NHWC activations, BN folded into weights/bias on the host.
+//   * conv_igemm_kernel : implicit-GEMM 3x3 / 1x1 convolution == Linear layer (H=1), fused
+//                         bias + residual + ReLU, strided input/output rows (writes straight into a
+//                         concat buffer)                         -> reference nets/sfd2.py:141-170,
+//                                                                   nn.Linear in segnetvit.py / gml.py
+//   * gconv3x3_kernel   : grouped 3x3 convolution, 32 groups x 8 channels (ResBlock.conv2,
+//                         reference nets/sfd2.py:101)
+//   * l2norm_rows       : channel L2 normalisation (F.normalize, reference nets/sfd2.py:333)
+//   * layernorm_gelu    : LayerNorm + exact (erf) GELU, reference nets/segnetvit.py:92-93
+//   * rotary_split      : de-interleaved qkv -> rotary(q), rotary(k), v in [B,h,N,64]
+//                         (reference nets/segnetvit.py:98-103)
+//   * attention_kernel  : softmax(QK^T * scale) V, flash-style (no N x N matrix in HBM), fp32,
+//                         optional per-key column mean of the attention (AdaGML, adagml.py:148)
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// implicit GEMM:  out[m][n] = act( sum_{tap,ci} in[pix(m,tap)][ci] * w[tap][ci][n] + bias[n] + res[m][n] )
+// ------------------------------------------------------------------------------------------
+constexpr int IG_BM = 128, IG_BN = 64, IG_BK = 16, IG_THREADS = 256;
+
+struct ConvParams {
+    const float* in; const float* w; const float* bias; const float* res; float* out;
+    int B, H, W, Cin, Ho, Wo, Cout, ksize, stride;
+    long long in_pix_stride;   // floats between consecutive input pixels (>= Cin)
+    long long out_pix_stride;  // floats between consecutive output pixels (>= Cout)
+    long long res_pix_stride;
+    int relu;
+    int w_layout;              // 0: w[tap][Cin][Cout]   1: w[Cout][Cin] (ksize 1; torch Linear layout)
+    long long in_batch_stride, w_batch_stride, out_batch_stride;  // blockIdx.z batching (bmm)
+};
+
+__global__ void __launch_bounds__(IG_THREADS) conv_igemm_kernel(ConvParams p) {
+    __shared__ float As[IG_BK][IG_BM + 4];
+    __shared__ float Bs[IG_BK][IG_BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, micro-tile 8 (m) x 4 (n)
+    p.in += blockIdx.z * p.in_batch_stride;
+    p.w += blockIdx.z * p.w_batch_stride;
+    p.out += blockIdx.z * p.out_batch_stride;
+    const long long M = (long long)p.B * p.Ho * p.Wo;
+    const long long m0 = (long long)blockIdx.x * IG_BM;
+    const int n0 = blockIdx.y * IG_BN;
+    const int pad = p.ksize / 2;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    // A-load assignment: 128 pixels x 16 channels -> thread handles pixel (tid>>1), channels (tid&1)*8..+8
+    const int a_m = tid >> 1, a_k = (tid & 1) * 8;
+    const long long am = m0 + a_m;
+    int ab = 0, aoy = 0, aox = 0;
+    const bool a_valid_m = am < M;
+    if (a_valid_m) {
+        ab = (int)(am / ((long long)p.Ho * p.Wo));
+        int rem = (int)(am - (long long)ab * p.Ho * p.Wo);
+        aoy = rem / p.Wo;
+        aox = rem - aoy * p.Wo;
+    }
+    // B-load assignment: 16 k x 64 n -> thread handles k = tid>>4, n = (tid&15)*4..+4
+    const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+    const bool vec_a = (p.Cin % 4 == 0) && (p.in_pix_stride % 4 == 0);
+    const bool vec_b = (p.Cout % 4 == 0);
+
+    const int taps = p.ksize * p.ksize;
+    for (int tap = 0; tap < taps; ++tap) {
+        const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
+        const int iy = aoy * p.stride + dy, ix = aox * p.stride + dx;
+        const bool pix_ok = a_valid_m && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        const float* ain = p.in + (((long long)ab * p.H + iy) * p.W + ix) * p.in_pix_stride;
+        const float* wt = p.w + (long long)tap * p.Cin * p.Cout;
+        for (int k0 = 0; k0 < p.Cin; k0 += IG_BK) {
+            // ---- stage A ----
+            float av[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) av[q] = 0.f;
+            if (pix_ok) {
+                int c = k0 + a_k;
+                if (vec_a && c + 8 <= p.Cin) {
+                    float4 v0 = *reinterpret_cast<const float4*>(ain + c);
+                    float4 v1 = *reinterpret_cast<const float4*>(ain + c + 4);
+                    av[0] = v0.x; av[1] = v0.y; av[2] = v0.z; av[3] = v0.w;
+                    av[4] = v1.x; av[5] = v1.y; av[6] = v1.z; av[7] = v1.w;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) if (c + q < p.Cin) av[q] = ain[c + q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) As[a_k + q][a_m] = av[q];
+            // ---- stage B ----
+            if (p.w_layout == 0) {
+                int k = k0 + b_k, n = n0 + b_n;
+                float bv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (k < p.Cin) {
+                    const float* wp = wt + (long long)k * p.Cout + n;
+                    if (vec_b && n + 4 <= p.Cout) {
+                        float4 v = *reinterpret_cast<const float4*>(wp);
+                        bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (n + q < p.Cout) bv[q] = wp[q];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) Bs[b_k][b_n + q] = bv[q];
+            } else {
+                // [Cout][Cin]: thread handles n = tid>>2, k = (tid&3)*4..+4 (contiguous along Cin)
+                const int n = n0 + (tid >> 2), kk = (tid & 3) * 4, k = k0 + kk;
+                float bv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (n < p.Cout) {
+                    const float* wp = p.w + (long long)n * p.Cin + k;
+                    if ((p.Cin % 4 == 0) && k + 4 <= p.Cin) {
+                        float4 v = *reinterpret_cast<const float4*>(wp);
+                        bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (k + q < p.Cin) bv[q] = wp[q];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) Bs[kk + q][tid >> 2] = bv[q];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < IG_BK; ++k) {
+                float a[8], b[4];
+                float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+                float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+                float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+                a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+                b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+    // ---- epilogue ----
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        long long m = m0 + ty * 8 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tx * 4 + j;
+            if (n >= p.Cout) continue;
+            float v = acc[i][j];
+            if (p.bias) v += p.bias[n];
+            if (p.res) v += p.res[m * p.res_pix_stride + n];
+            if (p.relu) v = fmaxf(v, 0.f);
+            p.out[m * p.out_pix_stride + n] = v;
+        }
+    }
+}
+
+PRAM_API int pram_conv_f32(const float* in, long long in_pix_stride, const float* w, const float* bias,
+                           const float* res, long long res_pix_stride, float* out,
+                           long long out_pix_stride, int B, int H, int W, int Cin, int Cout, int ksize,
+                           int stride, int relu, cudaStream_t stream) {
+    if (!in || !w || !out || B <= 0 || (ksize != 1 && ksize != 3) || (stride != 1 && stride != 2))
+        return PRAM_ERR_ARG;
+    ConvParams p;
+    p.in = in; p.w = w; p.bias = bias; p.res = res; p.out = out;
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.stride = stride;
+    const int pad = ksize / 2;
+    p.Ho = (H + 2 * pad - ksize) / stride + 1;
+    p.Wo = (W + 2 * pad - ksize) / stride + 1;
+    p.in_pix_stride = in_pix_stride; p.out_pix_stride = out_pix_stride; p.res_pix_stride = res_pix_stride;
+    p.relu = relu; p.w_layout = 0;
+    p.in_batch_stride = p.w_batch_stride = p.out_batch_stride = 0;
+    long long M = (long long)B * p.Ho * p.Wo;
+    dim3 grid(cdiv(M, IG_BM), cdiv(Cout, IG_BN));
+    conv_igemm_kernel<<<grid, IG_THREADS, 0, stream>>>(p);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+// out[z][m][n] = act( sum_k a[z][m][k] * w[z][n][k] + bias[n] + res[m][n] )   (torch Linear / bmm-NT)
+PRAM_API int pram_linear_f32(const float* a, long long lda, const float* w, const float* bias,
+                             const float* res, long long ldres, float* out, long long ldo, long long rows,
+                             int K, int N, int relu, int batch, long long a_batch_stride,
+                             long long w_batch_stride, long long out_batch_stride, cudaStream_t stream) {
+    if (!a || !w || !out || rows <= 0 || K <= 0 || N <= 0 || batch <= 0) return PRAM_ERR_ARG;
+    ConvParams p;
+    p.in = a; p.w = w; p.bias = bias; p.res = res; p.out = out;
+    p.B = 1; p.H = 1; p.W = (int)rows; p.Cin = K; p.Cout = N; p.ksize = 1; p.stride = 1;
+    p.Ho = 1; p.Wo = (int)rows;
+    p.in_pix_stride = lda; p.out_pix_stride = ldo; p.res_pix_stride = ldres;
+    p.relu = relu; p.w_layout = 1;
+    p.in_batch_stride = a_batch_stride; p.w_batch_stride = w_batch_stride; p.out_batch_stride = out_batch_stride;
+    dim3 grid(cdiv(rows, IG_BM), cdiv(N, IG_BN), batch);
+    conv_igemm_kernel<<<grid, IG_THREADS, 0, stream>>>(p);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// grouped 3x3 conv, G groups of 8 channels, stride 1, pad 1, + bias + ReLU.
+// lanes <-> groups (a warp reads one pixel's 256 channels as one 1 KB line), 4 consecutive output
+// pixels per thread so each shared-memory weight read feeds 4 FMAs.
+// weights in smem as [tap][ci][co][group].
+// ------------------------------------------------------------------------------------------
+constexpr int GC_PX = 4;
+__global__ void __launch_bounds__(256) gconv3x3_kernel(const float* __restrict__ in,
+                                                       const float* __restrict__ w,  // [9][8][8][G]
+                                                       const float* __restrict__ bias,
+                                                       float* __restrict__ out, int B, int H, int W,
+                                                       int G, int relu) {
+    extern __shared__ float ws[];
+    const int C = G * 8;
+    for (int i = threadIdx.x; i < 9 * 64 * G; i += blockDim.x) ws[i] = w[i];
+    __syncthreads();
+    const int g = threadIdx.x % G;
+    const int slot = threadIdx.x / G;            // which pixel-quad inside the block
+    const int quads_per_block = blockDim.x / G;  // 8 for G=32
+    const int wq = cdiv(W, GC_PX);
+    long long quad = (long long)blockIdx.x * quads_per_block + slot;
+    long long total = (long long)B * H * wq;
+    if (quad >= total) return;
+    const int b = (int)(quad / ((long long)H * wq));
+    const int rem = (int)(quad - (long long)b * H * wq);
+    const int y = rem / wq, x0 = (rem - y * wq) * GC_PX;
+    float acc[GC_PX][8];
+#pragma unroll
+    for (int p = 0; p < GC_PX; ++p)
+#pragma unroll
+        for (int co = 0; co < 8; ++co) acc[p][co] = 0.f;
+    for (int r = 0; r < 3; ++r) {
+        const int iy = y + r - 1;
+        if (iy < 0 || iy >= H) continue;
+        float v[GC_PX + 2][8];
+#pragma unroll
+        for (int q = 0; q < GC_PX + 2; ++q) {
+            const int ix = x0 + q - 1;
+            if (ix >= 0 && ix < W) {
+                const float* ip = in + (((long long)b * H + iy) * W + ix) * C + g * 8;
+                float4 a = *reinterpret_cast<const float4*>(ip);
+                float4 c = *reinterpret_cast<const float4*>(ip + 4);
+                v[q][0] = a.x; v[q][1] = a.y; v[q][2] = a.z; v[q][3] = a.w;
+                v[q][4] = c.x; v[q][5] = c.y; v[q][6] = c.z; v[q][7] = c.w;
+            } else {
+#pragma unroll
+                for (int ci = 0; ci < 8; ++ci) v[q][ci] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci)
+#pragma unroll
+                for (int co = 0; co < 8; ++co) {
+                    const float wv = ws[(((r * 3 + s) * 8 + ci) * 8 + co) * G + g];
+#pragma unroll
+                    for (int p = 0; p < GC_PX; ++p) acc[p][co] = fmaf(v[p + s][ci], wv, acc[p][co]);
+                }
+    }
+#pragma unroll
+    for (int p = 0; p < GC_PX; ++p) {
+        const int x = x0 + p;
+        if (x >= W) break;
+        float o[8];
+#pragma unroll
+        for (int co = 0; co < 8; ++co) {
+            float t = acc[p][co] + (bias ? bias[g * 8 + co] : 0.f);
+            o[co] = relu ? fmaxf(t, 0.f) : t;
+        }
+        float* op = out + (((long long)b * H + y) * W + x) * C + g * 8;
+        *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(op + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+PRAM_API int pram_gconv3x3_f32(const float* in, const float* w, const float* bias, float* out, int B,
+                               int H, int W, int groups, int relu, cudaStream_t stream) {
+    if (!in || !w || !out || groups != 32) return PRAM_ERR_UNSUPPORTED;
+    size_t smem = sizeof(float) * 9 * 64 * groups;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PRAM_CUDA(cudaFuncSetAttribute(gconv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        attr_set = true;
+    }
+    long long quads = (long long)B * H * cdiv(W, GC_PX);
+    int qpb = 256 / groups;
+    gconv3x3_kernel<<<cdiv(quads, qpb), 256, smem, stream>>>(in, w, bias, out, B, H, W, groups, relu);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// row-wise L2 normalisation (F.normalize over channels of an NHWC map), warp per row, in place ok
+// ------------------------------------------------------------------------------------------
+__global__ void l2norm_rows_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows,
+                                   int C) {
+    long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* p = in + row * C;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) { float v = p[c]; ss += v * v; }
+    float d = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+    for (int c = lane; c < C; c += 32) out[row * C + c] = p[c] / d;
+}
+
+PRAM_API int pram_l2norm_rows(const float* in, float* out, long long rows, int C, cudaStream_t stream) {
+    if (!in || !out) return PRAM_ERR_ARG;
+    l2norm_rows_kernel<<<cdiv(rows * 32, 256), 256, 0, stream>>>(in, out, rows, C);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (eps 1e-5, biased variance) + exact GELU, warp per row, in place ok
+// ------------------------------------------------------------------------------------------
+__global__ void layernorm_gelu_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float* __restrict__ out,
+                                      long long rows, int C, int gelu) {
+    long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* p = in + row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += p[c];
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+    for (int c = lane; c < C; c += 32) { float d = p[c] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) / C + 1e-5f);
+    for (int c = lane; c < C; c += 32) {
+        float v = (p[c] - mean) * rstd * gamma[c] + beta[c];
+        if (gelu) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+        out[row * C + c] = v;
+    }
+}
+
+PRAM_API int pram_layernorm_gelu(const float* in, const float* gamma, const float* beta, float* out,
+                                 long long rows, int C, int gelu, cudaStream_t stream) {
+    if (!in || !out || !gamma || !beta) return PRAM_ERR_ARG;
+    layernorm_gelu_kernel<<<cdiv(rows * 32, 256), 256, 0, stream>>>(in, gamma, beta, out, rows, C, gelu);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// qkv [tokens][3*H*64] laid out (q | k | v), each (head, dim) -- the host permutes the reference's
+// interleaved (head, dim, {q,k,v}) weight rows once at load time -- to q,k,v [B][H][N][64] with the
+// rotary embedding applied to q and k on adjacent pairs (2i,2i+1).
+// If cosb == nullptr no rotation is applied (cross attention: qk and v only re-laid out).
+// ------------------------------------------------------------------------------------------
+__global__ void rotary_split_kernel(const float* __restrict__ qkv, int nparts, int B, int N, int heads,
+                                    const float* __restrict__ cosb, const float* __restrict__ sinb,
+                                    float scale_qk, float* __restrict__ q, float* __restrict__ k,
+                                    float* __restrict__ v) {
+    // one thread per (token, part, head, pair)
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pairs = 32;
+    long long total = (long long)B * N * nparts * heads * pairs;
+    if (i >= total) return;
+    int pr = (int)(i % pairs);
+    int h = (int)((i / pairs) % heads);
+    int part = (int)((i / (pairs * heads)) % nparts);
+    long long t = i / ((long long)pairs * heads * nparts);
+    int b = (int)(t / N), n = (int)(t - (long long)b * N);
+    const float* src = qkv + t * (long long)(nparts * heads * 64) + (long long)part * heads * 64 + h * 64 + 2 * pr;
+    float x0 = src[0], x1 = src[1];
+    float* dst = (part == 0 ? q : (part == 1 ? k : v));
+    const bool is_v = (nparts == 3 && part == 2) || (nparts == 2 && part == 1);
+    if (nparts == 2 && part == 1) dst = v;
+    if (!is_v) {
+        if (cosb) {
+            float c = cosb[t * 32 + pr], s = sinb[t * 32 + pr];
+            float y0 = x0 * c + (-x1) * s;
+            float y1 = x1 * c + x0 * s;
+            x0 = y0; x1 = y1;
+        }
+        x0 *= scale_qk; x1 *= scale_qk;
+    }
+    float* o = dst + (((long long)b * heads + h) * N + n) * 64 + 2 * pr;
+    o[0] = x0; o[1] = x1;
+}
+
+PRAM_API int pram_rotary_split(const float* qkv, int nparts, int B, int N, int heads, const float* cosb,
+                               const float* sinb, float scale_qk, float* q, float* k, float* v,
+                               cudaStream_t stream) {
+    if (!qkv || !q || !v || (nparts != 2 && nparts != 3) || (nparts == 3 && !k)) return PRAM_ERR_ARG;
+    long long total = (long long)B * N * nparts * heads * 32;
+    rotary_split_kernel<<<cdiv(total, 256), 256, 0, stream>>>(qkv, nparts, B, N, heads, cosb, sinb, scale_qk,
+                                                             q, k, v);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// attention: out[b][n][h*64+d] = sum_j softmax_j(q_n . k_j * scale) v_j[d]   (head dim 64)
+// CTA = 64 queries x 1 (b,h); K/V streamed through shared memory in 64-row tiles; online softmax.
+// thread layout: 256 threads = 64 queries x 4 lanes; each lane owns 16 of the 64 dims.
+// Two passes when colmean != nullptr (needs the final row max / sum to form normalised weights).
+// ------------------------------------------------------------------------------------------
+constexpr int AT_BQ = 64, AT_BK = 32;
+__global__ void __launch_bounds__(256) attention_kernel(
+    const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int B, int heads,
+    int Nq, int Nk, float scale, float* __restrict__ out, int out_stride, float* __restrict__ colmean) {
+    __shared__ float Ks[AT_BK][64 + 1];
+    __shared__ float Vs[AT_BK][64 + 1];
+    __shared__ float Ps[AT_BQ][AT_BK + 1];
+    const int bh = blockIdx.y, b = bh / heads, h = bh - b * heads;
+    const int q0 = blockIdx.x * AT_BQ;
+    const int tid = threadIdx.x;
+    const int qi = tid >> 2, part = tid & 3;  // query row in tile, 16-dim slice
+    const int qn = q0 + qi;
+    const float* Qb = Q + ((long long)bh * Nq) * 64;
+    const float* Kb = K + ((long long)bh * Nk) * 64;
+    const float* Vb = V + ((long long)bh * Nk) * 64;
+    float qreg[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) qreg[d] = (qn < Nq) ? Qb[(long long)qn * 64 + part * 16 + d] * scale : 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    float acc[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) acc[d] = 0.f;
+    for (int k0 = 0; k0 < Nk; k0 += AT_BK) {
+        __syncthreads();
+        for (int i = tid; i < AT_BK * 16; i += 256) {
+            int r = i >> 4, c4 = (i & 15) * 4;
+            float4 kv = make_float4(0, 0, 0, 0), vv = make_float4(0, 0, 0, 0);
+            if (k0 + r < Nk) {
+                kv = *reinterpret_cast<const float4*>(Kb + (long long)(k0 + r) * 64 + c4);
+                vv = *reinterpret_cast<const float4*>(Vb + (long long)(k0 + r) * 64 + c4);
+            }
+            Ks[r][c4] = kv.x; Ks[r][c4 + 1] = kv.y; Ks[r][c4 + 2] = kv.z; Ks[r][c4 + 3] = kv.w;
+            Vs[r][c4] = vv.x; Vs[r][c4 + 1] = vv.y; Vs[r][c4 + 2] = vv.z; Vs[r][c4 + 3] = vv.w;
+        }
+        __syncthreads();
+        // scores for this query row against 64 keys: each of the 4 lanes does a partial dot, then
+        // quad-reduce.  Lane `part` keeps keys j with j%4==part for the softmax bookkeeping.
+        float tile_max = -INFINITY;
+        for (int j = 0; j < AT_BK; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) s = fmaf(qreg[d], Ks[j][part * 16 + d], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (k0 + j >= Nk) s = -INFINITY;
+            if ((j & 3) == part) Ps[qi][j] = s;  // the quad shares row qi; lane `part` owns j%4==part
+            tile_max = fmaxf(tile_max, s);
+        }
+        __syncwarp();
+        const float m_new = fmaxf(m_run, tile_max);
+        const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
+        float psum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < AT_BK / 4; ++jj) {
+            const float sv = Ps[qi][jj * 4 + part];
+            const float pv = (sv == -INFINITY) ? 0.f : expf(sv - m_new);
+            Ps[qi][jj * 4 + part] = pv;
+            psum += pv;
+        }
+        psum += __shfl_xor_sync(0xffffffffu, psum, 1);
+        psum += __shfl_xor_sync(0xffffffffu, psum, 2);
+        l_run = l_run * corr + psum;
+        m_run = m_new;
+        __syncwarp();
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[d] *= corr;
+        for (int j = 0; j < AT_BK; ++j) {
+            const float pv = Ps[qi][j];
+#pragma unroll
+            for (int d = 0; d < 16; ++d) acc[d] = fmaf(pv, Vs[j][part * 16 + d], acc[d]);
+        }
+    }
+    if (qn < Nq) {
+        float* o = out + ((long long)b * Nq + qn) * out_stride + h * 64 + part * 16;
+        const float inv = 1.f / l_run;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) o[d] = acc[d] * inv;
+    }
+    if (colmean) {
+        // second sweep: normalised attention weights, summed over this tile's queries and scaled by
+        // 1/(heads*Nq); accumulated over (head, query tile) with atomics.
+        const float inv = (qn < Nq) ? 1.f / l_run : 0.f;
+        const float wscale = 1.f / ((float)heads * (float)Nq);
+        for (int k0 = 0; k0 < Nk; k0 += AT_BK) {
+            __syncthreads();
+            for (int i = tid; i < AT_BK * 16; i += 256) {
+                int r = i >> 4, c4 = (i & 15) * 4;
+                float4 kv = make_float4(0, 0, 0, 0);
+                if (k0 + r < Nk) kv = *reinterpret_cast<const float4*>(Kb + (long long)(k0 + r) * 64 + c4);
+                Ks[r][c4] = kv.x; Ks[r][c4 + 1] = kv.y; Ks[r][c4 + 2] = kv.z; Ks[r][c4 + 3] = kv.w;
+            }
+            __syncthreads();
+            for (int j = 0; j < AT_BK; ++j) {
+                float s = 0.f;
+#pragma unroll
+                for (int d = 0; d < 16; ++d) s = fmaf(qreg[d], Ks[j][part * 16 + d], s);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                if (part == 0) Ps[qi][j] = (qn < Nq && k0 + j < Nk) ? expf(s - m_run) * inv : 0.f;
+            }
+            __syncthreads();
+            if (tid < AT_BK && k0 + tid < Nk) {
+                float cs = 0.f;
+                for (int r = 0; r < AT_BQ; ++r) cs += Ps[r][tid];
+                atomicAdd(&colmean[(long long)b * Nk + k0 + tid], cs * wscale);
+            }
+        }
+    }
+}
+
+PRAM_API int pram_attention_f32(const float* Q, const float* K, const float* V, int B, int heads, int Nq,
+                                int Nk, float scale, float* out, int out_stride, float* colmean,
+                                cudaStream_t stream) {
+    if (!Q || !K || !V || !out || B <= 0 || Nq <= 0 || Nk <= 0) return PRAM_ERR_ARG;
+    if (colmean) PRAM_CUDA(cudaMemsetAsync(colmean, 0, sizeof(float) * (size_t)B * Nk, stream));
+    dim3 grid(cdiv(Nq, AT_BQ), B * heads);
+    attention_kernel<<<grid, 256, 0, stream>>>(Q, K, V, B, heads, Nq, Nk, scale, out, out_stride, colmean);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}

@@ -1,0 +1,272 @@
+// K15 / K16 of SURVEY.md section 2b: dustbin-augmented probability-domain Sinkhorn + mutual-arg-max match
+// extraction.  Replaces reference nets/gml.py:27-46 (sinkhorn / sink_algorithm, ~125 launches each
+// streaming an M x N temporary) and nets/gml.py:304-319 (compute_matches, ~13 launches) with ONE
+// launch: a thread-block cluster per (M+1) x (N+1) problem.
+//
+//   p = softmax_rows([dist, bin; bin, bin])                       written once to the workspace
+//   20 x { u_i = r_i / (sum_j p_ij v_j + 1e-8) ;  v_j = c_j / (sum_i p_ij u_i + 1e-8) }
+//        -> ONE sweep over p per iteration: a warp finishes row i's dot product, gets u_i, and
+//           immediately accumulates p_ij * u_i into its register-resident column partials
+//   P_ij = (p_ij * u_i) * v_j ; row / column arg-max over the inner M x N ; mutual check ; threshold
+//
+// The rows of p are split across the G CTAs of the cluster; column partials are reduced in a fixed
+// order (warp order inside a CTA, CTA-rank order across the cluster through distributed shared
+// memory), so results are bit-reproducible run to run.  u, v, r, c never touch HBM.
+// Same algebra and eps placement as the reference (probability domain, eps inside the divisor).
+#include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+constexpr int SK_MAXG = 8;
+
+template <int NV, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
+    const float* __restrict__ dist, int M, int N, const float* __restrict__ bin_ptr, int iters,
+    float th, float* __restrict__ pws, int ldp, long long* __restrict__ matches0,
+    long long* __restrict__ matches1, float* __restrict__ mscores0, float* __restrict__ mscores1,
+    int* __restrict__ idx0_ws, int* __restrict__ idx1_ws, float* __restrict__ max0_ws, int G) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) float smem[];
+    const int NC = N + 1, MR = M + 1;
+    float* v_s = smem;                // [ldp]   column scaling, replicated in every CTA
+    float* col_s = smem + ldp;        // [ldp]   this CTA's partial column sums
+    float* u_s = smem + 2 * ldp;      // [rows_local]
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.y;
+    const int rows_per = (MR + G - 1) / G;
+    const int r0 = min(rank * rows_per, MR), r1 = min(r0 + rows_per, MR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float bin = *bin_ptr;
+    const float* D = dist + (long long)b * M * N;
+    float* P = pws + (long long)b * MR * ldp;
+    const float eps = 1e-8f;
+
+    // ---- phase 0: p = softmax over each augmented row ----
+    for (int i = r0 + warp; i < r1; i += WARPS) {
+        float z[NV * 4];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int j = k * 128 + lane * 4 + q;
+                float val = -INFINITY;
+                if (j < NC) val = (i < M && j < N) ? D[(long long)i * N + j] : bin;
+                z[k * 4 + q] = val;
+                mx = fmaxf(mx, val);
+            }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV * 4; ++k) {
+            z[k] = (z[k] == -INFINITY) ? 0.f : expf(z[k] - mx);
+            sum += z[k];
+        }
+        sum = warp_sum(sum);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            int j = k * 128 + lane * 4;
+            if (j < ldp)
+                *reinterpret_cast<float4*>(P + (long long)i * ldp + j) =
+                    make_float4(z[k * 4] / sum, z[k * 4 + 1] / sum, z[k * 4 + 2] / sum, z[k * 4 + 3] / sum);
+        }
+    }
+    for (int j = threadIdx.x; j < ldp; j += WARPS * 32) v_s[j] = (j < NC) ? 1.f : 0.f;
+    __syncthreads();
+
+    const int chunk = (ldp / 4 + G - 1) / G * 4;  // columns reduced by each rank (multiple of 4)
+    // ---- Sinkhorn iterations ----
+    for (int it = 0; it < iters; ++it) {
+        float4 cp[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) cp[k] = make_float4(0, 0, 0, 0);
+        for (int i = r0 + warp; i < r1; i += WARPS) {
+            constexpr bool kCacheRow = (NV <= 17);  // wider rows are re-read (L1-resident) instead
+            float4 pr[kCacheRow ? NV : 1];
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                int j = k * 128 + lane * 4;
+                float4 pv = make_float4(0, 0, 0, 0);
+                if (j < ldp) {
+                    pv = *reinterpret_cast<const float4*>(P + (long long)i * ldp + j);
+                    float4 vv = *reinterpret_cast<const float4*>(v_s + j);
+                    s += pv.x * vv.x + pv.y * vv.y + pv.z * vv.z + pv.w * vv.w;
+                }
+                if (kCacheRow) pr[kCacheRow ? k : 0] = pv;
+            }
+            s = warp_sum(s);
+            const float ri = (i == M) ? (float)MR : 1.f;
+            const float ui = ri / (s + eps);
+            if (lane == 0) u_s[i - r0] = ui;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                float4 pv;
+                if (kCacheRow) {
+                    pv = pr[kCacheRow ? k : 0];
+                } else {
+                    int j = k * 128 + lane * 4;
+                    pv = (j < ldp) ? *reinterpret_cast<const float4*>(P + (long long)i * ldp + j)
+                                   : make_float4(0, 0, 0, 0);
+                }
+                cp[k].x += pv.x * ui; cp[k].y += pv.y * ui;
+                cp[k].z += pv.z * ui; cp[k].w += pv.w * ui;
+            }
+        }
+        // fixed-order reduction of the per-warp partials into col_s
+        for (int w = 0; w < WARPS; ++w) {
+            if (warp == w) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    int j = k * 128 + lane * 4;
+                    if (j < ldp) {
+                        float4* d = reinterpret_cast<float4*>(col_s + j);
+                        if (w == 0) *d = cp[k];
+                        else { float4 o = *d; o.x += cp[k].x; o.y += cp[k].y; o.z += cp[k].z; o.w += cp[k].w; *d = o; }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        cluster.sync();
+        // rank-ordered reduction of this rank's column chunk over all CTAs, then broadcast v
+        {
+            const int c0 = rank * chunk, c1 = min(c0 + chunk, ldp);
+            for (int j = c0 + threadIdx.x; j < c1; j += WARPS * 32) {
+                float s = 0.f;
+                for (int g = 0; g < G; ++g) s += cluster.map_shared_rank(col_s, g)[j];
+                const float cj = (j == N) ? (float)NC : 1.f;
+                const float vj = (j < NC) ? cj / (s + eps) : 0.f;
+                for (int g = 0; g < G; ++g) cluster.map_shared_rank(v_s, g)[j] = vj;
+            }
+        }
+        cluster.sync();
+    }
+
+    // ---- final scaling: P = (p*u)*v, row arg-max over j < N for rows i < M; P written back ----
+    for (int i = r0 + warp; i < r1; i += WARPS) {
+        const float ui = (iters > 0) ? u_s[i - r0] : 1.f;
+        float best = -1.f;
+        int bj = 0;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            int j = k * 128 + lane * 4;
+            if (j < ldp) {
+                float4 pv = *reinterpret_cast<const float4*>(P + (long long)i * ldp + j);
+                float4 vv = *reinterpret_cast<const float4*>(v_s + j);
+                pv.x = (pv.x * ui) * vv.x; pv.y = (pv.y * ui) * vv.y;
+                pv.z = (pv.z * ui) * vv.z; pv.w = (pv.w * ui) * vv.w;
+                *reinterpret_cast<float4*>(P + (long long)i * ldp + j) = pv;
+                if (j < N && pv.x > best) { best = pv.x; bj = j; }
+                if (j + 1 < N && pv.y > best) { best = pv.y; bj = j + 1; }
+                if (j + 2 < N && pv.z > best) { best = pv.z; bj = j + 2; }
+                if (j + 3 < N && pv.w > best) { best = pv.w; bj = j + 3; }
+            }
+        }
+        // warp arg-max, first index wins ties
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (ob > best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+        }
+        if (lane == 0 && i < M) { idx0_ws[(long long)b * M + i] = bj; max0_ws[(long long)b * M + i] = best; }
+    }
+    __threadfence();
+    cluster.sync();
+    // ---- column arg-max over i < M for this rank's columns j < N ----
+    {
+        const int cols_per = (N + G - 1) / G;
+        const int c0 = rank * cols_per, c1 = min(c0 + cols_per, N);
+        for (int j = c0 + threadIdx.x; j < c1; j += WARPS * 32) {
+            float best = -1.f;
+            int bi = 0;
+            for (int i = 0; i < M; ++i) {
+                float pv = P[(long long)i * ldp + j];
+                if (pv > best) { best = pv; bi = i; }
+            }
+            idx1_ws[(long long)b * N + j] = bi;
+        }
+    }
+    __threadfence();
+    cluster.sync();
+    // ---- mutual check + threshold (reference nets/gml.py:304-319) ----
+    const int* i0 = idx0_ws + (long long)b * M;
+    const int* i1 = idx1_ws + (long long)b * N;
+    const float* m0 = max0_ws + (long long)b * M;
+    const int gthreads = G * WARPS * 32, gtid = rank * WARPS * 32 + threadIdx.x;
+    for (int i = gtid; i < M; i += gthreads) {
+        const int j = i0[i];
+        const bool mutual = (i1[j] == i);
+        const float s0 = mutual ? m0[i] : 0.f;
+        matches0[(long long)b * M + i] = (mutual && s0 > th) ? (long long)j : -1ll;
+        mscores0[(long long)b * M + i] = s0;
+    }
+    for (int j = gtid; j < N; j += gthreads) {
+        const int i = i1[j];
+        const bool mutual1 = (i0[i] == j);
+        // mscores0[i] recomputed locally: s0_i = (i1[i0[i]] == i) ? max0[i] : 0
+        const bool mutual0_i = (i1[i0[i]] == i);
+        const float s0_i = mutual0_i ? m0[i] : 0.f;
+        const bool valid0_i = mutual0_i && s0_i > th;
+        if (matches1) matches1[(long long)b * N + j] = (mutual1 && valid0_i) ? (long long)i : -1ll;
+        if (mscores1) mscores1[(long long)b * N + j] = mutual1 ? s0_i : 0.f;
+    }
+}
+
+template <int NV, int WARPS>
+static int launch_sinkhorn(const float* dist, int B, int M, int N, const float* bin, int iters, float th,
+                           float* pws, int ldp, long long* m0, long long* m1, float* s0, float* s1,
+                           int* idx0, int* idx1, float* max0, int G, cudaStream_t stream) {
+    auto kern = sinkhorn_match_kernel<NV, WARPS>;
+    const int rows_per = (M + 1 + G - 1) / G;
+    size_t smem = sizeof(float) * (2 * (size_t)ldp + rows_per);
+    PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G, B, 1);
+    cfg.blockDim = dim3(WARPS * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PRAM_CUDA(cudaLaunchKernelEx(&cfg, kern, dist, M, N, bin, iters, th, pws, ldp, m0, m1, s0, s1, idx0,
+                                 idx1, max0, G));
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+// workspace: pws  float [B][(M+1)][ldp], ldp = round_up(N+1, 4)   (holds P on return)
+//            iws  int   [B][M + N] , fws float [B][M]
+PRAM_API long long pram_sinkhorn_workspace_floats(int B, int M, int N) {
+    long long ldp = (N + 1 + 3) / 4 * 4;
+    return (long long)B * (M + 1) * ldp;
+}
+
+PRAM_API int pram_sinkhorn_match(const float* dist, int B, int M, int N, const float* bin_score, int iters,
+                                 float threshold, float* pws, int* iws, float* fws, long long* matches0,
+                                 long long* matches1, float* mscores0, float* mscores1, int cluster,
+                                 cudaStream_t stream) {
+    if (!dist || !bin_score || !pws || !iws || !fws || !matches0 || !mscores0 || B <= 0 || M <= 0 || N <= 0)
+        return PRAM_ERR_ARG;
+    int G = cluster <= 0 ? SK_MAXG : cluster;
+    if (G > SK_MAXG || (G & (G - 1))) return PRAM_ERR_ARG;
+    const int ldp = (N + 1 + 3) / 4 * 4;
+    int* idx0 = iws;
+    int* idx1 = iws + (long long)B * M;
+    const int nv = (ldp + 127) / 128;
+    if (nv <= 9)
+        return launch_sinkhorn<9, 16>(dist, B, M, N, bin_score, iters, threshold, pws, ldp, matches0, matches1,
+                                      mscores0, mscores1, idx0, idx1, fws, G, stream);
+    if (nv <= 17)
+        return launch_sinkhorn<17, 8>(dist, B, M, N, bin_score, iters, threshold, pws, ldp, matches0, matches1,
+                                       mscores0, mscores1, idx0, idx1, fws, G, stream);
+    if (nv <= 33)
+        return launch_sinkhorn<33, 8>(dist, B, M, N, bin_score, iters, threshold, pws, ldp, matches0, matches1,
+                                      mscores0, mscores1, idx0, idx1, fws, G, stream);
+    return PRAM_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,316 @@
+"""B200-native SFD2 feature operator -- drop-in for reference ``nets/sfd2.py``.
+
+Same class name, constructor, state-dict key schema (``load_state_dict(strict=True)`` of the shipped
+checkpoint works) and method contracts as the reference:
+
+* ``ResNet4x.extract_local_global(data, config)``  reference nets/sfd2.py:269-346
+* ``ResNet4x.sample(score_map, semi_descs, kpts, s, norm_desc)``  nets/sfd2.py:348-369
+* ``ResNet4x.det(x)`` / ``ResNet4x.forward(batch)``  nets/sfd2.py:172-233
+* ``extract_sfd2_return(model, img, ...)``  nets/sfd2.py:386-589
+* ``load_sfd2(weight_path)``  nets/sfd2.py:592-596
+
+The ``nn.Module`` containers below exist only to own the parameters under the reference's names; no
+torch operator runs in the forward path.  Inference repacks the weights once (BatchNorm folded into
+the preceding convolution, NHWC / tap-major layouts) and then calls hand-written sm_100a kernels
+through the C ABI (``include/pram_b200.h``).  Activations are NHWC on the device; the NCHW tensors the
+reference API promises are returned as channels-last *views* (same shape, same values).
+There is no CPU path: tensors must be CUDA tensors.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+
+RGB_mean = [0.485, 0.456, 0.406]
+RGB_std = [0.229, 0.224, 0.225]
+
+
+def _unit(cin: int, cout: int, stride: int = 1) -> nn.Sequential:
+    # parameter holder for conv3x3 + BN (+ReLU); indices 0/1 give the reference's key names
+    return nn.Sequential(nn.Conv2d(cin, cout, 3, stride, 1), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+
+class ResBlock(nn.Module):
+    """Parameter holder with the reference's key names (nets/sfd2.py:94-105)."""
+
+    def __init__(self, inplanes: int, outplanes: int, groups: int = 32):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, outplanes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(outplanes)
+        self.conv2 = nn.Conv2d(outplanes, outplanes, 3, 1, 1, groups=groups, bias=False)
+        self.bn2 = nn.BatchNorm2d(outplanes)
+        self.conv3 = nn.Conv2d(outplanes, outplanes, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(outplanes)
+
+
+def _fold(conv_w: torch.Tensor, conv_b: Optional[torch.Tensor], bn: Optional[nn.BatchNorm2d]):
+    """Fold eval-mode BatchNorm into the convolution (float64 on the host, once)."""
+    w = conv_w.detach().double()
+    b = conv_b.detach().double() if conv_b is not None else torch.zeros(w.shape[0], dtype=torch.float64,
+                                                                         device=w.device)
+    if bn is not None:
+        g = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        w = w * g.view(-1, 1, 1, 1)
+        b = (b - bn.running_mean.detach().double()) * g + bn.bias.detach().double()
+    return w, b
+
+
+def _tapmajor(w: torch.Tensor) -> torch.Tensor:
+    """[Cout,Cin,kh,kw] -> [kh*kw, Cin, Cout] fp32 contiguous."""
+    co, ci, kh, kw = w.shape
+    return w.permute(2, 3, 1, 0).reshape(kh * kw, ci, co).float().contiguous()
+
+
+class ResNet4x(nn.Module):
+    default_config = {
+        'conf_th': 0.005,
+        'remove_borders': 4,
+        'min_keypoints': 128,
+        'max_keypoints': 4096,
+    }
+
+    def __init__(self, inputdim: int = 3, outdim: int = 128, desc_compressor=None):
+        super().__init__()
+        self.outdim = outdim
+        self.desc_compressor = desc_compressor
+        self.conv1a = _unit(inputdim, 64)
+        self.conv1b = _unit(64, 64, 2)
+        self.conv2a = _unit(64, 128)
+        self.conv2b = _unit(128, 128, 2)
+        self.conv3a = _unit(128, 256)
+        self.conv3b = _unit(256, 256)
+        self.conv4 = nn.Sequential(ResBlock(256, 256), ResBlock(256, 256), ResBlock(256, 256))
+        self.convPa = nn.Sequential(nn.Conv2d(256, 256, 3, 2, 1), nn.BatchNorm2d(256), nn.ReLU(inplace=True),
+                                    nn.Conv2d(256, 256, 3, 1, 1))
+        self.convDa = nn.Sequential(nn.Conv2d(256, 256, 3, 1, 1), nn.BatchNorm2d(256), nn.ReLU(inplace=True),
+                                    nn.Conv2d(256, 256, 3, 1, 1))
+        self.convPb = nn.Conv2d(256, 65, 1)
+        self.convDb = nn.Conv2d(256, outdim, 1)
+        self._packed: Optional[Dict[str, torch.Tensor]] = None
+        self.eval()
+
+    # -- weight repacking ---------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._packed = None
+        return super().load_state_dict(*a, **k)
+
+    def prepare(self) -> Dict[str, torch.Tensor]:
+        """One-time repack: BN folded (fp64), tap-major [taps,Cin,Cout] fp32; grouped conv as
+        [tap][ci][co][group]."""
+        if self._packed is not None:
+            return self._packed
+        dev = self.convPb.weight.device
+        if dev.type != 'cuda':
+            raise _lib.PramError('ResNet4x must be moved to a CUDA device (.cuda()) before inference: '
+                                 'pram_b200 has no CPU path')
+        pk: Dict[str, torch.Tensor] = {}
+
+        def put(name, w, b):
+            pk[name + '.w'] = _tapmajor(w).to(dev)
+            pk[name + '.b'] = b.float().contiguous().to(dev)
+
+        for name in ('conv1a', 'conv1b', 'conv2a', 'conv2b', 'conv3a', 'conv3b'):
+            seq = getattr(self, name)
+            put(name, *_fold(seq[0].weight, seq[0].bias, seq[1]))
+        for i, blk in enumerate(self.conv4):
+            put(f'conv4.{i}.c1', *_fold(blk.conv1.weight, None, blk.bn1))
+            w2, b2 = _fold(blk.conv2.weight, None, blk.bn2)  # [256, 8, 3, 3]
+            g = 32
+            w2 = w2.view(g, 8, 8, 3, 3)  # [group, co, ci, kh, kw]
+            pk[f'conv4.{i}.c2.w'] = w2.permute(3, 4, 2, 1, 0).reshape(9, 8, 8, g).float().contiguous().to(dev)
+            pk[f'conv4.{i}.c2.b'] = b2.float().contiguous().to(dev)
+            put(f'conv4.{i}.c3', *_fold(blk.conv3.weight, None, blk.bn3))
+        for head in ('convPa', 'convDa'):
+            seq = getattr(self, head)
+            put(head + '.0', *_fold(seq[0].weight, seq[0].bias, seq[1]))
+            put(head + '.3', *_fold(seq[3].weight, seq[3].bias, None))
+        put('convPb', *_fold(self.convPb.weight, self.convPb.bias, None))
+        put('convDb', *_fold(self.convDb.weight, self.convDb.bias, None))
+        self._packed = pk
+        return pk
+
+    # -- the conv stack -----------------------------------------------------------------------
+    def _trunk(self, image: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """image [B,3,H,W] (normalised) -> NHWC fp32 maps.  K1-K4 of SURVEY.md section 2b."""
+        _lib.require_cuda(image, 'image')
+        pk = self.prepare()
+        x = image.float().permute(0, 2, 3, 1).contiguous()  # NHWC, 3 channels (layout plumbing only)
+        c = ops.conv_f32
+        o1a = c(x, pk['conv1a.w'], pk['conv1a.b'], 3, 1, True)
+        o1b = c(o1a, pk['conv1b.w'], pk['conv1b.b'], 3, 2, True)
+        o2a = c(o1b, pk['conv2a.w'], pk['conv2a.b'], 3, 1, True)
+        o2b = c(o2a, pk['conv2b.w'], pk['conv2b.b'], 3, 2, True)
+        o3a = c(o2b, pk['conv3a.w'], pk['conv3a.b'], 3, 1, True)
+        o3b = c(o3a, pk['conv3b.w'], pk['conv3b.b'], 3, 1, True)
+        o4 = o3b
+        for i in range(3):
+            t = c(o4, pk[f'conv4.{i}.c1.w'], pk[f'conv4.{i}.c1.b'], 1, 1, True)
+            t = ops.gconv3x3_f32(t, pk[f'conv4.{i}.c2.w'], pk[f'conv4.{i}.c2.b'], True)
+            o4 = c(t, pk[f'conv4.{i}.c3.w'], pk[f'conv4.{i}.c3.b'], 1, 1, True, res=o4)
+        p = c(o4, pk['convPa.0.w'], pk['convPa.0.b'], 3, 2, True)
+        p = c(p, pk['convPa.3.w'], pk['convPa.3.b'], 3, 1, False)
+        logits = c(p, pk['convPb.w'], pk['convPb.b'], 1, 1, False)
+        d = c(o4, pk['convDa.0.w'], pk['convDa.0.b'], 3, 1, True)
+        d = c(d, pk['convDa.3.w'], pk['convDa.3.b'], 3, 1, False)
+        desc = c(d, pk['convDb.w'], pk['convDb.b'], 1, 1, False)
+        ops.l2norm_rows_(desc, desc.shape[-1])
+        return {'out1b': o1b, 'out2b': o2b, 'out3b': o3b, 'out4': o4, 'logits': logits, 'desc': desc}
+
+    @staticmethod
+    def _nchw(x_nhwc: torch.Tensor) -> torch.Tensor:
+        return x_nhwc.permute(0, 3, 1, 2)  # channels-last view with the reference's NCHW shape
+
+    # -- reference API ------------------------------------------------------------------------
+    @torch.no_grad()
+    def det(self, x: torch.Tensor):
+        t = self._trunk(x)
+        return ops.score_map(t['logits']), self._nchw(t['desc'])
+
+    @torch.no_grad()
+    def forward(self, batch: dict) -> dict:
+        t = self._trunk(batch['image'])
+        logits = self._nchw(t['logits'])
+        semi = torch.softmax(logits, dim=1)[:, :-1]  # training-time convenience output only
+        return {'dense_features': self._nchw(t['desc']), 'scores': ops.score_map(t['logits']),
+                'logits': logits, 'semi_map': semi}
+
+    extract_patches = forward
+
+    @torch.no_grad()
+    def extract_local_global(self, data: dict, config: Optional[dict] = None) -> dict:
+        cfg = {**self.default_config, **(config or {})}
+        out = self.extract_batched(data['image'], cfg)
+        n = out['num_keypoints'].tolist()  # the only host sync of the feature stage
+        b = len(n)
+        if any(c > out['cand_cap'] for c in out['cand_count'].tolist()):
+            # plateau image: more NMS survivors than the candidate buffer -- redo with a full buffer
+            out = self.extract_batched(data['image'], cfg, cap=data['image'].shape[-1] * data['image'].shape[-2])
+            n = out['num_keypoints'].tolist()
+        return {
+            'score_map': out['score_map'],
+            'desc_map': self._nchw(out['desc_map_nhwc']),
+            'mid_features': self._nchw(out['mid_features_nhwc']),
+            'global_descriptors': [self._nchw(v) for v in out['global_nhwc']],
+            'keypoints': [out['keypoints'][i, :n[i]] for i in range(b)],
+            'scores': tuple(out['scores'][i, :n[i]] for i in range(b)),
+            'descriptors': [out['descriptors'][i, :n[i]].t() for i in range(b)],  # [128, n] views
+        }
+
+    @torch.no_grad()
+    def extract_batched(self, image: torch.Tensor, cfg: Optional[dict] = None, cap: Optional[int] = None) -> dict:
+        """Device-resident, sync-free form of ``extract_local_global`` (padded [B,K,...] outputs +
+        per-frame counts); the frame-parallel runner consumes this directly."""
+        cfg = {**self.default_config, **(cfg or {})}
+        b, _, ih, iw = image.shape
+        t = self._trunk(image)
+        score = ops.score_map(t['logits'], ih, iw)
+        kpts, scs, n, cand_count = ops.detect_keypoints(score, cfg['conf_th'], cfg['min_keypoints'],
+                                                        cfg['max_keypoints'], cfg['remove_borders'], radius=4,
+                                                        cap=cap)
+        desc = ops.sample_features(t['desc'], kpts, n, 4, True)
+        return {'score_map': score, 'desc_map_nhwc': t['desc'], 'mid_features_nhwc': t['out4'],
+                'global_nhwc': [t['out1b'], t['out2b'], t['out3b'], t['out4']],
+                'keypoints': kpts, 'scores': scs, 'descriptors': desc, 'num_keypoints': n,
+                'cand_count': cand_count, 'cand_cap': cap if cap is not None else 1 << 30, 'logits': t['logits']}
+
+    @torch.no_grad()
+    def sample(self, score_map: torch.Tensor, semi_descs: torch.Tensor, kpts: torch.Tensor, s: int = 4,
+               norm_desc: bool = True):
+        """(scores [n], descriptors [C,n]); reference nets/sfd2.py:348-369."""
+        _lib.require_cuda(semi_descs, 'semi_descs')
+        fm = semi_descs.permute(0, 2, 3, 1)
+        if not fm.is_contiguous() or fm.dtype != torch.float32:
+            fm = fm.float().contiguous()
+        k = kpts.reshape(1, -1, 2).float().contiguous()
+        d = ops.sample_features(fm[:1] if fm.shape[0] != 1 else fm, k, None, s, norm_desc)
+        sc = ops.gather_scores(score_map[:1], k, None)
+        return sc[0], d[0].t()
+
+
+class DescriptorCompressor(nn.Module):
+    """Parameter holder for the optional 1x1 Conv1d compressor (reference nets/sfd2.py:372-383); not on
+    the hot path (``desc_compressor=None`` everywhere the reference constructs ResNet4x)."""
+
+    def __init__(self, inputdim: int, outdim: int):
+        super().__init__()
+        self.inputdim, self.outdim = inputdim, outdim
+        self.conv = nn.Conv1d(inputdim, outdim, 1)
+
+
+def extract_sfd2_return(model: ResNet4x, img: torch.Tensor, conf_th: float = 0.001, mask=None, topK: int = -1,
+                        min_keypoints: int = 0, **kwargs):
+    """Offline-export variant (reference nets/sfd2.py:386-589): NMS radius 3, strict ``>`` threshold,
+    score-descending order, border 4, sampling with x/(w/2)-1, float64 numpy outputs.
+    ``img``: [1,3,H,W] (or [3,H,W]) RGB in [0,1], not normalised.  ``mask`` is not supported."""
+    if mask is not None:
+        raise NotImplementedError('mask-guided selection (reference nets/sfd2.py:502-571) is out of scope')
+    dev = next(model.parameters()).device
+    x = img.reshape(1, 3, img.shape[-2], img.shape[-1]).to(dev).float()
+    mean = torch.tensor(RGB_mean, device=dev).view(1, 3, 1, 1)
+    std = torch.tensor(RGB_std, device=dev).view(1, 3, 1, 1)
+    x = (x - mean) / std
+    H, W = x.shape[2:]
+    scales = kwargs.get('scales', [1.0])
+    all_pts, all_desc = [], []
+    for s in scales:
+        xi = x if s == 1.0 else torch.nn.functional.interpolate(x, size=(int(H * s), int(W * s)), mode='bilinear',
+                                                                align_corners=True)
+        nh, nw = xi.shape[2:]
+        t = model._trunk(xi)
+        heat = ops.score_map(t['logits'], nh, nw)
+        # every candidate above the threshold, best first (K = 4096 is the kernel's and the
+        # reference config's ceiling, extract_features.py:73)
+        kpts, scs, n, _ = ops.detect_keypoints(heat, conf_th, 0, 4096, 4, radius=3, strict=True, fallback=False)
+        n0 = int(n[0])
+        if n0 == 0:
+            continue
+        k = kpts[:, :n0]
+        order = torch.argsort(scs[0, :n0], descending=True, stable=True)  # row-major when n <= K
+        k, sc = k[:, order], scs[0, :n0][order]
+        # reference samples with g = x/(w/2) - 1 on the desc map: express through pixel coords of the
+        # generic sampler: (g+1)/2*(wd-1) with wd = desc width  ->  handled by s=1 on a coordinate remap
+        dh, dw = t['desc'].shape[1:3]
+        g = torch.stack([k[0, :, 0] / (float(nw) / 2.) - 1., k[0, :, 1] / (float(nh) / 2.) - 1.], -1)
+        pix = torch.stack([(g[:, 0] + 1) / 2 * (dw - 1), (g[:, 1] + 1) / 2 * (dh - 1)], -1)
+        d = _sample_at_map_coords(t['desc'], pix)
+        pts = torch.cat([k[0] * torch.tensor([W / nw, H / nh], device=dev), sc[:, None]], 1)
+        all_pts.append(pts.double().cpu().numpy())
+        all_desc.append(d.double().cpu().numpy())
+    if not all_pts:
+        return None, None, None
+    pts = np.vstack(all_pts)
+    desc = np.vstack(all_desc)
+    keypoints, scores = pts[:, :2], pts[:, 2]
+    if topK > 0:
+        idx = np.array(scores, dtype=float).argsort()[::-1][:topK]
+        keypoints, scores, desc = keypoints[idx], scores[idx], desc[idx]
+    return {'keypoints': np.array(keypoints, dtype=float), 'descriptors': np.array(desc, dtype=float),
+            'scores': np.array(scores, dtype=float)}
+
+
+def _sample_at_map_coords(desc_nhwc: torch.Tensor, pix: torch.Tensor) -> torch.Tensor:
+    """Bilinear sample at map-pixel coordinates, then L2 normalise -> [n, C].  The generic sampler maps
+    keypoint k to map coordinate ((k - off)/div*2-1+1)/2*(w-1); with s chosen so that off = 0 and
+    div = w-1... the export path's normalisation is not of that form, so the coordinates are
+    pre-inverted here: k' = pix * div/(w-1) + off."""
+    b, h, w, c = desc_nhwc.shape
+    s = 4
+    off = s / 2 - 0.5
+    divx, divy = w * s - s / 2 - 0.5, h * s - s / 2 - 0.5
+    k = torch.stack([pix[:, 0] * (divx / (w - 1)) + off, pix[:, 1] * (divy / (h - 1)) + off], -1)
+    return ops.sample_features(desc_nhwc[:1], k[None].contiguous(), None, s, True)[0]
+
+
+def load_sfd2(weight_path: str) -> ResNet4x:
+    net = ResNet4x(inputdim=3, outdim=128)
+    net.load_state_dict(torch.load(weight_path, map_location='cpu', weights_only=False)['state_dict'], strict=True)
+    return net

@@ -1,0 +1,206 @@
+"""Thin tensor-level wrappers over the C ABI (one function per kernel group of SURVEY.md section 2b).
+
+Everything here takes CUDA tensors, allocates outputs through torch, and launches on torch's
+current stream.  No arithmetic happens in Python.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+Tensor = torch.Tensor
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---- K5 / K5b ---------------------------------------------------------------------------------
+
+def score_map(logits_nhwc: Tensor, ih: Optional[int] = None, iw: Optional[int] = None) -> Tensor:
+    """logits [B,Hc,Wc,>=65] (any strides, channel-last view allowed) -> score [B,Hc*8,Wc*8]
+    (optionally bilinearly resized to [B,ih,iw]); reference nets/sfd2.py:294-303."""
+    _lib.require_cuda(logits_nhwc, 'logits')
+    b, hc, wc, _ = logits_nhwc.shape
+    sb, sy, sx, sc = logits_nhwc.stride()
+    out = torch.empty((b, hc * 8, wc * 8), device=logits_nhwc.device, dtype=torch.float32)
+    call('pram_score_map', ptr(logits_nhwc), sb, sy, sx, sc, b, hc, wc, ptr(out), stream_ptr())
+    if ih is not None and (ih != hc * 8 or iw != wc * 8):
+        res = torch.empty((b, ih, iw), device=out.device, dtype=torch.float32)
+        call('pram_resize_bilinear', ptr(out), b, hc * 8, wc * 8, ptr(res), ih, iw, stream_ptr())
+        out = res
+    return out
+
+
+# ---- K6 / K7 ----------------------------------------------------------------------------------
+
+def detect_keypoints(score: Tensor, conf_th: float, min_keypoints: int, max_keypoints: int, border: int,
+                     radius: int = 4, strict: bool = False, fallback: bool = True,
+                     return_nms: bool = False, cap: Optional[int] = None):
+    """score [B,H,W] -> (kpts [B,kpad,2] (x,y) f32, scores [B,kpad], n [B] int32 [, nms [B,H,W]]).
+
+    NMS + threshold + border + top-k on the device with no host sync (reference nets/sfd2.py:305-329).
+    ``strict`` selects the ``>`` comparison of the export path (nets/sfd2.py:435); ``fallback`` the
+    halve-the-threshold rule of nets/sfd2.py:311-315 (per frame).
+    """
+    _lib.require_cuda(score, 'score map')
+    score = _f32c(score)
+    b, h, w = score.shape
+    th_hi = np.float32(conf_th)
+    if strict:  # s > th  <=>  s >= nextafter(th)
+        th_hi = np.nextafter(th_hi, np.float32(np.inf))
+    th_lo = np.float32(conf_th * 0.5) if fallback else th_hi
+    if strict and fallback:
+        th_lo = np.nextafter(th_lo, np.float32(np.inf))
+    kmax = 4096
+    if max_keypoints > kmax:
+        raise _lib.PramError(f'max_keypoints > {kmax} is not supported by the selection kernel')
+    kpad = max_keypoints if max_keypoints >= 0 else kmax
+    kpad = max(kpad, 1)
+    if cap is None:
+        # local maxima are >= r+1 apart unless the map has exact plateaus; overflow is detected below
+        cap = max(4096, ((h + radius) // (radius + 1)) * ((w + radius) // (radius + 1)))
+    dev = score.device
+    cand = torch.empty((b, cap), device=dev, dtype=torch.int64)
+    counts = torch.empty((2, b), device=dev, dtype=torch.int32)
+    nms = torch.empty_like(score) if return_nms else None
+    call('pram_nms_candidates', ptr(score), b, h, w, radius, float(th_lo), float(th_hi), ptr(nms), ptr(cand), cap,
+         ptr(counts[0]), ptr(counts[1]), stream_ptr())
+    kpts = torch.empty((b, kpad, 2), device=dev, dtype=torch.float32)
+    scs = torch.empty((b, kpad), device=dev, dtype=torch.float32)
+    n = torch.empty((b,), device=dev, dtype=torch.int32)
+    call('pram_select_keypoints', ptr(cand), cap, ptr(counts[0]), ptr(counts[1]), ptr(score), b, h, w,
+         float(th_lo), float(th_hi), int(min_keypoints) if fallback else -1, int(max_keypoints), int(border),
+         ptr(kpts), ptr(scs), ptr(n), kpad, stream_ptr())
+    out = (kpts, scs, n, counts[0])
+    if return_nms:
+        out = out + (nms,)
+    return out
+
+
+# ---- K8 ---------------------------------------------------------------------------------------
+
+def sample_features(fmap_nhwc: Tensor, kpts: Tensor, counts: Optional[Tensor], s: int, normalize: bool) -> Tensor:
+    """fmap [B,h,w,C] contiguous NHWC, kpts [B,kpad,2] -> [B,kpad,C]; reference nets/sfd2.py:53-64."""
+    _lib.require_cuda(fmap_nhwc, 'feature map')
+    assert fmap_nhwc.is_contiguous() and fmap_nhwc.dtype == torch.float32
+    b, h, w, c = fmap_nhwc.shape
+    kpts = _f32c(kpts)
+    kpad = kpts.shape[1]
+    out = torch.empty((b, kpad, c), device=fmap_nhwc.device, dtype=torch.float32)
+    call('pram_sample_features', ptr(fmap_nhwc), b, c, h, w, ptr(kpts), ptr(counts), kpad, int(s),
+         int(bool(normalize)), ptr(out), stream_ptr())
+    return out
+
+
+def gather_scores(score: Tensor, kpts: Tensor, counts: Optional[Tensor]) -> Tensor:
+    score = _f32c(score)
+    b, h, w = score.shape
+    kpts = _f32c(kpts)
+    out = torch.empty(kpts.shape[:2], device=score.device, dtype=torch.float32)
+    call('pram_gather_scores', ptr(score), b, h, w, ptr(kpts), ptr(counts), kpts.shape[1], ptr(out), stream_ptr())
+    return out
+
+
+# ---- K9 ---------------------------------------------------------------------------------------
+
+def posenc(kpts: Tensor, width: float, height: float, wr: Tensor, prenormalized: bool = False) -> Tuple[Tensor, Tensor]:
+    """kpts [..., 2] -> (cos, sin) each [tokens, 32]; reference nets/utils.py:17-24 + segnetvit.py:35-40."""
+    kpts = _f32c(kpts)
+    tokens = kpts.numel() // 2
+    cos = torch.empty((tokens, 32), device=kpts.device, dtype=torch.float32)
+    sin = torch.empty_like(cos)
+    call('pram_posenc', ptr(kpts), tokens, float(width), float(height), int(prenormalized), ptr(wr), ptr(cos),
+         ptr(sin), stream_ptr())
+    return cos, sin
+
+
+# ---- fp32 network building blocks ----------------------------------------------------------------
+
+def conv_f32(x_nhwc: Tensor, w: Tensor, bias: Optional[Tensor], ksize: int, stride: int, relu: bool,
+             res: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """x [B,H,W,Cin] NHWC contiguous, w [taps,Cin,Cout] -> [B,Ho,Wo,Cout]."""
+    b, h, wd, cin = x_nhwc.shape
+    cout = w.shape[-1]
+    pad = ksize // 2
+    ho = (h + 2 * pad - ksize) // stride + 1
+    wo = (wd + 2 * pad - ksize) // stride + 1
+    if out is None:
+        out = torch.empty((b, ho, wo, cout), device=x_nhwc.device, dtype=torch.float32)
+    call('pram_conv_f32', ptr(x_nhwc), cin, ptr(w), ptr(bias), ptr(res), cout, ptr(out), cout, b, h, wd, cin, cout,
+         ksize, stride, int(relu), stream_ptr())
+    return out
+
+
+def gconv3x3_f32(x_nhwc: Tensor, w: Tensor, bias: Tensor, relu: bool) -> Tensor:
+    b, h, wd, c = x_nhwc.shape
+    out = torch.empty_like(x_nhwc)
+    call('pram_gconv3x3_f32', ptr(x_nhwc), ptr(w), ptr(bias), ptr(out), b, h, wd, c // 8, int(relu), stream_ptr())
+    return out
+
+
+def linear_f32(a: Tensor, lda: int, w: Tensor, bias: Optional[Tensor], out: Tensor, ldo: int, rows: int, k: int,
+               n: int, relu: bool = False, res: Optional[Tensor] = None, ldres: int = 0, batch: int = 1,
+               a_bs: int = 0, w_bs: int = 0, o_bs: int = 0) -> Tensor:
+    """out[rows, n] = a[rows, k] @ w[n, k]^T (+bias)(+res)(relu); raw row strides so that inputs and
+    outputs can be column slices of wider buffers (concat-free MLP)."""
+    call('pram_linear_f32', ptr(a), lda, ptr(w), ptr(bias), ptr(res), ldres, ptr(out), ldo, rows, k, n, int(relu),
+         batch, a_bs, w_bs, o_bs, stream_ptr())
+    return out
+
+
+def l2norm_rows_(x: Tensor, c: int) -> Tensor:
+    rows = x.numel() // c
+    call('pram_l2norm_rows', ptr(x), ptr(x), rows, c, stream_ptr())
+    return x
+
+
+def layernorm_gelu_(x: Tensor, gamma: Tensor, beta: Tensor, c: int, gelu: bool = True) -> Tensor:
+    rows = x.numel() // c
+    call('pram_layernorm_gelu', ptr(x), ptr(gamma), ptr(beta), ptr(x), rows, c, int(gelu), stream_ptr())
+    return x
+
+
+def rotary_split(qkv: Tensor, nparts: int, b: int, n: int, heads: int, cos: Optional[Tensor], sin: Optional[Tensor],
+                 scale_qk: float, q: Tensor, k: Optional[Tensor], v: Tensor):
+    call('pram_rotary_split', ptr(qkv), nparts, b, n, heads, ptr(cos), ptr(sin), float(scale_qk), ptr(q), ptr(k),
+         ptr(v), stream_ptr())
+
+
+def attention_f32(q: Tensor, k: Tensor, v: Tensor, b: int, heads: int, nq: int, nk: int, scale: float, out: Tensor,
+                  out_stride: int, colmean: Optional[Tensor] = None):
+    call('pram_attention_f32', ptr(q), ptr(k), ptr(v), b, heads, nq, nk, float(scale), ptr(out), out_stride,
+         ptr(colmean), stream_ptr())
+
+
+# ---- K15 / K16 --------------------------------------------------------------------------------
+
+def sinkhorn_match(dist: Tensor, bin_score: Tensor, iters: int, threshold: float, cluster: int = 0,
+                   return_P: bool = False):
+    """dist [B,M,N] f32, bin_score 0-dim device tensor -> matches0 [B,M] i64, matches1 [B,N] i64,
+    mscores0 [B,M], mscores1 [B,N] (+ P [B,M+1,N+1]); reference nets/gml.py:27-46, 304-319."""
+    _lib.require_cuda(dist, 'dist')
+    dist = _f32c(dist)
+    b, m, n = dist.shape
+    dev = dist.device
+    ldp = (n + 1 + 3) // 4 * 4
+    pws = torch.empty((b, m + 1, ldp), device=dev, dtype=torch.float32)
+    iws = torch.empty((b * (m + n),), device=dev, dtype=torch.int32)
+    fws = torch.empty((b * m,), device=dev, dtype=torch.float32)
+    m0 = torch.empty((b, m), device=dev, dtype=torch.int64)
+    m1 = torch.empty((b, n), device=dev, dtype=torch.int64)
+    s0 = torch.empty((b, m), device=dev, dtype=torch.float32)
+    s1 = torch.empty((b, n), device=dev, dtype=torch.float32)
+    bs = bin_score.detach().reshape(1).float().contiguous()
+    call('pram_sinkhorn_match', ptr(dist), b, m, n, ptr(bs), int(iters), float(threshold), ptr(pws), ptr(iws),
+         ptr(fws), ptr(m0), ptr(m1), ptr(s0), ptr(s1), int(cluster), stream_ptr())
+    if return_P:
+        return m0, m1, s0, s1, pws[:, :, :n + 1]
+    return m0, m1, s0, s1
