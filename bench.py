@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the PRAM per-frame localization hot path on B200 (BASELINE.json metric:
+localization frames/sec, 640x480, 1024 keypoints).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one pass of the hot path (SFD2 -> keypoints -> SegNetViT -> GML+Sinkhorn [-> PnP]) over one
+batch of synthetic frames per GPU.  Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+H, W, KPTS, NCLASS = 480, 640, 1024, 113
+METRIC = 'localization frames/sec (640x480, 1024 kpts)'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=32, help='frames per GPU per step')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def workload_name(batch):
+    return (f'7Scenes-shaped synthetic stream: SFD2 + SegNetViT(113 classes, 15 layers) + GML(9 layers, '
+            f'Sinkhorn 20) one matcher call per frame, {batch} frames/GPU/step')
+
+
+# ------------------------------------------------------------------------------------------------
+# inputs / weights (synthetic frames; shipped SFD2+GML checkpoints when staged, seeded random otherwise)
+# ------------------------------------------------------------------------------------------------
+
+def make_frames(batch, seed0=0):
+    import torch
+    from oracle import pram_oracle as O  # input generator only (polys frames)
+    return torch.cat([O.frame_tensor(H, W, seed=seed0 + i) for i in range(batch)], 0)
+
+
+def states():
+    from oracle import ref_loader as RL
+    sfd2 = RL.load_sfd2_state()
+    gml = RL.load_gml_state()
+    tag = 'shipped SFD2+GML checkpoints' if (sfd2 is not None and gml is not None) else 'seeded random weights'
+    sfd2 = sfd2 if sfd2 is not None else RL.random_sfd2_state(0)
+    gml = gml if gml is not None else RL.random_gml_state(seed=0)
+    vit = RL.random_segnetvit_state(NCLASS, seed=0)
+    return sfd2, vit, gml, tag
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 7 and r[3 + i].lower().startswith('active')})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (a port of the reference's torch-CPU path) on the host cores
+# ------------------------------------------------------------------------------------------------
+
+def cpu_chain(frames_cpu, sd_sfd2, sd_vit, sd_gml, perm):
+    import torch
+    from oracle import pram_oracle as O
+    cfg = {'min_keypoints': 128, 'max_keypoints': KPTS}
+    with torch.no_grad():
+        for i in range(frames_cpu.shape[0]):
+            img = frames_cpu[i:i + 1]
+            f = O.sfd2_extract_local_global(sd_sfd2, img, cfg)
+            k = f['keypoints'][0]
+            _, seg = O.sfd2_sample(f['score_map'], f['mid_features'], k, norm_desc=False)
+            O.segnetvit_forward(sd_vit, seg.t()[None], k[None], img.shape)
+            d0 = f['descriptors'][0].t()[None]
+            p = perm[:k.shape[0]] % k.shape[0]
+            O.gml_forward(sd_gml, {'descriptors0': d0, 'descriptors1': d0[:, p], 'keypoints0': k[None],
+                                   'keypoints1': k[p][None], 'image_shape0': (1, 3, W, H), 'image_shape1': (1, 3, W, H)})
+
+
+def time_cpu(n_frames, reps):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd_sfd2, sd_vit, sd_gml, tag = states()
+    frames = make_frames(n_frames)
+    perm = torch.randperm(KPTS, generator=torch.Generator().manual_seed(0))
+    cpu_chain(frames[:1], sd_sfd2, sd_vit, sd_gml, perm)  # warm-up
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_chain(frames, sd_sfd2, sd_vit, sd_gml, perm)
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return n_frames / ts[len(ts) // 2], cores, ts
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (its torch-CPU arithmetic,
+    restated in oracle/pram_oracle.py and pinned bit-identical to the reference modules) on all host
+    threads; each step = a bounded sample of the workload (1 frame)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd_sfd2, sd_vit, sd_gml, tag = states()
+    frames = make_frames(1)
+    perm = torch.randperm(KPTS, generator=torch.Generator().manual_seed(0))
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_chain(frames, sd_sfd2, sd_vit, sd_gml, perm)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_chain(frames, sd_sfd2, sd_vit, sd_gml, perm)
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': f'synthetic polygon frames; {tag}; seeded random SegNetViT',
+        'config': {'workload': workload_name(args.batch), 'sample': '1 frame per step'},
+        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{args.steps} steps x 1 frame, torch-CPU fp32, {cores} threads'},
+        'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pram_b200 import _lib
+    from pram_b200.nets.sfd2 import ResNet4x
+    from pram_b200.nets.segnetvit import SegNetViT
+    from pram_b200.nets.gml import GML
+    from pram_b200.runner import LocalizationPipeline
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.load()  # fails loudly if the CUDA library is missing
+
+    sd_sfd2, sd_vit, sd_gml, tag = states()
+    sfd2 = ResNet4x(); sfd2.load_state_dict(sd_sfd2, strict=True)
+    vit = SegNetViT({'n_class': NCLASS, 'n_layers': 15, 'output_dim': 1024, 'descriptor_dim': 256})
+    vit.load_state_dict(sd_vit, strict=True)
+    gml = GML({}); gml.load_state_dict(sd_gml, strict=True)
+    pipe = LocalizationPipeline(sfd2, vit, gml, max_keypoints=KPTS, device=dev)
+
+    B = args.batch
+    frames_host = make_frames(B, seed0=rank * B).pin_memory()
+    frames_dev = frames_host.to(dev)
+    smap = pipe.build_synthetic_map(frames_dev, seed=rank)
+    # L2 flush buffer (> 126 MB L2); the per-step working set (B x 640x480 activations) is itself > L2
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+    pose_rec = torch.zeros(B, 9, device=dev, dtype=torch.float64)
+    gathered = [torch.zeros_like(pose_rec) for _ in range(world)] if world > 1 else None
+
+    def step(images):
+        out = pipe.localize(images, smap)
+        # fixed-size pose record per frame [id, q(4), t(3), n_inliers]; the single collective of the path
+        pose_rec[:, 0] = torch.arange(B, device=dev, dtype=torch.float64) + rank * B
+        pose_rec[:, 8] = (out['matches0'] > -1).sum(-1).double()
+        if world > 1:
+            dist.all_gather(gathered, pose_rec)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step(frames_dev)
+    barrier()
+
+    # ---- timed: device-resident inputs ---------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _lib.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+        evs[i][0].record()
+        out = step(frames_dev)
+        evs[i][1].record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- timed: end to end through the public API with host buffers --------------------------------
+    res_host = torch.empty(B, KPTS, dtype=torch.int64).pin_memory()
+    lab_host = torch.empty(B, KPTS, dtype=torch.int64).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        img = frames_host.to(dev, non_blocking=True)
+        out = step(img)
+        res_host.copy_(out['matches0'], non_blocking=True)
+        lab_host.copy_(out['labels'], non_blocking=True)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = world * B * args.steps / (float(t.item()) * 1e-3)
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        roof = roofline_probe(pipe, frames_dev, dev)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, ts = time_cpu(2, 3)
+            cpu = {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                   'sample': f'2 frames x 3 reps (median), oracle torch-CPU fp32, {cores} threads'}
+        matched = float((out['matches0'] > -1).float().mean().item())
+        print(json.dumps({
+            'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': pipe.sfd2.compute_dtype if hasattr(pipe.sfd2, 'compute_dtype') else 'f32',
+            'data': f'synthetic polygon frames; {tag}; seeded random SegNetViT',
+            'config': {'workload': workload_name(B), 'frames_per_gpu_per_step': B, 'l2': 'flushed between timed steps (256 MiB memset)',
+                       'matched_fraction': matched},
+            'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': frames_host.numel() * 4,
+                    'd2h_bytes_per_step': res_host.numel() * 8 * 2},
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline_probe(pipe, frames_dev, dev):
+    """Dominant kernel = the 3x3 256->256 convolution at 1/4 resolution (conv3b / convDa.0 / convDa.3 /
+    convPa: 51 % of the conv-stack FLOPs).  Timed live with CUDA events on the launch
+    stream; algorithmic FLOPs = 2 * B*120*160 * 256 * 2304 per launch."""
+    import torch
+    from pram_b200 import ops
+    peaks = {}
+    p = ROOT / 'MEASURED_PEAKS.json'
+    if p.exists():
+        peaks = json.loads(p.read_text())
+    peak = float(peaks.get('bf16_tflops', 1590.0))
+    B = frames_dev.shape[0]
+    pk = pipe.sfd2.prepare()
+    x = torch.randn(B, H // 4, W // 4, 256, device=dev)
+    fn = getattr(pipe.sfd2, 'probe_conv3b', None)
+    if fn is None:
+        def fn(inp):
+            return ops.conv_f32(inp, pk['conv3b.w'], pk['conv3b.b'], 3, 1, True)
+    for _ in range(2):
+        fn(x)
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * B * (H // 4) * (W // 4) * 256 * 2304
+    ach = flops / (ms * 1e-3) / 1e12
+    return {'bound': 'tensor', 'kernel': 'conv3x3 256->256 @120x160 (conv3b)', 'achieved': ach, 'peak': peak,
+            'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': None,
+            'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst)' if peaks else 'fallback 1.59 PFLOP/s'}
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

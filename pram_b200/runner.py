@@ -1,0 +1,107 @@
+"""Frame-parallel localization runner: SFD2 -> SegNetViT -> GML(+Sinkhorn) -> PnP/RANSAC on a batch of
+frames, device-resident end to end (no D2H -> numpy -> H2D round trips between the stages, which the
+reference's loop does at every stage boundary, localization/loc_by_rec_online.py:109-189).
+
+One process per GPU; frames are independent units (relocalisation mode, reference README.md:62), so
+multi-GPU is plain sharding of frames across ranks with a single gather of fixed-size pose records.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .nets.gml import GML
+from .nets.segnetvit import SegNetViT
+from .nets.sfd2 import ResNet4x
+
+
+@dataclass
+class SyntheticMap:
+    """Per-frame reference set for the synthetic stream: the frame's own
+    keypoints/descriptors under a seeded permutation, lifted to 3-D with a known pose, 20 % outliers."""
+    descriptors: torch.Tensor  # [B,N,128]
+    keypoints: torch.Tensor    # [B,N,2]
+    xyz: torch.Tensor          # [B,N,3]
+    perm: torch.Tensor         # [B,N]  reference j  <-  query perm[j]
+    outlier: torch.Tensor      # [B,N] bool
+    R: torch.Tensor            # [B,3,3]
+    t: torch.Tensor            # [B,3]
+
+
+class LocalizationPipeline:
+    def __init__(self, sfd2: ResNet4x, segnet: SegNetViT, matcher: GML, max_keypoints: int = 1024,
+                 focal: float = 525.0, ransac_max_error: float = 8.0, device='cuda'):
+        self.dev = torch.device(device)
+        self.sfd2 = sfd2.to(self.dev)
+        self.segnet = segnet.to(self.dev)
+        self.matcher = matcher.to(self.dev)
+        self.K = max_keypoints
+        self.focal = focal
+        self.max_error = ransac_max_error
+        self.cfg = {'min_keypoints': 128, 'max_keypoints': max_keypoints}
+
+    # -- stages -------------------------------------------------------------------------------
+    def features(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """images [B,3,H,W] normalised -> padded keypoints/descriptors + 256-d recognition features."""
+        f = self.sfd2.extract_batched(images, self.cfg)
+        f['seg_descriptors'] = ops.sample_features(f['mid_features_nhwc'], f['keypoints'], f['num_keypoints'], 4, False)
+        return f
+
+    def recognize(self, f: Dict[str, torch.Tensor], image_shape) -> torch.Tensor:
+        """-> landmark logits [B,K,n_class] (reference loc_by_rec_online.py:130)."""
+        return self.segnet({'seg_descriptors': f['seg_descriptors'], 'keypoints': f['keypoints'],
+                            'image': torch.empty(image_shape, device='meta')})['prediction']
+
+    def match(self, f: Dict[str, torch.Tensor], smap: SyntheticMap, image_shape) -> Dict[str, torch.Tensor]:
+        """query (frame) vs reference (map) sets, one pair per frame (reference singlemap3d.py:143-154,
+        including its (1,3,W,H) image_shape convention)."""
+        b, _, h, w = image_shape
+        shp = (1, 3, w, h)
+        return self.matcher({'descriptors0': f['descriptors'], 'keypoints0': f['keypoints'],
+                             'descriptors1': smap.descriptors, 'keypoints1': smap.keypoints,
+                             'image_shape0': shp, 'image_shape1': shp})
+
+    def localize(self, images: torch.Tensor, smap: Optional[SyntheticMap] = None) -> Dict[str, torch.Tensor]:
+        shape = tuple(images.shape)
+        f = self.features(images)
+        out = {'keypoints': f['keypoints'], 'num_keypoints': f['num_keypoints'],
+               'prediction': self.recognize(f, shape)}
+        out['labels'] = out['prediction'].argmax(-1)
+        if smap is not None:
+            m = self.match(f, smap, shape)
+            out.update(m)
+        return out
+
+    # -- synthetic map ------------------------------------------------------------------------
+    @torch.no_grad()
+    def build_synthetic_map(self, images: torch.Tensor, seed: int = 0, outlier_frac: float = 0.2) -> SyntheticMap:
+        f = self.features(images)
+        b, k, _ = f['keypoints'].shape
+        g = torch.Generator(device='cpu').manual_seed(seed)
+        perm = torch.stack([torch.randperm(k, generator=g) for _ in range(b)]).to(self.dev)
+        kp = torch.gather(f['keypoints'], 1, perm[..., None].expand(-1, -1, 2))
+        desc = torch.gather(f['descriptors'], 1, perm[..., None].expand(-1, -1, 128)).clone()
+        # known pose per frame: small rotation (<= 15 deg) and translation (<= 0.5 m)
+        ax = torch.nn.functional.normalize(torch.randn(b, 3, generator=g), dim=-1)
+        ang = (torch.rand(b, generator=g) * 15.0 * 3.14159265 / 180.0)
+        Kx = torch.zeros(b, 3, 3)
+        Kx[:, 0, 1], Kx[:, 0, 2], Kx[:, 1, 0] = -ax[:, 2], ax[:, 1], ax[:, 2]
+        Kx[:, 1, 2], Kx[:, 2, 0], Kx[:, 2, 1] = -ax[:, 0], -ax[:, 1], ax[:, 0]
+        R = torch.eye(3)[None] + torch.sin(ang)[:, None, None] * Kx + (1 - torch.cos(ang))[:, None, None] * (Kx @ Kx)
+        t = (torch.rand(b, 3, generator=g) - 0.5)
+        z = 1.0 + 4.0 * torch.rand(b, k, generator=g)
+        outl = torch.rand(b, k, generator=g) < outlier_frac
+        R, t, z, outl = R.to(self.dev), t.to(self.dev), z.to(self.dev), outl.to(self.dev)
+        h, w = images.shape[-2:]
+        cx, cy = w / 2.0, h / 2.0
+        ray = torch.stack([(kp[..., 0] + 0.5 - cx) / self.focal, (kp[..., 1] + 0.5 - cy) / self.focal,
+                           torch.ones_like(z)], -1) * z[..., None]
+        xyz = torch.einsum('bji,bnj->bni', R, ray - t[:, None])  # X = R^T (x_cam - t)
+        rnd_desc = torch.nn.functional.normalize(torch.randn(b, k, 128, generator=g), dim=-1).to(self.dev)
+        rnd_xyz = (torch.rand(b, k, 3, generator=g) * 4 - 2).to(self.dev)
+        desc = torch.where(outl[..., None], rnd_desc, desc)
+        xyz = torch.where(outl[..., None], rnd_xyz, xyz)
+        return SyntheticMap(desc.contiguous(), kp.contiguous(), xyz.contiguous(), perm, outl, R, t)
