@@ -109,6 +109,34 @@ int pram_sinkhorn_match(const float* dist, int B, int M, int N, const float* bin
                         float threshold, float* pws, int* iws, float* fws, long long* matches0,
                         long long* matches1, float* mscores0, float* mscores1, int cluster, pram_stream_t stream);
 
+/* K1-K4, K10-K14 (tensor-core path): tcgen05 implicit GEMM, TMA-fed, accumulators in TMEM.
+ *   D[pixel][n] = sum_{tap,c} A[pixel + offset(tap)][c] * W[tap][n][c]  (+bias)(+res)(ReLU)(L2 norm)
+ * A: bf16 NHWC activations (optionally hi/lo split planes; optionally 2x2 phase-split for stride 2),
+ * W: bf16 [planes][N][Cin].  Replaces cuDNN/cuBLAS under nets/sfd2.py:141-170 and the nn.Linear /
+ * einsum calls of nets/segnetvit.py:88-106, nets/gml.py:119-186, 278-282. */
+typedef struct pram_tc_args {
+    const void* a_hi; const void* a_lo; long long a_ld;
+    int in_W, in_H, in_planes, Cin;
+    const void* w_hi; const void* w_lo; int w_planes;
+    int B, Ho, Wo, N;
+    int tw_log2;
+    int ntaps;
+    int tap_dx[9], tap_dy[9], tap_plane[9];
+    int planes_per_image;
+    int w_batch_mult;
+    const float* bias; const float* res; long long res_ld; int relu;
+    float* out_f32; long long ld_f32;
+    void* out_hi; void* out_lo; long long ld_bf;
+    void* ps_hi; void* ps_lo; long long ld_ps;
+    int l2norm;
+    int split; /* 1: bf16, 3: error-compensated bf16x3 */
+    int bn;    /* N tile (64/128/256), 0 = auto */
+} pram_tc_args;
+int pram_gemm_tc(const pram_tc_args* args, pram_stream_t stream);
+
+/* fp32 -> split bf16 planes: hi = bf16(x), lo = bf16(x - hi) (lo may be NULL). */
+int pram_split_bf16(const float* in, void* hi, void* lo, long long n, pram_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,29 @@ SIGNATURES = {
     'pram_sinkhorn_match': (_I, [_P, _I, _I, _I, _P, _I, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
 }
 
+
+
+class TcArgs(C.Structure):
+    """Mirror of ``struct pram_tc_args`` (include/pram_b200.h)."""
+    _fields_ = [
+        ('a_hi', _P), ('a_lo', _P), ('a_ld', _L),
+        ('in_W', _I), ('in_H', _I), ('in_planes', _I), ('Cin', _I),
+        ('w_hi', _P), ('w_lo', _P), ('w_planes', _I),
+        ('B', _I), ('Ho', _I), ('Wo', _I), ('N', _I),
+        ('tw_log2', _I), ('ntaps', _I),
+        ('tap_dx', _I * 9), ('tap_dy', _I * 9), ('tap_plane', _I * 9),
+        ('planes_per_image', _I), ('w_batch_mult', _I),
+        ('bias', _P), ('res', _P), ('res_ld', _L), ('relu', _I),
+        ('out_f32', _P), ('ld_f32', _L),
+        ('out_hi', _P), ('out_lo', _P), ('ld_bf', _L),
+        ('ps_hi', _P), ('ps_lo', _P), ('ld_ps', _L),
+        ('l2norm', _I), ('split', _I), ('bn', _I),
+    ]
+
+
+SIGNATURES['pram_gemm_tc'] = (_I, [C.POINTER(TcArgs), _P])
+SIGNATURES['pram_split_bf16'] = (_I, [_P, _P, _P, _L, _P])
+
 _lib = None
 
 

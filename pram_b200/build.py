@@ -45,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             print(out)
         if p.returncode != 0:
             raise RuntimeError(f'nvcc failed on {src.name}:\n{out}')
-    cmd = [nvcc, '-shared', '-o', str(LIB), *map(str, objs), '-lcuda']
+    cmd = [nvcc, '-shared', '-o', str(LIB), *map(str, objs)]  # driver API is resolved at run time
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f'link failed:\n{r.stdout}')

@@ -1,0 +1,531 @@
+// tcgen05 tensor-core implicit GEMM for sm_100a: the 3x3 / 1x1 convolutions of SFD2 (K1-K4) and every
+// Linear layer / batched A.B^T of SegNetViT and GML (K10-K14) -- reference nets/sfd2.py:141-170,
+// nets/segnetvit.py:88-106, nets/gml.py:119-186,278-282 (cuDNN / cuBLAS fp32 there).
+//
+//   D[pixel, n] = sum_{tap, c} A[pixel + offset(tap), c] * W[tap][n][c]       (fp32 accumulate in TMEM)
+//
+// * persistent kernel, one CTA per SM, static round-robin tile scheduler
+// * warp 0 (one lane): TMA producer -- A tiles are 4-D boxes {64 ch, TW, TH, 1} of the NHWC activation
+//   tensor shifted by the filter tap (out-of-bounds = zero fill = the convolution's padding), which land
+//   in shared memory as a 128 x 64 K-major SWIZZLE_128B operand; W tiles are {64, BN, 1} boxes
+// * warp 1 (one lane): tcgen05.mma issuer, accumulators in TMEM, double-buffered (2 x BN columns) so
+//   the epilogue of tile i overlaps the main loop of tile i+1
+// * warps 2-5: epilogue -- tcgen05.ld -> bias / residual / ReLU -> fp32 and/or split-bf16 stores
+//   (NHWC, and optionally a 2x2 phase-split copy that feeds a following stride-2 convolution with
+//   unit-stride TMA boxes)
+// * SPLIT=3: error-compensated bf16x3 (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, all into the same fp32
+//   accumulator) -- ~16 mantissa bits, needed for bit-stable keypoint selection;
+//   SPLIT=1: plain bf16.
+#include "common.cuh"
+#include <cuda.h>
+#include <stdio.h>
+
+namespace tc {
+
+constexpr int BM = 128;       // UMMA_M
+constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_TAPS = 9;
+
+struct Args {
+    // geometry of the output
+    int B, Ho, Wo, N;
+    int tw_log2;         // tile = (128 >> tw_log2) rows x (1 << tw_log2) columns of output pixels
+    int ntaps, kblocks;  // kblocks = ceil(Cin / 64)
+    int planes_per_image;  // 1, or 4 when A is a phase-split tensor
+    int tap_dx[MAX_TAPS], tap_dy[MAX_TAPS], tap_plane[MAX_TAPS];
+    int w_batch_mult;    // weight plane = tap + b * w_batch_mult
+    // epilogue
+    const float* bias;
+    const float* res; long long res_ld;
+    int relu;
+    float* out_f32; long long ld_f32;
+    __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; long long ld_bf;
+    __nv_bfloat16* ps_hi; __nv_bfloat16* ps_lo; long long ld_ps;  // phase-split copy
+    int l2norm;          // normalise each output row (requires N <= BN)
+};
+
+// ---------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must trap, never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            printf("pram gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): start>>4, LBO=0, SBO=1024 B
+// (8 rows x 128 B), version 1, layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both,
+// N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+template <int BN, int SPLIT>
+struct Cfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int NPLANES = (SPLIT == 3) ? 2 : 1;
+    static constexpr int STAGE_BYTES = NPLANES * (A_BYTES + B_BYTES);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+template <int BN, int SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
+    const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const Args p) {
+    using C = Cfg<BN, SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;                       // [STAGES]
+    uint64_t* empty = bars + C::STAGES;          // [STAGES]
+    uint64_t* tfull = bars + 2 * C::STAGES;      // [2]
+    uint64_t* tempty = bars + 2 * C::STAGES + 2; // [2]
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int TW = 1 << p.tw_log2, TH = BM >> p.tw_log2;
+    const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int m_tiles = p.B * tiles_y * tiles_x;
+    const int total = m_tiles * n_tiles;
+    const int num_kb = p.ntaps * p.kblocks;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_a_hi);
+        prefetch_tmap(&map_w_hi);
+        if (SPLIT == 3) { prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_lo); }
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(C::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const int nt = tile % n_tiles, mt = tile / n_tiles;
+            const int txi = mt % tiles_x, tyi = (mt / tiles_x) % tiles_y, b = mt / (tiles_x * tiles_y);
+            const int x0 = txi * TW, y0 = tyi * TH, n0 = nt * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int tap = kb / p.kblocks, kc = kb - tap * p.kblocks;
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = smem + stage * C::STAGE_BYTES;
+                mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap];
+                const int ap = b * p.planes_per_image + p.tap_plane[tap];
+                const int wp = tap + b * p.w_batch_mult;
+                tma_load_4d(st, &map_a_hi, &full[stage], kc * BK, ax, ay, ap);
+                tma_load_3d(st + C::NPLANES * C::A_BYTES, &map_w_hi, &full[stage], kc * BK, n0, wp);
+                if (SPLIT == 3) {
+                    tma_load_4d(st + C::A_BYTES, &map_a_lo, &full[stage], kc * BK, ax, ay, ap);
+                    tma_load_3d(st + 2 * C::A_BYTES + C::B_BYTES, &map_w_lo, &full[stage], kc * BK, n0, wp);
+                }
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc(BM, BN);
+        int stage = 0; uint32_t phase = 0;
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            mbar_wait(&tempty[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+                const uint32_t a_hi = sa, a_lo = sa + C::A_BYTES;
+                const uint32_t b_hi = sa + C::NPLANES * C::A_BYTES, b_lo = b_hi + C::B_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint32_t koff = k * UMMA_K * 2;
+                    umma(d_tmem, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, (kb | k) != 0);
+                    if (SPLIT == 3) {
+                        umma(d_tmem, make_desc(a_lo + koff), make_desc(b_hi + koff), idesc, 1);
+                        umma(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), idesc, 1);
+                    }
+                }
+                umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tfull[as]);  // accumulator ready for the epilogue
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    } else if (warp >= 2) {
+        // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;  // row of the tile == TMEM lane
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const int nt = tile % n_tiles, mt = tile / n_tiles;
+            const int txi = mt % tiles_x, tyi = (mt / tiles_x) % tiles_y, b = mt / (tiles_x * tiles_y);
+            const int y = tyi * TH + (r >> p.tw_log2), x = txi * TW + (r & (TW - 1));
+            const bool valid = (y < p.Ho) && (x < p.Wo);
+            const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
+            const int Hp = (p.Ho + 1) >> 1, Wp = (p.Wo + 1) >> 1;
+            const long long pix_ps = (((long long)(b * 4 + (y & 1) * 2 + (x & 1))) * Hp + (y >> 1)) * Wp + (x >> 1);
+            const int n0 = nt * BN;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+            float inv_norm = 1.f;
+            if (p.l2norm) {
+                float ss = 0.f;
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        int n = n0 + c + j;
+                        if (n < p.N) {
+                            float f = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + n) : 0.f);
+                            ss += f * f;
+                        }
+                    }
+                }
+                inv_norm = fmaxf(sqrtf(ss), 1e-12f);
+            }
+            for (int c = 0; c < BN; c += 32) {
+                if (n0 + c >= p.N) break;  // warp-uniform
+                uint32_t v[32];
+                tmem_ld32(taddr + c, v);
+                if (valid) {
+                    const int nb = n0 + c;
+                    const bool full32 = (nb + 32 <= p.N);
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float t = __uint_as_float(v[j]);
+                        if (p.bias && (full32 || nb + j < p.N)) t += __ldg(p.bias + nb + j);
+                        f[j] = t;
+                    }
+                    if (p.res) {
+                        const float* rp = p.res + pix * p.res_ld + nb;
+                        if (full32 && ((p.res_ld & 3) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 t = *reinterpret_cast<const float4*>(rp + j);
+                                f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (nb + j < p.N) f[j] += rp[j];
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    if (p.l2norm) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = f[j] / inv_norm;
+                    }
+                    if (p.out_f32) {
+                        float* op = p.out_f32 + pix * p.ld_f32 + nb;
+                        if (full32 && ((p.ld_f32 & 3) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (nb + j < p.N) op[j] = f[j];
+                        }
+                    }
+                    if (p.out_hi || p.ps_hi) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            split_bf16(f[j], h0, l0);
+                            split_bf16(f[j + 1], h1, l1);
+                            hi[j >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[j >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        // bf16 outputs require N % 32 == 0 and ld % 8 == 0 (checked on the host)
+                        if (p.out_hi) {
+                            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.ld_bf + nb);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            if (p.out_lo) {
+                                uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.ld_bf + nb);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                            }
+                        }
+                        if (p.ps_hi) {
+                            uint4* oh = reinterpret_cast<uint4*>(p.ps_hi + pix_ps * p.ld_ps + nb);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            if (p.ps_lo) {
+                                uint4* ol = reinterpret_cast<uint4*>(p.ps_lo + pix_ps * p.ld_ps + nb);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box) {
+    EncodeTiledFn fn = get_encode();
+    if (!fn) return PRAM_ERR_CUDA;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PRAM_OK : PRAM_ERR_CUDA;
+}
+
+static int g_num_sms = 0;
+
+template <int BN, int SPLIT>
+static int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
+                  const Args& a, int total_tiles, cudaStream_t stream) {
+    using C = Cfg<BN, SPLIT>;
+    auto kern = gemm_tc_kernel<BN, SPLIT>;
+    static bool attr = false;
+    if (!attr) {
+        PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr = true;
+    }
+    int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
+    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ah, al, wh, wl, a);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+}  // namespace tc
+
+// Public argument block of pram_gemm_tc (mirrored by ctypes in pram_b200/_lib.py).
+struct pram_tc_args {
+    const void* a_hi; const void* a_lo;   // bf16 activations [planes][in_H][in_W][a_ld], lo may be NULL (split=1)
+    long long a_ld;                       // elements between consecutive pixels
+    int in_W, in_H, in_planes, Cin;
+    const void* w_hi; const void* w_lo;   // bf16 weights [w_planes][N][Cin]
+    int w_planes;
+    int B, Ho, Wo, N;
+    int tw_log2;
+    int ntaps;
+    int tap_dx[9], tap_dy[9], tap_plane[9];
+    int planes_per_image;
+    int w_batch_mult;
+    const float* bias; const float* res; long long res_ld; int relu;
+    float* out_f32; long long ld_f32;
+    void* out_hi; void* out_lo; long long ld_bf;
+    void* ps_hi; void* ps_lo; long long ld_ps;
+    int l2norm;
+    int split;                            // 1: bf16, 3: error-compensated bf16x3
+    int bn;                               // 0 = auto
+};
+
+PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
+    using namespace tc;
+    if (!a || !a->a_hi || !a->w_hi || a->B <= 0 || a->N <= 0 || a->ntaps <= 0 || a->ntaps > MAX_TAPS) return PRAM_ERR_ARG;
+    if (a->split != 1 && a->split != 3) return PRAM_ERR_ARG;
+    if (a->split == 3 && (!a->a_lo || !a->w_lo)) return PRAM_ERR_ARG;
+    if ((a->a_ld % 8) || (a->Cin % 8)) return PRAM_ERR_UNSUPPORTED;  // 16-byte TMA strides
+    if ((a->out_hi || a->ps_hi) && ((a->N % 32) || (a->ld_bf % 8) || (a->ps_hi && (a->ld_ps % 8)))) return PRAM_ERR_UNSUPPORTED;
+    if (g_num_sms == 0) {
+        int dev = 0;
+        PRAM_CUDA(cudaGetDevice(&dev));
+        PRAM_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int bn = a->bn;
+    if (bn == 0) bn = (a->N > 128) ? 256 : (a->N > 64 ? 128 : 64);
+    if (a->l2norm && a->N > bn) return PRAM_ERR_UNSUPPORTED;
+    const int TW = 1 << a->tw_log2, TH = BM >> a->tw_log2;
+    if (TW > 256 || TH < 1) return PRAM_ERR_ARG;
+
+    CUtensorMap ah, al, wh, wl;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->in_W, (cuuint64_t)a->in_H, (cuuint64_t)a->in_planes};
+        cuuint64_t str[3] = {(cuuint64_t)a->a_ld * 2, (cuuint64_t)a->a_ld * 2 * a->in_W,
+                             (cuuint64_t)a->a_ld * 2 * a->in_W * a->in_H};
+        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+        int rc = encode(&ah, a->a_hi, 4, dims, str, box);
+        if (rc) return rc;
+        rc = encode(&al, a->a_lo ? a->a_lo : a->a_hi, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)a->Cin, (cuuint64_t)a->N, (cuuint64_t)a->w_planes};
+        cuuint64_t str[2] = {(cuuint64_t)a->Cin * 2, (cuuint64_t)a->Cin * 2 * a->N};
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 1};
+        int rc = encode(&wh, a->w_hi, 3, dims, str, box);
+        if (rc) return rc;
+        rc = encode(&wl, a->w_lo ? a->w_lo : a->w_hi, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    Args k;
+    k.B = a->B; k.Ho = a->Ho; k.Wo = a->Wo; k.N = a->N; k.tw_log2 = a->tw_log2; k.ntaps = a->ntaps;
+    k.kblocks = (a->Cin + BK - 1) / BK;
+    k.planes_per_image = a->planes_per_image;
+    for (int i = 0; i < MAX_TAPS; ++i) { k.tap_dx[i] = a->tap_dx[i]; k.tap_dy[i] = a->tap_dy[i]; k.tap_plane[i] = a->tap_plane[i]; }
+    k.w_batch_mult = a->w_batch_mult;
+    k.bias = a->bias; k.res = a->res; k.res_ld = a->res_ld; k.relu = a->relu;
+    k.out_f32 = a->out_f32; k.ld_f32 = a->ld_f32;
+    k.out_hi = (__nv_bfloat16*)a->out_hi; k.out_lo = (__nv_bfloat16*)a->out_lo; k.ld_bf = a->ld_bf;
+    k.ps_hi = (__nv_bfloat16*)a->ps_hi; k.ps_lo = (__nv_bfloat16*)a->ps_lo; k.ld_ps = a->ld_ps;
+    k.l2norm = a->l2norm;
+    const int tiles_x = (a->Wo + TW - 1) / TW, tiles_y = (a->Ho + TH - 1) / TH;
+    const int total = a->B * tiles_x * tiles_y * ((a->N + bn - 1) / bn);
+    if (a->split == 3) {
+        if (bn == 256) return launch<256, 3>(ah, al, wh, wl, k, total, stream);
+        if (bn == 128) return launch<128, 3>(ah, al, wh, wl, k, total, stream);
+        return launch<64, 3>(ah, al, wh, wl, k, total, stream);
+    }
+    if (bn == 256) return launch<256, 1>(ah, al, wh, wl, k, total, stream);
+    if (bn == 128) return launch<128, 1>(ah, al, wh, wl, k, total, stream);
+    return launch<64, 1>(ah, al, wh, wl, k, total, stream);
+}
+
+// fp32 -> split bf16 planes (hi = bf16(x), lo = bf16(x - hi)); used for weights (once) and for tensors
+// produced by CUDA-core kernels that feed a tensor-core GEMM.
+__global__ void split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long long n) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    if (i + 4 <= n) {
+        float4 v = *reinterpret_cast<const float4*>(in + i);
+        __nv_bfloat16 h[4], l[4];
+        tc::split_bf16(v.x, h[0], l[0]); tc::split_bf16(v.y, h[1], l[1]);
+        tc::split_bf16(v.z, h[2], l[2]); tc::split_bf16(v.w, h[3], l[3]);
+        *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<uint2*>(h);
+        if (lo) *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<uint2*>(l);
+    } else {
+        for (; i < n; ++i) {
+            __nv_bfloat16 h, l;
+            tc::split_bf16(in[i], h, l);
+            hi[i] = h;
+            if (lo) lo[i] = l;
+        }
+    }
+}
+
+PRAM_API int pram_split_bf16(const float* in, void* hi, void* lo, long long n, cudaStream_t stream) {
+    if (!in || !hi || n <= 0 || (n % 4 && false)) return PRAM_ERR_ARG;
+    split_bf16_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, stream>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}

@@ -204,3 +204,117 @@ def sinkhorn_match(dist: Tensor, bin_score: Tensor, iters: int, threshold: float
     if return_P:
         return m0, m1, s0, s1, pws[:, :, :n + 1]
     return m0, m1, s0, s1
+
+
+# ---- tensor-core (tcgen05) implicit GEMM ----------------------------------------------------------
+
+class Split:
+    """An activation / weight tensor as error-compensated bf16 planes: x ~= hi + lo."""
+    __slots__ = ('hi', 'lo')
+
+    def __init__(self, hi: Tensor, lo: Optional[Tensor]):
+        self.hi, self.lo = hi, lo
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    def float(self) -> Tensor:
+        return self.hi.float() + (self.lo.float() if self.lo is not None else 0)
+
+
+def split_bf16(x: Tensor, with_lo: bool = True) -> Split:
+    x = _f32c(x)
+    hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi) if with_lo else None
+    call('pram_split_bf16', ptr(x), ptr(hi), ptr(lo), x.numel(), stream_ptr())
+    return Split(hi, lo)
+
+
+def empty_split(shape, device, with_lo: bool = True, zero: bool = False) -> Split:
+    mk = torch.zeros if zero else torch.empty
+    hi = mk(shape, device=device, dtype=torch.bfloat16)
+    return Split(hi, mk(shape, device=device, dtype=torch.bfloat16) if with_lo else None)
+
+
+_S1_TAPS = [(dy, dx, 0) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+# stride 2 on a 2x2 phase-split input: tap r in {0,1,2} reads phase (1,0,1) at offset (-1,0,0)
+_PH = ((1, -1), (0, 0), (1, 0))
+_S2_TAPS = [(_PH[r][1], _PH[s][1], _PH[r][0] * 2 + _PH[s][0]) for r in range(3) for s in range(3)]
+
+
+def gemm_tc(a: Split, a_ld: int, in_w: int, in_h: int, in_planes: int, cin: int, w: Split, w_planes: int,
+            b: int, ho: int, wo: int, n: int, taps, planes_per_image: int = 1, tw_log2: int = 7,
+            w_batch_mult: int = 0, bias: Optional[Tensor] = None, res: Optional[Tensor] = None, res_ld: int = 0,
+            relu: bool = False, out_f32: Optional[Tensor] = None, ld_f32: int = 0, out_bf: Optional[Split] = None,
+            ld_bf: int = 0, out_ps: Optional[Split] = None, ld_ps: int = 0, l2norm: bool = False, split: int = 3,
+            bn: int = 0):
+    """Raw launch of the tcgen05 implicit-GEMM kernel (see include/pram_b200.h: pram_gemm_tc)."""
+    A = _lib.TcArgs()
+    A.a_hi, A.a_lo, A.a_ld = a.hi.data_ptr(), (a.lo.data_ptr() if a.lo is not None else None), a_ld
+    A.in_W, A.in_H, A.in_planes, A.Cin = in_w, in_h, in_planes, cin
+    A.w_hi, A.w_lo, A.w_planes = w.hi.data_ptr(), (w.lo.data_ptr() if w.lo is not None else None), w_planes
+    A.B, A.Ho, A.Wo, A.N = b, ho, wo, n
+    A.tw_log2, A.ntaps = tw_log2, len(taps)
+    for i, (dy, dx, pl) in enumerate(taps):
+        A.tap_dy[i], A.tap_dx[i], A.tap_plane[i] = dy, dx, pl
+    A.planes_per_image, A.w_batch_mult = planes_per_image, w_batch_mult
+    A.bias = bias.data_ptr() if bias is not None else None
+    A.res, A.res_ld = (res.data_ptr() if res is not None else None), res_ld
+    A.relu = int(relu)
+    A.out_f32, A.ld_f32 = (out_f32.data_ptr() if out_f32 is not None else None), ld_f32
+    if out_bf is not None:
+        A.out_hi, A.out_lo, A.ld_bf = out_bf.hi.data_ptr(), (out_bf.lo.data_ptr() if out_bf.lo is not None else None), ld_bf
+    if out_ps is not None:
+        A.ps_hi, A.ps_lo, A.ld_ps = out_ps.hi.data_ptr(), (out_ps.lo.data_ptr() if out_ps.lo is not None else None), ld_ps
+    A.l2norm, A.split, A.bn = int(l2norm), split, bn
+    import ctypes
+    call('pram_gemm_tc', ctypes.byref(A), stream_ptr())
+
+
+def conv_tc(x: Split, w: Split, bias: Optional[Tensor], ksize: int, stride: int, relu: bool, split: int,
+            res: Optional[Tensor] = None, want_f32: bool = False, want_bf: bool = True, want_ps: bool = False,
+            l2norm: bool = False, out_shape_hw=None, bn: int = 0):
+    """3x3 / 1x1 convolution on tensor cores.  x: Split [B,H,W,Cin] NHWC (stride 1) or the 2x2 phase-split
+    tensor [B*4,ceil(H/2),ceil(W/2),Cin] of it (stride 2; then ``out_shape_hw`` = (Ho, Wo) of the conv).
+    w: Split [taps,Cout,Cin].  Returns dict with any of 'f32' [B,Ho,Wo,Cout], 'bf' Split, 'ps' Split."""
+    dev = x.hi.device
+    taps_n, cout, cin = w.shape
+    if stride == 1:
+        b, h, wd, _ = x.shape
+        ho, wo = h, wd
+        taps = _S1_TAPS if ksize == 3 else [(0, 0, 0)]
+        in_planes, ppi, in_h, in_w = b, 1, h, wd
+    else:
+        assert ksize == 3 and out_shape_hw is not None
+        b4, in_h, in_w, _ = x.shape
+        b = b4 // 4
+        ho, wo = out_shape_hw
+        taps, in_planes, ppi = _S2_TAPS, b4, 4
+    out = {}
+    f32 = torch.empty((b, ho, wo, cout), device=dev, dtype=torch.float32) if want_f32 else None
+    obf = empty_split((b, ho, wo, cout), dev, with_lo=(split == 3)) if want_bf else None
+    ops_ps = None
+    if want_ps:
+        ops_ps = empty_split((b * 4, (ho + 1) // 2, (wo + 1) // 2, cout), dev, with_lo=(split == 3),
+                             zero=bool(ho % 2 or wo % 2))
+    tw_log2 = 4 if wo >= 16 else max(0, (wo - 1).bit_length())
+    gemm_tc(x, x.shape[-1], in_w, in_h, in_planes, cin, w, taps_n, b, ho, wo, cout, taps, ppi, tw_log2, 0, bias, res,
+            cout, relu, f32, cout, obf, cout, ops_ps, cout, l2norm, split, bn)
+    if f32 is not None:
+        out['f32'] = f32
+    if obf is not None:
+        out['bf'] = obf
+    if ops_ps is not None:
+        out['ps'] = ops_ps
+    return out
+
+
+def linear_tc(a: Split, lda: int, rows: int, k: int, w: Split, n: int, bias: Optional[Tensor] = None,
+              res: Optional[Tensor] = None, ldres: int = 0, relu: bool = False, out_f32: Optional[Tensor] = None,
+              ld_f32: int = 0, out_bf: Optional[Split] = None, ld_bf: int = 0, split: int = 3, batch: int = 1,
+              w_batched: bool = False, bn: int = 0):
+    """out[rows, n] = a[rows, k] @ w[n, k]^T on tensor cores (row strides allow column slices of wider
+    buffers).  batch > 1: a is [batch, rows, lda], w is [batch, n, k] when ``w_batched``."""
+    gemm_tc(a, lda, rows, 1, batch, k, w, (batch if w_batched else 1), batch, 1, rows, n, [(0, 0, 0)], 1, 7,
+            1 if w_batched else 0, bias, res, ldres, relu, out_f32, ld_f32, out_bf, ld_bf, None, 0, False, split, bn)

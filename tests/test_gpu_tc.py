@@ -1,0 +1,105 @@
+"""tcgen05 tensor-core GEMM / implicit-GEMM convolution vs torch-CPU fp32 (the oracle's arithmetic).
+split=3 (error-compensated bf16x3): tolerance 2e-4 of the output scale; split=1 (plain bf16): 2e-2."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = {1: 2e-2, 3: 2e-4}
+
+
+@pytest.fixture(scope='module')
+def ops(lib, dev):
+    from pram_b200 import ops as _ops
+    return _ops
+
+
+def _relerr(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
+
+
+@pytest.mark.parametrize('split', [1, 3])
+@pytest.mark.parametrize('rows,k,n,bn', [(128, 64, 64, 64), (300, 256, 256, 0), (1000, 512, 768, 0), (77, 128, 113, 0),
+                                         (4096, 256, 256, 128)])
+def test_linear_tc(ops, dev, split, rows, k, n, bn):
+    g = torch.Generator().manual_seed(rows + k + n)
+    a = torch.randn(rows, k, generator=g)
+    w = torch.randn(n, k, generator=g) / k ** 0.5
+    bias = torch.randn(n, generator=g)
+    res = torch.randn(rows, n, generator=g)
+    ref = torch.relu(a @ w.t() + bias + res)
+    A = ops.split_bf16(a.to(dev), split == 3)
+    Wt = ops.split_bf16(w.to(dev), split == 3)
+    out = torch.zeros(rows, n, device=dev)
+    obf = ops.empty_split((rows, n), dev, split == 3) if n % 32 == 0 else None
+    ops.linear_tc(A, k, rows, k, Wt, n, bias.to(dev), res.to(dev), n, True, out, n, obf, n, split=split, bn=bn)
+    torch.cuda.synchronize()
+    assert _relerr(out.cpu(), ref) < TOL[split]
+    if obf is not None:
+        assert _relerr(obf.float().cpu(), ref) < (TOL[split] if split == 3 else 3e-2)
+
+
+@pytest.mark.parametrize('split', [1, 3])
+@pytest.mark.parametrize('b,h,w,cin,cout', [(2, 24, 40, 64, 128), (1, 30, 40, 256, 256), (3, 17, 21, 128, 64)])
+def test_conv3x3_s1_tc(ops, dev, split, b, h, w, cin, cout):
+    g = torch.Generator().manual_seed(h * w + cin)
+    x = torch.randn(b, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    bias = torch.randn(cout, generator=g)
+    ref = torch.relu(torch.nn.functional.conv2d(x, wt, bias, padding=1))
+    X = ops.split_bf16(x.permute(0, 2, 3, 1).contiguous().to(dev), split == 3)
+    Wp = ops.split_bf16(wt.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous().to(dev), split == 3)
+    out = ops.conv_tc(X, Wp, bias.to(dev), 3, 1, True, split, want_f32=True, want_bf=True, want_ps=True)
+    torch.cuda.synchronize()
+    assert _relerr(out['f32'].permute(0, 3, 1, 2).cpu(), ref) < TOL[split]
+    assert _relerr(out['bf'].float().permute(0, 3, 1, 2).cpu(), ref) < max(TOL[split], 1e-2 if split == 1 else 0)
+    # phase-split copy holds the same values: plane (y&1)*2+(x&1) at (y>>1, x>>1)
+    ps = out['ps'].float().view(b, 2, 2, (h + 1) // 2, (w + 1) // 2, cout).cpu()
+    full = out['bf'].float().cpu()
+    for py in range(2):
+        for px in range(2):
+            sub = full[:, py::2, px::2]
+            assert torch.equal(ps[:, py, px, :sub.shape[1], :sub.shape[2]], sub)
+
+
+@pytest.mark.parametrize('split', [1, 3])
+@pytest.mark.parametrize('b,h,w,cin,cout', [(2, 24, 40, 64, 64), (1, 31, 45, 128, 128)])
+def test_conv3x3_s2_tc(ops, dev, split, b, h, w, cin, cout):
+    """stride-2 convolution fed by the phase-split tensor a stride-1 conv produced."""
+    g = torch.Generator().manual_seed(h + w + cin)
+    x = torch.randn(b, cin, h, w, generator=g)
+    w1 = torch.randn(cin, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    w2 = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    mid = torch.relu(torch.nn.functional.conv2d(x, w1, None, padding=1))
+    ref = torch.nn.functional.conv2d(mid, w2, None, stride=2, padding=1)
+    X = ops.split_bf16(x.permute(0, 2, 3, 1).contiguous().to(dev), split == 3)
+    W1 = ops.split_bf16(w1.permute(2, 3, 0, 1).reshape(9, cin, cin).contiguous().to(dev), split == 3)
+    W2 = ops.split_bf16(w2.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous().to(dev), split == 3)
+    o1 = ops.conv_tc(X, W1, None, 3, 1, True, split, want_bf=False, want_ps=True)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    o2 = ops.conv_tc(o1['ps'], W2, None, 3, 2, False, split, want_f32=True, want_bf=False, out_shape_hw=(ho, wo))
+    torch.cuda.synchronize()
+    assert o2['f32'].shape == (b, ho, wo, cout)
+    assert _relerr(o2['f32'].permute(0, 3, 1, 2).cpu(), ref) < 2 * TOL[split]
+
+
+def test_bmm_and_l2norm_tc(ops, dev):
+    g = torch.Generator().manual_seed(0)
+    bsz, m, n, k = 3, 200, 150, 256
+    a = torch.randn(bsz, m, k, generator=g)
+    b = torch.randn(bsz, n, k, generator=g)
+    ref = torch.einsum('bmd,bnd->bmn', a, b)
+    A, Bm = ops.split_bf16(a.to(dev)), ops.split_bf16(b.to(dev))
+    out = torch.zeros(bsz, m, n, device=dev)
+    ops.linear_tc(A, k, m, k, Bm, n, out_f32=out, ld_f32=n, split=3, batch=bsz, w_batched=True)
+    torch.cuda.synchronize()
+    assert _relerr(out.cpu(), ref) < 2e-4
+    # fused row L2 normalisation (descriptor head)
+    w = torch.randn(128, k, generator=g) / 16
+    bias = torch.randn(128, generator=g) * 0.1
+    ref = torch.nn.functional.normalize(a[0] @ w.t() + bias, dim=-1)
+    out = torch.zeros(m, 128, device=dev)
+    from pram_b200.ops import gemm_tc
+    gemm_tc(ops.split_bf16(a[0].to(dev)), k, m, 1, 1, k, ops.split_bf16(w.to(dev)), 1, 1, 1, m, 128, [(0, 0, 0)],
+            bias=bias.to(dev), out_f32=out, ld_f32=128, l2norm=True, split=3)
+    torch.cuda.synchronize()
+    assert _relerr(out.cpu(), ref) < 2e-4
