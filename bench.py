@@ -31,6 +31,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=32, help='frames per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16', 'fp32'])
     return ap.parse_args()
 
 
@@ -185,6 +186,8 @@ def run_ours(args):
     vit = SegNetViT({'n_class': NCLASS, 'n_layers': 15, 'output_dim': 1024, 'descriptor_dim': 256})
     vit.load_state_dict(sd_vit, strict=True)
     gml = GML({}); gml.load_state_dict(sd_gml, strict=True)
+    for m_ in (sfd2, vit, gml):
+        m_.set_precision(args.precision)
     pipe = LocalizationPipeline(sfd2, vit, gml, max_keypoints=KPTS, device=dev)
 
     B = args.batch
@@ -266,7 +269,7 @@ def run_ours(args):
         print(json.dumps({
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': pipe.sfd2.compute_dtype if hasattr(pipe.sfd2, 'compute_dtype') else 'f32',
+            'vs_baseline': None, 'dtype': pipe.sfd2.compute_dtype,
             'data': f'synthetic polygon frames; {tag}; seeded random SegNetViT',
             'config': {'workload': workload_name(B), 'frames_per_gpu_per_step': B, 'l2': 'flushed between timed steps (256 MiB memset)',
                        'matched_fraction': matched},
@@ -292,10 +295,16 @@ def roofline_probe(pipe, frames_dev, dev):
     B = frames_dev.shape[0]
     pk = pipe.sfd2.prepare()
     x = torch.randn(B, H // 4, W // 4, 256, device=dev)
-    fn = getattr(pipe.sfd2, 'probe_conv3b', None)
-    if fn is None:
+    prec = pipe.sfd2.precision
+    if prec == 'fp32':
         def fn(inp):
             return ops.conv_f32(inp, pk['conv3b.w'], pk['conv3b.b'], 3, 1, True)
+    else:
+        split = 3 if prec == 'bf16x3' else 1
+        xs = ops.split_bf16(x, split == 3)
+
+        def fn(inp):
+            return ops.conv_tc(xs, pk['conv3b.tc'], pk['conv3b.b'], 3, 1, True, split)
     for _ in range(2):
         fn(x)
     reps = 5
@@ -309,7 +318,9 @@ def roofline_probe(pipe, frames_dev, dev):
     ms = e0.elapsed_time(e1) / reps
     flops = 2.0 * B * (H // 4) * (W // 4) * 256 * 2304
     ach = flops / (ms * 1e-3) / 1e12
-    return {'bound': 'tensor', 'kernel': 'conv3x3 256->256 @120x160 (conv3b)', 'achieved': ach, 'peak': peak,
+    mma_mult = 3 if prec == 'bf16x3' else 1
+    return {'bound': 'tensor', 'kernel': f'conv3x3 256->256 @120x160 (conv3b), precision {prec}', 'achieved': ach,
+            'tensor_flops_issued_per_algorithmic_flop': mma_mult, 'peak': peak,
             'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': None,
             'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst)' if peaks else 'fallback 1.59 PFLOP/s'}
 

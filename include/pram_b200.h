@@ -85,12 +85,24 @@ int pram_linear_f32(const float* a, long long lda, const float* w, const float* 
 int pram_gconv3x3_f32(const float* in, const float* w, const float* bias, float* out, int B, int H, int W,
                       int groups, int relu, pram_stream_t stream);
 
+int pram_gconv3x3_split(const float* in, const float* w, const float* bias, float* out_f32, void* out_hi,
+                        void* out_lo, int B, int H, int W, int groups, int relu, pram_stream_t stream);
+
+/* K1 first layer: conv1a 3->64 + BN + ReLU straight from the NCHW image, output as split-bf16 NHWC in
+ * the 2x2 phase-split layout consumed by the stride-2 conv1b (and/or fp32 NHWC).  nets/sfd2.py:141.
+ * w[27][64] (tap-major (r,s,c)), bias[64]. */
+int pram_conv1a(const float* img_nchw, const float* w, const float* bias, int B, int H, int W, void* ps_hi,
+                void* ps_lo, float* out_f32, pram_stream_t stream);
+
 /* F.normalize over the channel axis of an NHWC map.  nets/sfd2.py:333. */
 int pram_l2norm_rows(const float* in, float* out, long long rows, int C, pram_stream_t stream);
 
 /* LayerNorm + exact GELU.  nets/segnetvit.py:92-93. */
 int pram_layernorm_gelu(const float* in, const float* gamma, const float* beta, float* out, long long rows, int C,
                         int gelu, pram_stream_t stream);
+
+int pram_layernorm_gelu_split(const float* in, const float* gamma, const float* beta, float* out_f32, void* out_hi,
+                              void* out_lo, long long rows, int C, int gelu, pram_stream_t stream);
 
 /* qkv split + rotary embedding -> q,k,v [B][heads][N][64].  nets/segnetvit.py:15-23, 98-103. */
 int pram_rotary_split(const float* qkv, int nparts, int B, int N, int heads, const float* cosb, const float* sinb,

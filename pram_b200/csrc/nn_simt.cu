@@ -210,7 +210,8 @@ constexpr int GC_PX = 4;
 __global__ void __launch_bounds__(256) gconv3x3_kernel(const float* __restrict__ in,
                                                        const float* __restrict__ w,  // [9][8][8][G]
                                                        const float* __restrict__ bias,
-                                                       float* __restrict__ out, int B, int H, int W,
+                                                       float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
+                                                       __nv_bfloat16* __restrict__ out_lo, int B, int H, int W,
                                                        int G, int relu) {
     extern __shared__ float ws[];
     const int C = G * 8;
@@ -270,15 +271,43 @@ __global__ void __launch_bounds__(256) gconv3x3_kernel(const float* __restrict__
             float t = acc[p][co] + (bias ? bias[g * 8 + co] : 0.f);
             o[co] = relu ? fmaxf(t, 0.f) : t;
         }
-        float* op = out + (((long long)b * H + y) * W + x) * C + g * 8;
-        *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(op + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        const long long off = (((long long)b * H + y) * W + x) * C + g * 8;
+        if (out) {
+            *reinterpret_cast<float4*>(out + off) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(out + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (out_hi) {
+            __nv_bfloat16 h[8], l[8];
+#pragma unroll
+            for (int co = 0; co < 8; ++co) {
+                h[co] = __float2bfloat16_rn(o[co]);
+                l[co] = __float2bfloat16_rn(o[co] - __bfloat162float(h[co]));
+            }
+            *reinterpret_cast<uint4*>(out_hi + off) = *reinterpret_cast<uint4*>(h);
+            if (out_lo) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<uint4*>(l);
+        }
     }
 }
 
+static int gconv_launch(const float* in, const float* w, const float* bias, float* out, void* out_hi, void* out_lo,
+                        int B, int H, int W, int groups, int relu, cudaStream_t stream);
+
 PRAM_API int pram_gconv3x3_f32(const float* in, const float* w, const float* bias, float* out, int B,
                                int H, int W, int groups, int relu, cudaStream_t stream) {
-    if (!in || !w || !out || groups != 32) return PRAM_ERR_UNSUPPORTED;
+    if (!out) return PRAM_ERR_ARG;
+    return gconv_launch(in, w, bias, out, nullptr, nullptr, B, H, W, groups, relu, stream);
+}
+
+// same, with the result also (or only) emitted as split bf16 planes for a following tensor-core GEMM
+PRAM_API int pram_gconv3x3_split(const float* in, const float* w, const float* bias, float* out_f32, void* out_hi,
+                                 void* out_lo, int B, int H, int W, int groups, int relu, cudaStream_t stream) {
+    if (!out_f32 && !out_hi) return PRAM_ERR_ARG;
+    return gconv_launch(in, w, bias, out_f32, out_hi, out_lo, B, H, W, groups, relu, stream);
+}
+
+static int gconv_launch(const float* in, const float* w, const float* bias, float* out, void* out_hi, void* out_lo,
+                        int B, int H, int W, int groups, int relu, cudaStream_t stream) {
+    if (!in || !w || groups != 32) return PRAM_ERR_UNSUPPORTED;
     size_t smem = sizeof(float) * 9 * 64 * groups;
     static bool attr_set = false;
     if (!attr_set) {
@@ -288,7 +317,8 @@ PRAM_API int pram_gconv3x3_f32(const float* in, const float* w, const float* bia
     }
     long long quads = (long long)B * H * cdiv(W, GC_PX);
     int qpb = 256 / groups;
-    gconv3x3_kernel<<<cdiv(quads, qpb), 256, smem, stream>>>(in, w, bias, out, B, H, W, groups, relu);
+    gconv3x3_kernel<<<cdiv(quads, qpb), 256, smem, stream>>>(in, w, bias, out, (__nv_bfloat16*)out_hi,
+                                                             (__nv_bfloat16*)out_lo, B, H, W, groups, relu);
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
 }
@@ -320,6 +350,7 @@ PRAM_API int pram_l2norm_rows(const float* in, float* out, long long rows, int C
 // ------------------------------------------------------------------------------------------
 __global__ void layernorm_gelu_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, float* __restrict__ out,
+                                      __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
                                       long long rows, int C, int gelu) {
     long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -334,14 +365,29 @@ __global__ void layernorm_gelu_kernel(const float* __restrict__ in, const float*
     for (int c = lane; c < C; c += 32) {
         float v = (p[c] - mean) * rstd * gamma[c] + beta[c];
         if (gelu) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-        out[row * C + c] = v;
+        if (out) out[row * C + c] = v;
+        if (out_hi) {
+            __nv_bfloat16 h = __float2bfloat16_rn(v);
+            out_hi[row * C + c] = h;
+            if (out_lo) out_lo[row * C + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
     }
 }
 
 PRAM_API int pram_layernorm_gelu(const float* in, const float* gamma, const float* beta, float* out,
                                  long long rows, int C, int gelu, cudaStream_t stream) {
     if (!in || !out || !gamma || !beta) return PRAM_ERR_ARG;
-    layernorm_gelu_kernel<<<cdiv(rows * 32, 256), 256, 0, stream>>>(in, gamma, beta, out, rows, C, gelu);
+    layernorm_gelu_kernel<<<cdiv(rows * 32, 256), 256, 0, stream>>>(in, gamma, beta, out, nullptr, nullptr, rows, C, gelu);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+PRAM_API int pram_layernorm_gelu_split(const float* in, const float* gamma, const float* beta, float* out_f32,
+                                       void* out_hi, void* out_lo, long long rows, int C, int gelu,
+                                       cudaStream_t stream) {
+    if (!in || !gamma || !beta || (!out_f32 && !out_hi)) return PRAM_ERR_ARG;
+    layernorm_gelu_kernel<<<cdiv(rows * 32, 256), 256, 0, stream>>>(in, gamma, beta, out_f32, (__nv_bfloat16*)out_hi,
+                                                                   (__nv_bfloat16*)out_lo, rows, C, gelu);
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
 }
@@ -518,6 +564,84 @@ PRAM_API int pram_attention_f32(const float* Q, const float* K, const float* V, 
     if (colmean) PRAM_CUDA(cudaMemsetAsync(colmean, 0, sizeof(float) * (size_t)B * Nk, stream));
     dim3 grid(cdiv(Nq, AT_BQ), B * heads);
     attention_kernel<<<grid, 256, 0, stream>>>(Q, K, V, B, heads, Nq, Nk, scale, out, out_stride, colmean);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// conv1a: 3 -> 64 channels, 3x3, BN folded, ReLU (reference nets/sfd2.py:141).  13 FLOP/B, i.e.
+// HBM-bound: reads the NCHW fp32 image directly (coalesced along x), keeps the 27x64 weights in shared
+// memory (broadcast reads), and writes split-bf16 NHWC output in the 2x2 PHASE-SPLIT layout that lets
+// the following stride-2 convolution (conv1b) fetch its taps with unit-stride TMA boxes.
+// One thread = one pixel x 64 channels (each output line of 128 B written whole by one thread).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) conv1a_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, int B, int H, int W,
+                                                     __nv_bfloat16* __restrict__ ps_hi, __nv_bfloat16* __restrict__ ps_lo,
+                                                     float* __restrict__ out_f32) {
+    __shared__ __align__(16) float ws[27 * 64];
+    __shared__ float bs[64];
+    for (int i = threadIdx.x; i < 27 * 64; i += 128) ws[i] = w[i];
+    if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    float in[27];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int iy = y + r - 1, ix = x + q - 1;
+                // tap-major order (r, q, c) to match w[tap][ci][co]
+                in[(r * 3 + q) * 3 + c] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                                              ? __ldg(img + (((long long)b * 3 + c) * H + iy) * W + ix) : 0.f;
+            }
+    float acc[64];
+#pragma unroll
+    for (int co = 0; co < 64; ++co) acc[co] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+        const float a = in[t];
+#pragma unroll
+        for (int co = 0; co < 64; co += 4) {
+            const float4 wv = *reinterpret_cast<const float4*>(&ws[t * 64 + co]);
+            acc[co] = fmaf(a, wv.x, acc[co]);
+            acc[co + 1] = fmaf(a, wv.y, acc[co + 1]);
+            acc[co + 2] = fmaf(a, wv.z, acc[co + 2]);
+            acc[co + 3] = fmaf(a, wv.w, acc[co + 3]);
+        }
+    }
+#pragma unroll
+    for (int co = 0; co < 64; ++co) acc[co] = fmaxf(acc[co] + bs[co], 0.f);
+    if (out_f32) {
+        float* op = out_f32 + (((long long)b * H + y) * W + x) * 64;
+#pragma unroll
+        for (int co = 0; co < 64; co += 4) *reinterpret_cast<float4*>(op + co) = make_float4(acc[co], acc[co + 1], acc[co + 2], acc[co + 3]);
+    }
+    if (ps_hi) {
+        const int Hp = (H + 1) >> 1, Wp = (W + 1) >> 1;
+        const long long off = ((((long long)(b * 4 + (y & 1) * 2 + (x & 1))) * Hp + (y >> 1)) * Wp + (x >> 1)) * 64;
+#pragma unroll
+        for (int co = 0; co < 64; co += 8) {
+            __nv_bfloat16 h[8], l[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                h[j] = __float2bfloat16_rn(acc[co + j]);
+                l[j] = __float2bfloat16_rn(acc[co + j] - __bfloat162float(h[j]));
+            }
+            *reinterpret_cast<uint4*>(ps_hi + off + co) = *reinterpret_cast<uint4*>(h);
+            if (ps_lo) *reinterpret_cast<uint4*>(ps_lo + off + co) = *reinterpret_cast<uint4*>(l);
+        }
+    }
+}
+
+PRAM_API int pram_conv1a(const float* img_nchw, const float* w, const float* bias, int B, int H, int W, void* ps_hi,
+                         void* ps_lo, float* out_f32, cudaStream_t stream) {
+    if (!img_nchw || !w || !bias || (!ps_hi && !out_f32)) return PRAM_ERR_ARG;
+    dim3 grid(cdiv(W, 128), H, B);
+    conv1a_kernel<<<grid, 128, 0, stream>>>(img_nchw, w, bias, B, H, W, (__nv_bfloat16*)ps_hi, (__nv_bfloat16*)ps_lo, out_f32);
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
 }

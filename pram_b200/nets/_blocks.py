@@ -59,33 +59,50 @@ def _c(t: torch.Tensor) -> torch.Tensor:
     return t.detach().float().contiguous()
 
 
+def _tc(t: torch.Tensor) -> ops.Split:
+    """[N,K] Linear weight -> split-bf16 planes (the tensor-core operand layout is torch's own [out,in])."""
+    return ops.split_bf16(_c(t))
+
+
 def pack_self(blk: SelfBlockParams) -> Dict[str, torch.Tensor]:
     """De-interleave the qkv rows once: reference feature index = head*192 + dim*3 + {q,k,v}
     (``unflatten(-1, (heads, -1, 3))``, nets/segnetvit.py:99) -> rows ordered (part, head, dim)."""
     w, b = blk.qkv.weight.detach(), blk.qkv.bias.detach()
     idx = torch.arange(3 * HEADS * HDIM, device=w.device).view(HEADS, HDIM, 3).permute(2, 0, 1).reshape(-1)
     return {'qkv.w': _c(w[idx]), 'qkv.b': _c(b[idx]), 'proj.w': _c(blk.proj.weight), 'proj.b': _c(blk.proj.bias),
-            **pack_mlp(blk.mlp, 'mlp')}
+            'qkv.tc': _tc(w[idx]), 'proj.tc': _tc(blk.proj.weight), **pack_mlp(blk.mlp, 'mlp')}
 
 
 def pack_cross(blk: CrossBlockParams) -> Dict[str, torch.Tensor]:
     """to_qk and to_v fused into one [512,256] projection (rows: qk | v)."""
-    return {'qkv.w': _c(torch.cat([blk.to_qk.weight.detach(), blk.to_v.weight.detach()], 0)),
+    wqkv = torch.cat([blk.to_qk.weight.detach(), blk.to_v.weight.detach()], 0)
+    return {'qkv.w': _c(wqkv), 'qkv.tc': _tc(wqkv),
             'qkv.b': _c(torch.cat([blk.to_qk.bias.detach(), blk.to_v.bias.detach()], 0)),
-            'proj.w': _c(blk.proj.weight), 'proj.b': _c(blk.proj.bias), **pack_mlp(blk.mlp, 'mlp')}
+            'proj.w': _c(blk.proj.weight), 'proj.b': _c(blk.proj.bias), 'proj.tc': _tc(blk.proj.weight),
+            **pack_mlp(blk.mlp, 'mlp')}
 
 
 def pack_mlp(mlp: nn.Sequential, pre: str) -> Dict[str, torch.Tensor]:
-    return {pre + '.0.w': _c(mlp[0].weight), pre + '.0.b': _c(mlp[0].bias), pre + '.ln.g': _c(mlp[1].weight),
-            pre + '.ln.b': _c(mlp[1].bias), pre + '.3.w': _c(mlp[3].weight), pre + '.3.b': _c(mlp[3].bias)}
+    d = {pre + '.0.w': _c(mlp[0].weight), pre + '.0.b': _c(mlp[0].bias), pre + '.ln.g': _c(mlp[1].weight),
+         pre + '.ln.b': _c(mlp[1].bias), pre + '.3.w': _c(mlp[3].weight), pre + '.3.b': _c(mlp[3].bias)}
+    if mlp[0].weight.shape[1] % 8 == 0 and mlp[3].weight.shape[1] % 8 == 0:
+        d[pre + '.0.tc'] = _tc(mlp[0].weight)
+        d[pre + '.3.tc'] = _tc(mlp[3].weight)
+    return d
 
 
 class Workspace:
     """Per-call scratch for T tokens (all fp32): two concat buffers, qkv, q/k/v, ctx, hidden."""
 
-    def __init__(self, tokens: int, device):
+    def __init__(self, tokens: int, device, split: int = 0):
         e = lambda *s: torch.empty(s, device=device, dtype=torch.float32)
         self.T = tokens
+        self.split = split  # 0: fp32 CUDA-core path; 1 / 3: tcgen05 path with bf16 / bf16x3 operands
+        if split:
+            lo = split == 3
+            self.cat_bf = [ops.empty_split((tokens, 2 * D), device, lo), ops.empty_split((tokens, 2 * D), device, lo)]
+            self.ctx_bf = ops.empty_split((tokens, D), device, lo)
+            self.hid_bf = ops.empty_split((tokens, 2 * D), device, lo)
         self.cat = [e(tokens, 2 * D), e(tokens, 2 * D)]
         self.cur = 0
         self.qkv = e(tokens, 3 * D)
@@ -96,6 +113,20 @@ class Workspace:
     @property
     def x(self) -> torch.Tensor:  # current activations: left half of the current concat buffer
         return self.cat[self.cur]
+
+    @property
+    def x_bf(self) -> ops.Split:
+        return self.cat_bf[self.cur]
+
+
+def linear(ws: Workspace, a_f32, a_bf, lda: int, rows: int, k: int, n: int, pk, name: str, out_f32=None, ld_f32: int = 0,
+           out_bf=None, ld_bf: int = 0, res=None, ldres: int = 0):
+    """One Linear layer on whichever path the workspace selects (fp32 CUDA cores / tcgen05)."""
+    if ws.split:
+        ops.linear_tc(a_bf, lda, rows, k, pk[name + '.tc'], n, pk[name + '.b'], res, ldres, False, out_f32, ld_f32,
+                      out_bf, ld_bf, split=ws.split)
+    else:
+        ops.linear_f32(a_f32, lda, pk[name + '.w'], pk[name + '.b'], out_f32, ld_f32, rows, k, n, res=res, ldres=ldres)
 
 
 def run_mlp(pk: Dict[str, torch.Tensor], pre: str, a: torch.Tensor, lda: int, rows: int, d_in: int, d_hid: int,
@@ -112,8 +143,17 @@ def _finish_block(ws: Workspace, pk: Dict[str, torch.Tensor]):
     T = ws.T
     cat = ws.cat[ws.cur]
     nxt = ws.cat[ws.cur ^ 1]
-    ops.linear_f32(ws.ctx, D, pk['proj.w'], pk['proj.b'], cat[:, D:], 2 * D, T, D, D)
-    run_mlp(pk, 'mlp', cat, 2 * D, T, 2 * D, 2 * D, D, ws.hid, nxt, 2 * D, res=cat, ldres=2 * D)
+    if not ws.split:
+        ops.linear_f32(ws.ctx, D, pk['proj.w'], pk['proj.b'], cat[:, D:], 2 * D, T, D, D)
+        run_mlp(pk, 'mlp', cat, 2 * D, T, 2 * D, 2 * D, D, ws.hid, nxt, 2 * D, res=cat, ldres=2 * D)
+    else:
+        cbf, nbf = ws.cat_bf[ws.cur], ws.cat_bf[ws.cur ^ 1]
+        ops.split_bf16_into(ws.ctx, ws.ctx_bf)
+        linear(ws, None, ws.ctx_bf, D, T, D, D, pk, 'proj', out_bf=ops.split_cols(cbf, D), ld_bf=2 * D)
+        linear(ws, None, cbf, 2 * D, T, 2 * D, 2 * D, pk, 'mlp.0', out_f32=ws.hid, ld_f32=2 * D)
+        ops.layernorm_gelu_split(ws.hid, pk['mlp.ln.g'], pk['mlp.ln.b'], 2 * D, ws.hid_bf)
+        linear(ws, None, ws.hid_bf, 2 * D, T, 2 * D, D, pk, 'mlp.3', out_f32=nxt, ld_f32=2 * D, out_bf=nbf, ld_bf=2 * D,
+               res=cat, ldres=2 * D)
     ws.cur ^= 1
 
 
@@ -123,7 +163,7 @@ def self_block(ws: Workspace, pk: Dict[str, torch.Tensor], segments: Sequence[Tu
     attention is computed independently inside each (segment, batch element).
     Reference nets/segnetvit.py:97-106 == nets/gml.py:128-137."""
     T = ws.T
-    ops.linear_f32(ws.x, 2 * D, pk['qkv.w'], pk['qkv.b'], ws.qkv, 3 * D, T, D, 3 * D)
+    linear(ws, ws.x, ws.x_bf if ws.split else None, 2 * D, T, D, 3 * D, pk, 'qkv', out_f32=ws.qkv, ld_f32=3 * D)
     for si, (off, b, n) in enumerate(segments):
         sl = slice(off, off + b * n)
         ops.rotary_split(ws.qkv[sl], 3, b, n, HEADS, cos[sl], sin[sl], 1.0, ws.q[sl], ws.k[sl], ws.v[sl])
@@ -140,7 +180,7 @@ def cross_block(ws: Workspace, pk: Dict[str, torch.Tensor], seg0: Tuple[int, int
     set 0, mean attn01 -> per token of set 1] (reference nets/adagml.py:229)."""
     T = ws.T
     qkv = ws.qkv.view(-1)[:T * 2 * D].view(T, 2 * D)  # (qk | v) rows, 512 wide
-    ops.linear_f32(ws.x, 2 * D, pk['qkv.w'], pk['qkv.b'], qkv, 2 * D, T, D, 2 * D)
+    linear(ws, ws.x, ws.x_bf if ws.split else None, 2 * D, T, D, 2 * D, pk, 'qkv', out_f32=qkv, ld_f32=2 * D)
     (o0, b, m), (o1, _, n) = seg0, seg1
     s0, s1 = slice(o0, o0 + b * m), slice(o1, o1 + b * n)
     sc = (HDIM ** -0.5) ** 0.5  # applied to both qk0 and qk1 (nets/gml.py:174)
@@ -153,3 +193,29 @@ def cross_block(ws: Workspace, pk: Dict[str, torch.Tensor], seg0: Tuple[int, int
     ops.attention_f32(ws.q[s1], ws.q[s0], ws.v[s0], b, HEADS, n, m, 1.0, ws.ctx[s1], D,
                       None if colmeans is None else colmeans[0])
     _finish_block(ws, pk)
+
+
+def input_tokens(ws: Workspace, pk, x: torch.Tensor, row0: int):
+    """input_proj: x [rows, dd] fp32 -> rows [row0, row0+rows) of the current activation buffers."""
+    rows, dd = x.shape
+    x = x.float()
+    x = x if x.is_contiguous() else x.contiguous()
+    if ws.split:
+        ops.linear_tc(ops.split_bf16(x, ws.split == 3), dd, rows, dd, pk['in.tc'], D, pk['in.b'], None, 0, False,
+                      ws.x[row0:], 2 * D, ops.split_rows(ws.x_bf, row0), 2 * D, split=ws.split)
+    else:
+        ops.linear_f32(x, dd, pk['in.w'], pk['in.b'], ws.x[row0:], 2 * D, rows, dd, D)
+
+
+def head_mlp(ws: Workspace, pk, pre: str, d_hid: int, d_out: int, out: torch.Tensor):
+    """Linear(256->d_hid) -> LN -> GELU -> Linear(d_hid->d_out) on the current activations (seg head)."""
+    T = ws.T
+    hid = torch.empty((T, d_hid), device=out.device, dtype=torch.float32)
+    if ws.split and (pre + '.0.tc') in pk:
+        linear(ws, None, ws.x_bf, 2 * D, T, D, d_hid, pk, pre + '.0', out_f32=hid, ld_f32=d_hid)
+        hb = ops.empty_split((T, d_hid), out.device, ws.split == 3)
+        ops.layernorm_gelu_split(hid, pk[pre + '.ln.g'], pk[pre + '.ln.b'], d_hid, hb)
+        linear(ws, None, hb, d_hid, T, d_hid, d_out, pk, pre + '.3', out_f32=out, ld_f32=d_out)
+    else:
+        run_mlp(pk, pre, ws.x, 2 * D, T, D, d_hid, d_out, hid, out, d_out)
+    return out

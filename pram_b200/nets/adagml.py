@@ -81,7 +81,7 @@ class AdaGML(GML):
         dev = d0.device
         m_full, n_full = d0.shape[1], d1.shape[1]
         cos, sin = self._encode(pk, data)
-        ws = B.Workspace(m_full + n_full, dev)
+        ws = B.Workspace(m_full + n_full, dev, self._split)
         self._input_tokens(pk, ws, d0, d1)
         ind0 = torch.arange(m_full, device=dev)
         ind1 = torch.arange(n_full, device=dev)
@@ -115,8 +115,13 @@ class AdaGML(GML):
                     if m == 0 or n == 0:
                         raise ValueError('AdaGML pruned a keypoint set to zero tokens (the reference raises at '
                                          'nets/adagml.py:500 in the same situation)')
-                    ws = B.Workspace(m + n, dev)
+                    ws = B.Workspace(m + n, dev, self._split)
                     ws.x[:, :256] = x
+                    if ws.split:
+                        xs = ops.split_bf16(x, ws.split == 3)
+                        ws.x_bf.hi[:, :256] = xs.hi
+                        if xs.lo is not None:
+                            ws.x_bf.lo[:, :256] = xs.lo
                 if stop:
                     break
         dist = self._distance(pk, ni, ws, 1, m, n)

@@ -61,7 +61,17 @@ class GML(nn.Module):
         self.out_proj = nn.ModuleList([nn.Linear(256, 256) for _ in range(self.n_layers)])
         self.register_parameter('bin_score', nn.Parameter(torch.tensor(1.)))
         self._packed = None
+        self.precision = 'bf16x3'  # 'bf16x3' | 'bf16' (tcgen05) | 'fp32' (CUDA cores); see nets/sfd2.py
         self.eval()
+
+    def set_precision(self, precision: str):
+        assert precision in ('bf16x3', 'bf16', 'fp32')
+        self.precision = precision
+        return self
+
+    @property
+    def _split(self) -> int:
+        return {'fp32': 0, 'bf16': 1, 'bf16x3': 3}[self.precision]
 
     def _apply(self, fn, *a, **k):
         self._packed = None
@@ -79,6 +89,8 @@ class GML(nn.Module):
                 'self': [B.pack_self(l) for l in self.self_attn],
                 'cross': [B.pack_cross(l) for l in self.cross_attn],
                 'in.w': B._c(self.input_proj.weight), 'in.b': B._c(self.input_proj.bias),
+                'in.tc': B._tc(self.input_proj.weight),
+                'out.tc': [B._tc(l.weight * 0.25) for l in self.out_proj],
                 'Wr': B._c(self.poseenc.Wr.weight),
                 # out_proj(desc) / d**.25 with d = 256: the factor 1/4 is exact, folded into the weights
                 'out': [(B._c(l.weight * 0.25), B._c(l.bias * 0.25)) for l in self.out_proj],
@@ -111,19 +123,24 @@ class GML(nn.Module):
     def _input_tokens(pk, ws, d0, d1):
         b, m, dd = d0.shape
         n = d1.shape[1]
-        x0 = d0.float().reshape(b * m, dd).contiguous()
-        x1 = d1.float().reshape(b * n, dd).contiguous()
-        ops.linear_f32(x0, dd, pk['in.w'], pk['in.b'], ws.x, 2 * B.D, b * m, dd, B.D)
-        ops.linear_f32(x1, dd, pk['in.w'], pk['in.b'], ws.x[b * m:], 2 * B.D, b * n, dd, B.D)
+        B.input_tokens(ws, pk, d0.reshape(b * m, dd), 0)
+        B.input_tokens(ws, pk, d1.reshape(b * n, dd), b * m)
 
     @staticmethod
     def _distance(pk, layer, ws, b, m, n):
+        """mdesc = out_proj(desc)/4 for both sets, dist[b] = mdesc0[b] . mdesc1[b]^T (nets/gml.py:278-282)."""
         T = ws.T
         w, bias = pk['out'][layer]
-        md = ws.qkv.view(-1)[:T * B.D].view(T, B.D)
-        ops.linear_f32(ws.x, 2 * B.D, w, bias, md, B.D, T, B.D, B.D)
-        dist = torch.empty((b, m, n), device=md.device, dtype=torch.float32)
-        ops.linear_f32(md, B.D, md[b * m:], None, dist, n, m, B.D, n, batch=b, a_bs=m * B.D, w_bs=n * B.D, o_bs=m * n)
+        dist = torch.empty((b, m, n), device=ws.x.device, dtype=torch.float32)
+        if ws.split:
+            md = ops.empty_split((T, B.D), ws.x.device, ws.split == 3)
+            ops.linear_tc(ws.x_bf, 2 * B.D, T, B.D, pk['out.tc'][layer], B.D, bias, out_bf=md, ld_bf=B.D, split=ws.split)
+            ops.linear_tc(md, B.D, m, B.D, ops.split_rows(md, b * m), n, out_f32=dist, ld_f32=n, split=ws.split,
+                          batch=b, w_batched=True)
+        else:
+            md = ws.qkv.view(-1)[:T * B.D].view(T, B.D)
+            ops.linear_f32(ws.x, 2 * B.D, w, bias, md, B.D, T, B.D, B.D)
+            ops.linear_f32(md, B.D, md[b * m:], None, dist, n, m, B.D, n, batch=b, a_bs=m * B.D, w_bs=n * B.D, o_bs=m * n)
         return dist
 
     @torch.no_grad()
@@ -136,7 +153,7 @@ class GML(nn.Module):
         if m == 0 or n == 0:
             raise ValueError('GML needs at least one keypoint per set (the reference fails on empty sets too)')
         cos, sin = self._encode(pk, data)
-        ws = B.Workspace(b * (m + n), d0.device)
+        ws = B.Workspace(b * (m + n), d0.device, self._split)
         self._input_tokens(pk, ws, d0, d1)
         seg0, seg1 = (0, b, m), (b * m, b, n)
         for i in range(self.n_layers):

@@ -55,7 +55,13 @@ class SegNetViT(nn.Module):
         if self.with_sc:
             self.sc = B.mlp_holder(c['hidden_dim'], c['output_dim'], 3)
         self._packed = None
+        self.precision = 'bf16x3'  # 'bf16x3' | 'bf16' (tcgen05) | 'fp32' (CUDA cores); see nets/sfd2.py
         self.eval()
+
+    def set_precision(self, precision: str):
+        assert precision in ('bf16x3', 'bf16', 'fp32')
+        self.precision = precision
+        return self
 
     def _apply(self, fn, *a, **k):
         self._packed = None
@@ -71,6 +77,7 @@ class SegNetViT(nn.Module):
                 raise _lib.PramError('SegNetViT must be on a CUDA device: pram_b200 has no CPU path')
             pk = {'layers': [B.pack_self(l) for l in self.gnn.layers],
                   'in.w': B._c(self.input_proj.weight), 'in.b': B._c(self.input_proj.bias),
+                  'in.tc': B._tc(self.input_proj.weight),
                   'Wr': B._c(self.kenc.Wr.weight), **B.pack_mlp(self.seg, 'seg')}
             if self.with_sc:
                 pk.update(B.pack_mlp(self.sc, 'sc'))
@@ -91,20 +98,18 @@ class SegNetViT(nn.Module):
             cos, sin = ops.posenc(data['keypoints'], w, h, pk['Wr'])
         else:
             raise ValueError('Require image shape for keypoint coordinate normalization')
-        ws = B.Workspace(T, desc.device)
-        x = desc.float().reshape(T, dd)
-        x = x if x.is_contiguous() else x.contiguous()
-        ops.linear_f32(x, dd, pk['in.w'], pk['in.b'], ws.x, 2 * B.D, T, dd, B.D)
+        split = {'fp32': 0, 'bf16': 1, 'bf16x3': 3}[self.precision]
+        ws = B.Workspace(T, desc.device, split)
+        B.input_tokens(ws, pk, desc.reshape(T, dd), 0)
         seg = [(0, b, n)]
         for lp in pk['layers']:
             B.self_block(ws, lp, seg, cos, sin)
         c = self.config
-        hid = torch.empty((T, c['output_dim']), device=desc.device, dtype=torch.float32)
         out = torch.empty((b, n, c['n_class']), device=desc.device, dtype=torch.float32)
-        B.run_mlp(pk, 'seg', ws.x, 2 * B.D, T, B.D, c['output_dim'], c['n_class'], hid, out, c['n_class'])
+        B.head_mlp(ws, pk, 'seg', c['output_dim'], c['n_class'], out)
         output = {'prediction': out}
         if self.with_sc:
             sc = torch.empty((b, n, 3), device=desc.device, dtype=torch.float32)
-            B.run_mlp(pk, 'sc', ws.x, 2 * B.D, T, B.D, c['output_dim'], 3, hid, sc, 3)
+            B.head_mlp(ws, pk, 'sc', c['output_dim'], 3, sc)
             output['sc'] = sc
         return output

@@ -92,7 +92,21 @@ class ResNet4x(nn.Module):
         self.convPb = nn.Conv2d(256, 65, 1)
         self.convDb = nn.Conv2d(256, outdim, 1)
         self._packed: Optional[Dict[str, torch.Tensor]] = None
+        # 'bf16x3' : tcgen05 tensor cores, error-compensated split-bf16 operands (default; ~fp32 results)
+        # 'bf16'   : tcgen05 tensor cores, plain bf16 operands (fastest; keypoint order not stable)
+        # 'fp32'   : CUDA-core fp32 kernels (exact-arithmetic reference path)
+        self.precision = 'bf16x3'
         self.eval()
+
+    @property
+    def compute_dtype(self) -> str:
+        return {'bf16x3': 'bf16x3 (split-bf16 tcgen05, fp32 accumulate)', 'bf16': 'bf16', 'fp32': 'f32'}[self.precision]
+
+    def set_precision(self, precision: str):
+        if precision not in ('bf16x3', 'bf16', 'fp32'):
+            raise ValueError(precision)
+        self.precision = precision
+        return self
 
     # -- weight repacking ---------------------------------------------------------------------
     def _apply(self, fn, *a, **k):
@@ -117,6 +131,10 @@ class ResNet4x(nn.Module):
         def put(name, w, b):
             pk[name + '.w'] = _tapmajor(w).to(dev)
             pk[name + '.b'] = b.float().contiguous().to(dev)
+            # tensor-core layout: [taps, Cout, Cin] (K-major rows), split into bf16 hi/lo planes
+            co, ci, kh, kw = w.shape
+            if ci % 8 == 0:
+                pk[name + '.tc'] = ops.split_bf16(w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).float().contiguous().to(dev))
 
         for name in ('conv1a', 'conv1b', 'conv2a', 'conv2b', 'conv3a', 'conv3b'):
             seq = getattr(self, name)
@@ -143,6 +161,8 @@ class ResNet4x(nn.Module):
         """image [B,3,H,W] (normalised) -> NHWC fp32 maps.  K1-K4 of SURVEY.md section 2b."""
         _lib.require_cuda(image, 'image')
         pk = self.prepare()
+        if self.precision != 'fp32':
+            return self._trunk_tc(image, pk, 3 if self.precision == 'bf16x3' else 1)
         x = image.float().permute(0, 2, 3, 1).contiguous()  # NHWC, 3 channels (layout plumbing only)
         c = ops.conv_f32
         o1a = c(x, pk['conv1a.w'], pk['conv1a.b'], 3, 1, True)
@@ -165,8 +185,43 @@ class ResNet4x(nn.Module):
         ops.l2norm_rows_(desc, desc.shape[-1])
         return {'out1b': o1b, 'out2b': o2b, 'out3b': o3b, 'out4': o4, 'logits': logits, 'desc': desc}
 
+    def _trunk_tc(self, image: torch.Tensor, pk, split: int) -> Dict[str, torch.Tensor]:
+        """Tensor-core conv stack: tcgen05 implicit GEMMs fed by TMA, activations as split-bf16 NHWC planes
+        (phase-split in front of the three stride-2 convolutions); CUDA cores only for conv1a (Cin=3,
+        HBM-bound) and the 32-group 3x3 convolutions (1.6 % of the FLOPs)."""
+        b, _, h, w = image.shape
+        ct = ops.conv_tc
+        T = lambda n: pk[n + '.tc']
+        ps1a, _ = ops.conv1a(image, pk['conv1a.w'], pk['conv1a.b'], split)
+        h2, w2 = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        o1b = ct(ps1a, T('conv1b'), pk['conv1b.b'], 3, 2, True, split, out_shape_hw=(h2, w2))['bf']
+        ps2a = ct(o1b, T('conv2a'), pk['conv2a.b'], 3, 1, True, split, want_bf=False, want_ps=True)['ps']
+        h4, w4 = (h2 - 1) // 2 + 1, (w2 - 1) // 2 + 1
+        o2b = ct(ps2a, T('conv2b'), pk['conv2b.b'], 3, 2, True, split, out_shape_hw=(h4, w4))['bf']
+        o3a = ct(o2b, T('conv3a'), pk['conv3a.b'], 3, 1, True, split)['bf']
+        o3 = ct(o3a, T('conv3b'), pk['conv3b.b'], 3, 1, True, split, want_f32=True)
+        cur_bf, cur_f32 = o3['bf'], o3['f32']
+        o3b_bf = cur_bf
+        last = None
+        for i in range(3):
+            t = ct(cur_bf, T(f'conv4.{i}.c1'), pk[f'conv4.{i}.c1.b'], 1, 1, True, split, want_f32=True, want_bf=False)['f32']
+            t = ops.gconv3x3_split(t, pk[f'conv4.{i}.c2.w'], pk[f'conv4.{i}.c2.b'], True, split)
+            last = ct(t, T(f'conv4.{i}.c3'), pk[f'conv4.{i}.c3.b'], 1, 1, True, split, res=cur_f32, want_f32=True,
+                      want_ps=(i == 2))
+            cur_bf, cur_f32 = last['bf'], last['f32']
+        h8, w8 = (h4 - 1) // 2 + 1, (w4 - 1) // 2 + 1
+        p = ct(last['ps'], T('convPa.0'), pk['convPa.0.b'], 3, 2, True, split, out_shape_hw=(h8, w8))['bf']
+        p = ct(p, T('convPa.3'), pk['convPa.3.b'], 3, 1, False, split)['bf']
+        logits = ct(p, T('convPb'), pk['convPb.b'], 1, 1, False, split, want_f32=True, want_bf=False)['f32']
+        d = ct(cur_bf, T('convDa.0'), pk['convDa.0.b'], 3, 1, True, split)['bf']
+        d = ct(d, T('convDa.3'), pk['convDa.3.b'], 3, 1, False, split)['bf']
+        desc = ct(d, T('convDb'), pk['convDb.b'], 1, 1, False, split, want_f32=True, want_bf=False, l2norm=True)['f32']
+        return {'out1b': o1b, 'out2b': o2b, 'out3b': o3b_bf, 'out4': cur_f32, 'logits': logits, 'desc': desc}
+
     @staticmethod
-    def _nchw(x_nhwc: torch.Tensor) -> torch.Tensor:
+    def _nchw(x_nhwc) -> torch.Tensor:
+        if isinstance(x_nhwc, ops.Split):  # tensor-core path keeps some maps only as split-bf16 planes
+            x_nhwc = x_nhwc.float()
         return x_nhwc.permute(0, 3, 1, 2)  # channels-last view with the reference's NCHW shape
 
     # -- reference API ------------------------------------------------------------------------

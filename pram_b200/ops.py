@@ -231,6 +231,21 @@ def split_bf16(x: Tensor, with_lo: bool = True) -> Split:
     return Split(hi, lo)
 
 
+def split_bf16_into(x: Tensor, out: Split) -> Split:
+    """Same as split_bf16 but into preallocated planes (x contiguous fp32, same numel)."""
+    call('pram_split_bf16', ptr(x), ptr(out.hi), ptr(out.lo), x.numel(), stream_ptr())
+    return out
+
+
+def split_cols(s: Split, start: int) -> Split:
+    """Column-offset view of 2-D split planes (keeps the parent's row stride)."""
+    return Split(s.hi[:, start:], s.lo[:, start:] if s.lo is not None else None)
+
+
+def split_rows(s: Split, start: int) -> Split:
+    return Split(s.hi[start:], s.lo[start:] if s.lo is not None else None)
+
+
 def empty_split(shape, device, with_lo: bool = True, zero: bool = False) -> Split:
     mk = torch.zeros if zero else torch.empty
     hi = mk(shape, device=device, dtype=torch.bfloat16)
@@ -318,3 +333,30 @@ def linear_tc(a: Split, lda: int, rows: int, k: int, w: Split, n: int, bias: Opt
     buffers).  batch > 1: a is [batch, rows, lda], w is [batch, n, k] when ``w_batched``."""
     gemm_tc(a, lda, rows, 1, batch, k, w, (batch if w_batched else 1), batch, 1, rows, n, [(0, 0, 0)], 1, 7,
             1 if w_batched else 0, bias, res, ldres, relu, out_f32, ld_f32, out_bf, ld_bf, None, 0, False, split, bn)
+
+
+def conv1a(image_nchw: Tensor, w: Tensor, bias: Tensor, split: int, want_f32: bool = False):
+    """conv1a + BN + ReLU from the NCHW fp32 image -> phase-split Split [B*4,ceil(H/2),ceil(W/2),64]
+    (and optionally fp32 NHWC)."""
+    image_nchw = _f32c(image_nchw)
+    b, _, h, wd = image_nchw.shape
+    dev = image_nchw.device
+    ps = empty_split((b * 4, (h + 1) // 2, (wd + 1) // 2, 64), dev, with_lo=(split == 3), zero=bool(h % 2 or wd % 2))
+    f32 = torch.empty((b, h, wd, 64), device=dev, dtype=torch.float32) if want_f32 else None
+    call('pram_conv1a', ptr(image_nchw), ptr(w), ptr(bias), b, h, wd, ptr(ps.hi), ptr(ps.lo), ptr(f32), stream_ptr())
+    return ps, f32
+
+
+def gconv3x3_split(x_nhwc: Tensor, w: Tensor, bias: Tensor, relu: bool, split: int) -> Split:
+    b, h, wd, c = x_nhwc.shape
+    out = empty_split((b, h, wd, c), x_nhwc.device, with_lo=(split == 3))
+    call('pram_gconv3x3_split', ptr(x_nhwc), ptr(w), ptr(bias), None, ptr(out.hi), ptr(out.lo), b, h, wd, c // 8,
+         int(relu), stream_ptr())
+    return out
+
+
+def layernorm_gelu_split(x: Tensor, gamma: Tensor, beta: Tensor, c: int, out: Split, gelu: bool = True):
+    rows = x.numel() // c
+    call('pram_layernorm_gelu_split', ptr(x), ptr(gamma), ptr(beta), None, ptr(out.hi), ptr(out.lo), rows, c, int(gelu),
+         stream_ptr())
+    return out
