@@ -1,0 +1,546 @@
+// tcgen05 flash attention for sm_100a (head dim 64): out = softmax(Q K^T * scale) V without ever
+// materialising the Nq x Nk matrix (the reference writes S as [B,4,N,N] fp32: 16.8 MB per layer at
+// N=1024, 268 MB at N=4096 -- nets/segnetvit.py:73-76, nets/gml.py:104-107, 175-181).
+//
+// persistent CTAs, work item = (batch*head, 128-query tile); per 128-key tile:
+//   warp 0  : TMA producer   Q {64 x 128}, K {64 x 128}, V^T {2 x (64 keys x 64 d)} -> SWIZZLE_128B smem
+//   warp 1  : MMA issuer     S = Q K^T  (SS, fp32 in TMEM, double buffered)
+//                            O += P V   (TS: P read from TMEM as the A operand, V^T from smem)
+//   warps 2-5: softmax       one thread per query row (TMEM lane): tcgen05.ld S, running max with lazy
+//                            rescale of O (only when the max moved by > 8 in log2 units), exp2,
+//                            P packed to bf16 and written back to TMEM with tcgen05.st; epilogue O / l
+// SPLIT=3 keeps ~fp32 accuracy with bf16 tensor-core operands: Q,K,V and P are hi/lo split and each
+// product is three MMAs (hi*hi + lo*hi + hi*lo) into the same fp32 accumulator.
+#include "common.cuh"
+#include <cuda.h>
+#include <stdio.h>
+
+namespace fa {
+
+constexpr int BQ = 128, BKV = 128, HD = 64;
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_PHI = 256, COL_PLO = 320, COL_O = 384, TMEM_COLS = 512;
+
+struct Args {
+    int BH, heads, Nq, Nk;
+    float scale_log2;  // softmax scale * log2(e)
+    float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_ld;
+    int p_swap;        // debug: swap the two bf16 halves of a packed P column
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            printf("pram attention_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {  // K-major SWIZZLE_128B, see gemm_tc.cu
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int SPLIT>
+struct Cfg {
+    static constexpr int NPL = (SPLIT == 3) ? 2 : 1;
+    static constexpr int Q_BYTES = BQ * HD * 2;           // 16 KB per plane
+    static constexpr int K_BYTES = BKV * HD * 2;          // 16 KB per plane
+    static constexpr int V_BYTES = BKV * HD * 2;          // two boxes of 64 d x 64 keys
+    static constexpr int KV_STAGE = NPL * (K_BYTES + V_BYTES);
+    static constexpr int STAGES = 2;
+    static constexpr int SMEM_BYTES = NPL * Q_BYTES + STAGES * KV_STAGE + 1024 + 256;
+};
+
+template <int SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
+    const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
+    const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo,
+    const __grid_constant__ CUtensorMap map_v_hi, const __grid_constant__ CUtensorMap map_v_lo, const Args p) {
+    using C = Cfg<SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* q_s = smem;                                  // [NPL][16 KB]
+    uint8_t* kv_s = smem + C::NPL * C::Q_BYTES;           // [STAGES][K planes | V planes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(kv_s + C::STAGES * C::KV_STAGE);
+    uint64_t* q_full = bars + 0;
+    uint64_t* q_empty = bars + 1;
+    uint64_t* kv_full = bars + 2;   // [2]
+    uint64_t* kv_empty = bars + 4;  // [2]
+    uint64_t* s_full = bars + 6;    // [2]
+    uint64_t* s_empty = bars + 8;   // [2]
+    uint64_t* p_full = bars + 10;
+    uint64_t* o_done = bars + 11;
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q_tiles = (p.Nq + BQ - 1) / BQ;
+    const int kv_tiles = (p.Nk + BKV - 1) / BKV;
+    const int total = p.BH * q_tiles;
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1); mbar_init(q_empty, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+            mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4);
+        }
+        mbar_init(p_full, 4); mbar_init(o_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        uint32_t g = 0, w = 0;  // global kv-tile counter, work-item counter
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++w) {
+            const int bh = item / q_tiles, q0 = (item % q_tiles) * BQ;
+            mbar_wait(q_empty, (w & 1) ^ 1);
+            mbar_expect_tx(q_full, C::NPL * C::Q_BYTES);
+            tma_load_3d(q_s, &map_q_hi, q_full, 0, q0, bh);
+            if (SPLIT == 3) tma_load_3d(q_s + C::Q_BYTES, &map_q_lo, q_full, 0, q0, bh);
+            for (int j = 0; j < kv_tiles; ++j, ++g) {
+                const int st = g & 1;
+                mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
+                uint8_t* ks = kv_s + st * C::KV_STAGE;
+                uint8_t* vs = ks + C::NPL * C::K_BYTES;
+                mbar_expect_tx(&kv_full[st], C::KV_STAGE);
+                const int k0 = j * BKV;
+                tma_load_3d(ks, &map_k_hi, &kv_full[st], 0, k0, bh);
+                tma_load_3d(vs, &map_v_hi, &kv_full[st], k0, 0, bh);
+                tma_load_3d(vs + C::V_BYTES / 2, &map_v_hi, &kv_full[st], k0 + 64, 0, bh);
+                if (SPLIT == 3) {
+                    tma_load_3d(ks + C::K_BYTES, &map_k_lo, &kv_full[st], 0, k0, bh);
+                    tma_load_3d(vs + C::V_BYTES, &map_v_lo, &kv_full[st], k0, 0, bh);
+                    tma_load_3d(vs + C::V_BYTES + C::V_BYTES / 2, &map_v_lo, &kv_full[st], k0 + 64, 0, bh);
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_s = make_idesc(BQ, BKV);
+        constexpr uint32_t idesc_o = make_idesc(BQ, HD);
+        uint32_t g = 0, w = 0;
+        const uint32_t q_hi = smem_u32(q_s), q_lo = q_hi + C::Q_BYTES;
+        auto issue_S = [&](uint32_t gg) {
+            const int st = gg & 1;
+            mbar_wait(&kv_full[st], (gg >> 1) & 1);
+            mbar_wait(&s_empty[st], ((gg >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t k_hi = smem_u32(kv_s + st * C::KV_STAGE), k_lo = k_hi + C::K_BYTES;
+            const uint32_t d = tmem_base + (st ? COL_S1 : COL_S0);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) {
+                const uint32_t ko = k * 32;
+                umma_ss(d, make_desc(q_hi + ko), make_desc(k_hi + ko), idesc_s, k != 0);
+                if (SPLIT == 3) {
+                    umma_ss(d, make_desc(q_lo + ko), make_desc(k_hi + ko), idesc_s, 1);
+                    umma_ss(d, make_desc(q_hi + ko), make_desc(k_lo + ko), idesc_s, 1);
+                }
+            }
+            umma_commit(&s_full[st]);
+        };
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++w) {
+            mbar_wait(q_full, w & 1);
+            tc_fence_after();
+            issue_S(g);
+            for (int j = 0; j < kv_tiles; ++j, ++g) {
+                if (j + 1 < kv_tiles) issue_S(g + 1);
+                else umma_commit(q_empty);  // every S MMA of this item has been issued: Q slot frees when they retire
+                mbar_wait(p_full, g & 1);
+                tc_fence_after();
+                const int st = g & 1;
+                const uint32_t v_hi = smem_u32(kv_s + st * C::KV_STAGE + C::NPL * C::K_BYTES), v_lo = v_hi + C::V_BYTES;
+                const uint32_t d = tmem_base + COL_O;
+#pragma unroll
+                for (int ks = 0; ks < BKV / 16; ++ks) {
+                    const uint32_t vo = (ks >> 2) * (C::V_BYTES / 2) + (ks & 3) * 32;
+                    const uint32_t a_hi = tmem_base + COL_PHI + ks * 8, a_lo = tmem_base + COL_PLO + ks * 8;
+                    umma_ts(d, a_hi, make_desc(v_hi + vo), idesc_o, (j | ks) != 0);
+                    if (SPLIT == 3) {
+                        umma_ts(d, a_lo, make_desc(v_hi + vo), idesc_o, 1);
+                        umma_ts(d, a_hi, make_desc(v_lo + vo), idesc_o, 1);
+                    }
+                }
+                umma_commit(&kv_empty[st]);
+                umma_commit(o_done);
+            }
+        }
+    } else if (warp >= 2) {
+        // ===================== softmax + epilogue: thread <-> query row =====================
+        const int qd = warp & 3;
+        const int r = qd * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        uint32_t g = 0;
+        for (int item = blockIdx.x; item < total; item += gridDim.x) {
+            const int bh = item / q_tiles, q0 = (item % q_tiles) * BQ;
+            float m_used = -INFINITY, l = 0.f;
+            for (int j = 0; j < kv_tiles; ++j, ++g) {
+                const int st = g & 1;
+                const uint32_t s_addr = tmem_base + lane_off + (st ? COL_S1 : COL_S0);
+                const int nvalid = min(BKV, p.Nk - j * BKV);
+                mbar_wait(&s_full[st], (g >> 1) & 1);
+                tc_fence_after();
+                // pass 1: row max of the scaled logits over the valid keys
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < BKV; c += 32) {
+                    if (c >= nvalid) break;
+                    uint32_t v[32];
+                    tmem_ld32(s_addr + c, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]) * p.scale_log2);
+                }
+                // lazy rescale: keep the stale reference max unless it moved by more than 8 (log2 units)
+                const bool need = (mx > m_used + 8.f);
+                const bool warp_need = __any_sync(0xffffffffu, need) || (j == 0);
+                float corr = 1.f;
+                if (warp_need) {
+                    const float m_new = fmaxf(m_used, mx);
+                    corr = (m_used == -INFINITY) ? 0.f : exp2f(m_used - m_new);
+                    m_used = m_new;
+                    l *= corr;
+                }
+                // P (and O) may be touched only after the previous PV retired
+                if (j > 0) {
+                    mbar_wait(o_done, (g - 1) & 1);
+                    tc_fence_after();
+                    if (warp_need) {
+                        const uint32_t o_addr = tmem_base + lane_off + COL_O;
+#pragma unroll 1
+                        for (int c = 0; c < HD; c += 32) {
+                            uint32_t v[32];
+                            tmem_ld32(o_addr + c, v);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * corr);
+                            tmem_st32(o_addr + c, v);
+                        }
+                    }
+                }
+                // pass 2: p = exp2(s*scale - m), packed bf16 (hi / lo) back into TMEM
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t ph[32], pl[32];
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int c = h * 64 + cc * 32;
+                        uint32_t v[32];
+                        if (c < nvalid) tmem_ld32(s_addr + c, v);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            float p0 = 0.f, p1 = 0.f;
+                            if (c + i < nvalid) p0 = exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_used);
+                            if (c + i + 1 < nvalid) p1 = exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_used);
+                            l += p0 + p1;
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(p0), h1 = __float2bfloat16_rn(p1);
+                            const __nv_bfloat16 l0 = __float2bfloat16_rn(p0 - __bfloat162float(h0));
+                            const __nv_bfloat16 l1 = __float2bfloat16_rn(p1 - __bfloat162float(h1));
+                            uint32_t a = __bfloat16_as_ushort(h0), b = __bfloat16_as_ushort(h1);
+                            uint32_t la = __bfloat16_as_ushort(l0), lb = __bfloat16_as_ushort(l1);
+                            if (p.p_swap) { uint32_t t = a; a = b; b = t; t = la; la = lb; lb = t; }
+                            ph[cc * 16 + (i >> 1)] = a | (b << 16);
+                            pl[cc * 16 + (i >> 1)] = la | (lb << 16);
+                        }
+                    }
+                    tmem_st32(tmem_base + lane_off + COL_PHI + h * 32, ph);
+                    if (SPLIT == 3) tmem_st32(tmem_base + lane_off + COL_PLO + h * 32, pl);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&s_empty[st]); mbar_arrive(p_full); }
+            }
+            // epilogue: O / l
+            mbar_wait(o_done, (g - 1) & 1);
+            tc_fence_after();
+            const int qn = q0 + r;
+            const float inv = 1.f / l;
+            const int b = bh / p.heads, hh = bh - b * p.heads;
+            const long long orow = ((long long)b * p.Nq + qn) * p.out_ld + hh * HD;
+#pragma unroll 1
+            for (int c = 0; c < HD; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_off + COL_O + c, v);
+                if (qn < p.Nq) {
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * inv;
+                    if (p.out_f32) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4*>(p.out_f32 + orow + c + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                    }
+                    if (p.out_hi) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(f[i]), h1 = __float2bfloat16_rn(f[i + 1]);
+                            const __nv_bfloat16 l0 = __float2bfloat16_rn(f[i] - __bfloat162float(h0));
+                            const __nv_bfloat16 l1 = __float2bfloat16_rn(f[i + 1] - __bfloat162float(h1));
+                            hi[i >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[i >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        uint4* oh = reinterpret_cast<uint4*>(p.out_hi + orow + c);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                        if (p.out_lo) {
+                            uint4* ol = reinterpret_cast<uint4*>(p.out_lo + orow + c);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();  // O reads ordered before the next item's first PV (gated by p_full)
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+static int encode3(CUtensorMap* m, const void* base, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2, cuuint64_t s1_bytes,
+                   cuuint64_t s2_bytes, cuuint32_t b0, cuuint32_t b1) {
+    EncodeTiledFn fn = get_encode();
+    if (!fn) return PRAM_ERR_CUDA;
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t str[2] = {s1_bytes, s2_bytes};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, str, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PRAM_OK : PRAM_ERR_CUDA;
+}
+
+}  // namespace fa
+
+// q/k: bf16 [BH][N][64]; vt: bf16 [BH][64][nk_pad] (keys contiguous, nk_pad % 8 == 0, padding zeroed);
+// *_lo may be NULL when split == 1.  out: f32 and/or split bf16 [B][Nq][out_ld] at column head*64.
+PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
+                               const void* vt_lo, int B, int heads, int Nq, int Nk, int nk_pad, float scale,
+                               float* out_f32, void* out_hi, void* out_lo, int out_ld, int split, int p_swap,
+                               cudaStream_t stream) {
+    using namespace fa;
+    if (!q_hi || !k_hi || !vt_hi || B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return PRAM_ERR_ARG;
+    if (split != 1 && split != 3) return PRAM_ERR_ARG;
+    if (split == 3 && (!q_lo || !k_lo || !vt_lo)) return PRAM_ERR_ARG;
+    if ((nk_pad % 8) || nk_pad < Nk || (out_ld % 8)) return PRAM_ERR_UNSUPPORTED;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        PRAM_CUDA(cudaGetDevice(&dev));
+        PRAM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int BH = B * heads;
+    CUtensorMap mq[2], mk[2], mv[2];
+    const void* qs[2] = {q_hi, q_lo ? q_lo : q_hi};
+    const void* ks[2] = {k_hi, k_lo ? k_lo : k_hi};
+    const void* vs[2] = {vt_hi, vt_lo ? vt_lo : vt_hi};
+    for (int i = 0; i < 2; ++i) {
+        int rc = encode3(&mq[i], qs[i], HD, Nq, BH, HD * 2, (cuuint64_t)Nq * HD * 2, HD, BQ);
+        if (rc) return rc;
+        rc = encode3(&mk[i], ks[i], HD, Nk, BH, HD * 2, (cuuint64_t)Nk * HD * 2, HD, BKV);
+        if (rc) return rc;
+        rc = encode3(&mv[i], vs[i], nk_pad, HD, BH, (cuuint64_t)nk_pad * 2, (cuuint64_t)nk_pad * HD * 2, 64, HD);
+        if (rc) return rc;
+    }
+    Args a;
+    a.BH = BH; a.heads = heads; a.Nq = Nq; a.Nk = Nk;
+    a.scale_log2 = scale * 1.4426950408889634f;
+    a.out_f32 = out_f32; a.out_hi = (__nv_bfloat16*)out_hi; a.out_lo = (__nv_bfloat16*)out_lo; a.out_ld = out_ld;
+    a.p_swap = p_swap;
+    const int total = BH * ((Nq + BQ - 1) / BQ);
+    const int grid = total < num_sms ? total : num_sms;
+    if (split == 3) {
+        auto kern = attention_tc_kernel<3>;
+        static bool attr = false;
+        if (!attr) { PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::SMEM_BYTES)); attr = true; }
+        kern<<<grid, NUM_THREADS, Cfg<3>::SMEM_BYTES, stream>>>(mq[0], mq[1], mk[0], mk[1], mv[0], mv[1], a);
+    } else {
+        auto kern = attention_tc_kernel<1>;
+        static bool attr = false;
+        if (!attr) { PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES)); attr = true; }
+        kern<<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, stream>>>(mq[0], mq[1], mk[0], mk[1], mv[0], mv[1], a);
+    }
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// qkv [tokens][nparts*heads*64] fp32 -> split-bf16 operands of the attention kernel:
+//   Q, K [B][heads][N][64] (rotary on adjacent pairs, scale_qk applied), V^T [B][heads][64][n_pad]
+// nparts = 3: (q | k | v);  nparts = 2: (qk | v) (cross attention: only Q=qk and V^T are produced)
+// ------------------------------------------------------------------------------------------
+__global__ void qk_prep_kernel(const float* __restrict__ qkv, int nparts, int B, int N, int heads,
+                               const float* __restrict__ cosb, const float* __restrict__ sinb, float scale_qk,
+                               __nv_bfloat16* __restrict__ q_hi, __nv_bfloat16* __restrict__ q_lo,
+                               __nv_bfloat16* __restrict__ k_hi, __nv_bfloat16* __restrict__ k_lo) {
+    const int nqk = nparts - 1;  // number of rotated parts
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * N * nqk * heads * 32;
+    if (i >= total) return;
+    const int pr = (int)(i & 31);
+    const int h = (int)((i >> 5) % heads);
+    const int part = (int)((i / (32 * heads)) % nqk);
+    const long long t = i / ((long long)32 * heads * nqk);
+    const int b = (int)(t / N), n = (int)(t - (long long)b * N);
+    const float* src = qkv + t * (long long)(nparts * heads * 64) + (long long)part * heads * 64 + h * 64 + 2 * pr;
+    float x0 = src[0], x1 = src[1];
+    if (cosb) {
+        const float c = cosb[t * 32 + pr], s = sinb[t * 32 + pr];
+        const float y0 = x0 * c + (-x1) * s, y1 = x1 * c + x0 * s;
+        x0 = y0; x1 = y1;
+    }
+    x0 *= scale_qk; x1 *= scale_qk;
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    const long long o = (((long long)b * heads + h) * N + n) * 64 + 2 * pr;
+    __nv_bfloat16* dh = part == 0 ? q_hi : k_hi;
+    __nv_bfloat16* dl = part == 0 ? q_lo : k_lo;
+    *reinterpret_cast<uint32_t*>(dh + o) = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    if (dl) {
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+        *reinterpret_cast<uint32_t*>(dl + o) = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+}
+
+// V part -> V^T [B][heads][64][n_pad] through a shared-memory transpose (coalesced on both sides)
+__global__ void __launch_bounds__(256) vt_prep_kernel(const float* __restrict__ qkv, int row_stride, int v_off, int B, int N,
+                                                      int heads, int n_pad, __nv_bfloat16* __restrict__ vt_hi,
+                                                      __nv_bfloat16* __restrict__ vt_lo) {
+    __shared__ float tile[64][65];
+    const int n0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int tk = i >> 6, d = i & 63;
+        const int n = n0 + tk;
+        tile[tk][d] = (n < N) ? qkv[((long long)b * N + n) * row_stride + v_off + h * 64 + d] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int d = i >> 6, tk = i & 63;
+        const int n = n0 + tk;
+        if (n < n_pad) {
+            const float v = tile[tk][d];
+            const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+            const long long o = (((long long)b * heads + h) * 64 + d) * n_pad + n;
+            vt_hi[o] = hv;
+            if (vt_lo) vt_lo[o] = __float2bfloat16_rn(v - __bfloat162float(hv));
+        }
+    }
+}
+
+PRAM_API int pram_attention_prep(const float* qkv, int nparts, int B, int N, int heads, const float* cosb,
+                                 const float* sinb, float scale_qk, void* q_hi, void* q_lo, void* k_hi, void* k_lo,
+                                 void* vt_hi, void* vt_lo, int n_pad, cudaStream_t stream) {
+    if (!qkv || !q_hi || !vt_hi || (nparts != 2 && nparts != 3) || (nparts == 3 && !k_hi) || n_pad < N) return PRAM_ERR_ARG;
+    const long long total = (long long)B * N * (nparts - 1) * heads * 32;
+    qk_prep_kernel<<<cdiv(total, 256), 256, 0, stream>>>(qkv, nparts, B, N, heads, cosb, sinb, scale_qk,
+                                                        (__nv_bfloat16*)q_hi, (__nv_bfloat16*)q_lo, (__nv_bfloat16*)k_hi,
+                                                        (__nv_bfloat16*)k_lo);
+    PRAM_CHECK_LAUNCH();
+    dim3 grid(cdiv(n_pad, 64), heads, B);
+    vt_prep_kernel<<<grid, 256, 0, stream>>>(qkv, nparts * heads * 64, (nparts - 1) * heads * 64, B, N, heads, n_pad,
+                                             (__nv_bfloat16*)vt_hi, (__nv_bfloat16*)vt_lo);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}

@@ -98,6 +98,7 @@ class Workspace:
         e = lambda *s: torch.empty(s, device=device, dtype=torch.float32)
         self.T = tokens
         self.split = split  # 0: fp32 CUDA-core path; 1 / 3: tcgen05 path with bf16 / bf16x3 operands
+        self.ctx_in_bf = False
         if split:
             lo = split == 3
             self.cat_bf = [ops.empty_split((tokens, 2 * D), device, lo), ops.empty_split((tokens, 2 * D), device, lo)]
@@ -148,7 +149,8 @@ def _finish_block(ws: Workspace, pk: Dict[str, torch.Tensor]):
         run_mlp(pk, 'mlp', cat, 2 * D, T, 2 * D, 2 * D, D, ws.hid, nxt, 2 * D, res=cat, ldres=2 * D)
     else:
         cbf, nbf = ws.cat_bf[ws.cur], ws.cat_bf[ws.cur ^ 1]
-        ops.split_bf16_into(ws.ctx, ws.ctx_bf)
+        if not ws.ctx_in_bf:  # CUDA-core attention produced fp32 ctx (AdaGML's mean-attention variant)
+            ops.split_bf16_into(ws.ctx, ws.ctx_bf)
         linear(ws, None, ws.ctx_bf, D, T, D, D, pk, 'proj', out_bf=ops.split_cols(cbf, D), ld_bf=2 * D)
         linear(ws, None, cbf, 2 * D, T, 2 * D, 2 * D, pk, 'mlp.0', out_f32=ws.hid, ld_f32=2 * D)
         ops.layernorm_gelu_split(ws.hid, pk['mlp.ln.g'], pk['mlp.ln.b'], 2 * D, ws.hid_bf)
@@ -164,8 +166,14 @@ def self_block(ws: Workspace, pk: Dict[str, torch.Tensor], segments: Sequence[Tu
     Reference nets/segnetvit.py:97-106 == nets/gml.py:128-137."""
     T = ws.T
     linear(ws, ws.x, ws.x_bf if ws.split else None, 2 * D, T, D, 3 * D, pk, 'qkv', out_f32=ws.qkv, ld_f32=3 * D)
+    use_tc = bool(ws.split) and colmeans is None
+    ws.ctx_in_bf = use_tc
     for si, (off, b, n) in enumerate(segments):
         sl = slice(off, off + b * n)
+        if use_tc:
+            q, k, vt, n_pad = ops.attention_prep(ws.qkv[sl], 3, b, n, HEADS, cos[sl], sin[sl], 1.0, ws.split)
+            ops.attention_tc(q, k, vt, b, HEADS, n, n, n_pad, HDIM ** -0.5, None, ops.split_rows(ws.ctx_bf, off), D, ws.split)
+            continue
         ops.rotary_split(ws.qkv[sl], 3, b, n, HEADS, cos[sl], sin[sl], 1.0, ws.q[sl], ws.k[sl], ws.v[sl])
         ops.attention_f32(ws.q[sl], ws.k[sl], ws.v[sl], b, HEADS, n, n, HDIM ** -0.5, ws.ctx[sl], D,
                           None if colmeans is None else colmeans[si])
@@ -184,6 +192,15 @@ def cross_block(ws: Workspace, pk: Dict[str, torch.Tensor], seg0: Tuple[int, int
     (o0, b, m), (o1, _, n) = seg0, seg1
     s0, s1 = slice(o0, o0 + b * m), slice(o1, o1 + b * n)
     sc = (HDIM ** -0.5) ** 0.5  # applied to both qk0 and qk1 (nets/gml.py:174)
+    use_tc = bool(ws.split) and colmeans is None
+    ws.ctx_in_bf = use_tc
+    if use_tc:
+        q0, _, vt0, mp = ops.attention_prep(qkv[s0], 2, b, m, HEADS, None, None, sc, ws.split)
+        q1, _, vt1, np_ = ops.attention_prep(qkv[s1], 2, b, n, HEADS, None, None, sc, ws.split)
+        ops.attention_tc(q0, q1, vt1, b, HEADS, m, n, np_, 1.0, None, ops.split_rows(ws.ctx_bf, o0), D, ws.split)
+        ops.attention_tc(q1, q0, vt0, b, HEADS, n, m, mp, 1.0, None, ops.split_rows(ws.ctx_bf, o1), D, ws.split)
+        _finish_block(ws, pk)
+        return
     ops.rotary_split(qkv[s0], 2, b, m, HEADS, None, None, sc, ws.q[s0], None, ws.v[s0])
     ops.rotary_split(qkv[s1], 2, b, n, HEADS, None, None, sc, ws.q[s1], None, ws.v[s1])
     # m0 = softmax_rows(sim) v1 ; the column mean of attn01 indexes tokens of set 1

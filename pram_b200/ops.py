@@ -360,3 +360,31 @@ def layernorm_gelu_split(x: Tensor, gamma: Tensor, beta: Tensor, c: int, out: Sp
     call('pram_layernorm_gelu_split', ptr(x), ptr(gamma), ptr(beta), None, ptr(out.hi), ptr(out.lo), rows, c, int(gelu),
          stream_ptr())
     return out
+
+
+# ---- tensor-core flash attention ---------------------------------------------------------------------
+
+P_SWAP = 0  # debug knob for the bf16 packing order of P inside a TMEM column
+
+
+def attention_prep(qkv: Tensor, nparts: int, b: int, n: int, heads: int, cos: Optional[Tensor], sin: Optional[Tensor],
+                   scale_qk: float, split: int):
+    """qkv rows [b*n, nparts*heads*64] fp32 -> (Q Split [b*heads, n, 64], K Split or None, V^T Split
+    [b*heads, 64, n_pad], n_pad)."""
+    dev = qkv.device
+    lo = split == 3
+    n_pad = (n + 7) // 8 * 8
+    q = empty_split((b * heads, n, 64), dev, lo)
+    k = empty_split((b * heads, n, 64), dev, lo) if nparts == 3 else None
+    vt = empty_split((b * heads, 64, n_pad), dev, lo)
+    call('pram_attention_prep', ptr(qkv), nparts, b, n, heads, ptr(cos), ptr(sin), float(scale_qk), ptr(q.hi), ptr(q.lo),
+         ptr(k.hi) if k is not None else None, ptr(k.lo) if k is not None else None, ptr(vt.hi), ptr(vt.lo), n_pad,
+         stream_ptr())
+    return q, k, vt, n_pad
+
+
+def attention_tc(q: Split, k: Split, vt: Split, b: int, heads: int, nq: int, nk: int, nk_pad: int, scale: float,
+                 out_f32: Optional[Tensor], out_bf: Optional[Split], out_ld: int, split: int):
+    call('pram_attention_tc', ptr(q.hi), ptr(q.lo), ptr(k.hi), ptr(k.lo), ptr(vt.hi), ptr(vt.lo), b, heads, nq, nk, nk_pad,
+         float(scale), ptr(out_f32), ptr(out_bf.hi) if out_bf is not None else None,
+         ptr(out_bf.lo) if (out_bf is not None and out_bf.lo is not None) else None, out_ld, split, P_SWAP, stream_ptr())

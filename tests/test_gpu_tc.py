@@ -103,3 +103,52 @@ def test_bmm_and_l2norm_tc(ops, dev):
             bias=bias.to(dev), out_f32=out, ld_f32=128, l2norm=True, split=3)
     torch.cuda.synchronize()
     assert _relerr(out.cpu(), ref) < 2e-4
+
+
+@pytest.mark.parametrize('split', [3, 1])
+@pytest.mark.parametrize('b,nq,nk', [(1, 128, 128), (2, 75, 130), (1, 1024, 1024), (2, 300, 1000)])
+def test_attention_tc(ops, dev, split, b, nq, nk):
+    """tcgen05 flash attention vs torch fp32 softmax(QK^T/8)V.  bf16x3: 2e-4 of the output scale."""
+    g = torch.Generator().manual_seed(nq + nk)
+    h = 4
+    q, k, v = (torch.randn(b, h, n, 64, generator=g) for n in (nq, nk, nk))
+    attn = torch.softmax(torch.einsum('bhid,bhjd->bhij', q, k) * 0.125, -1)
+    ref = torch.einsum('bhij,bhjd->bhid', attn, v).transpose(1, 2).flatten(-2)  # [b, nq, 256]
+    lo = split == 3
+    nk_pad = (nk + 7) // 8 * 8
+    vt = torch.zeros(b, h, 64, nk_pad)
+    vt[..., :nk] = v.transpose(-1, -2)
+    Q = ops.split_bf16(q.reshape(b * h, nq, 64).to(dev), lo)
+    K = ops.split_bf16(k.reshape(b * h, nk, 64).to(dev), lo)
+    VT = ops.split_bf16(vt.reshape(b * h, 64, nk_pad).to(dev), lo)
+    errs = {}
+    for swap in (0, 1):
+        ops.P_SWAP = swap
+        out = torch.zeros(b, nq, 256, device=dev)
+        obf = ops.empty_split((b, nq, 256), dev, lo)
+        ops.attention_tc(Q, K, VT, b, h, nq, nk, nk_pad, 0.125, out, obf, 256, split)
+        torch.cuda.synchronize()
+        errs[swap] = _relerr(out.cpu(), ref)
+        if swap == 0:
+            err_bf = _relerr(obf.float().cpu(), ref)
+    ops.P_SWAP = 0
+    tol = 2e-4 if split == 3 else 2e-2
+    assert errs[0] < tol, f'P packing order: errors by p_swap = {errs}'
+    assert err_bf < (tol if split == 3 else 3e-2)
+
+
+def test_attention_prep_matches_rotary_split(ops, dev):
+    g = torch.Generator().manual_seed(0)
+    b, n, h = 2, 70, 4
+    qkv = torch.randn(b * n, 768, generator=g).to(dev)
+    cos = torch.rand(b * n, 32, generator=g).to(dev)
+    sin = torch.rand(b * n, 32, generator=g).to(dev)
+    q = torch.empty(b * n, 256, device=dev); k = torch.empty_like(q); v = torch.empty_like(q)
+    ops.rotary_split(qkv, 3, b, n, h, cos, sin, 0.5, q, k, v)
+    Q, K, VT, n_pad = ops.attention_prep(qkv, 3, b, n, h, cos, sin, 0.5, 3)
+    torch.cuda.synchronize()
+    assert torch.allclose(Q.float().view(-1), q.view(-1), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(K.float().view(-1), k.view(-1), atol=1e-5, rtol=1e-5)
+    vref = v.view(b, h, n, 64).transpose(-1, -2)
+    assert torch.allclose(VT.float().view(b, h, 64, n_pad)[..., :n], vref, atol=1e-5, rtol=1e-5)
+    assert (VT.float().view(b, h, 64, n_pad)[..., n:] == 0).all()
