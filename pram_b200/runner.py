@@ -75,6 +75,33 @@ class LocalizationPipeline:
             out.update(m)
         return out
 
+    # -- CUDA graph: one replay per batch instead of ~1000 launches + tensor-map encodes -----------------
+    @torch.no_grad()
+    def capture(self, images: torch.Tensor, smap: Optional[SyntheticMap] = None):
+        """Capture ``localize`` for this batch shape into a CUDA graph (all shapes are static and no stage
+        syncs with the host).  Returns the number of library kernels inside one replay."""
+        from . import _lib
+        self._static_in = images.clone()
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.localize(self._static_in, smap)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self._graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self._graph):
+            self._static_out = self.localize(self._static_in, smap)
+        self.graph_launches = _lib.launch_count() - n0
+        return self.graph_launches
+
+    def replay(self, images: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        if images is not None:
+            self._static_in.copy_(images, non_blocking=True)
+        self._graph.replay()
+        return self._static_out
+
     # -- synthetic map ------------------------------------------------------------------------
     @torch.no_grad()
     def build_synthetic_map(self, images: torch.Tensor, seed: int = 0, outlier_frac: float = 0.2) -> SyntheticMap:

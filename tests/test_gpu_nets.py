@@ -154,10 +154,9 @@ def test_sinkhorn_match_shapes_vs_oracle(ops, dev, m, n):
     i0, i1, s0, s1 = O.compute_matches(P, 0.2)
     m0, m1, t0, t1, Pg = ops.sinkhorn_match(dist.to(dev), bin_score.to(dev), 20, 0.2, return_P=True)
     assert torch.allclose(Pg.cpu(), P, rtol=5e-4, atol=1e-7)
-    # size-independent property the reference's iteration has even when M != N (inconsistent marginals
-    # make it a fixed point of the row update only): real rows sum to 1, the dustbin row to M+1
-    rs = Pg[0].sum(1).cpu()
-    assert torch.allclose(rs[:-1], torch.ones(m), atol=1e-3) and abs(rs[-1].item() - (m + 1)) < 1e-3 * (m + 1)
+    # total mass agrees with the oracle (no size-independent marginal property exists: with M != N the
+    # reference's marginals are inconsistent and the 20 iterations do not converge to either of them)
+    assert abs(Pg.sum().item() - P.sum().item()) < 1e-3 * P.sum().item()
     decisive = (s0[0] - 0.2).abs() > 1e-3
     assert torch.equal(m0.cpu()[0][decisive], i0[0][decisive])
     assert torch.allclose(t0.cpu(), s0, rtol=5e-4, atol=1e-6)
