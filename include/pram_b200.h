@@ -161,6 +161,16 @@ int pram_attention_prep(const float* qkv, int nparts, int B, int N, int heads, c
                         float scale_qk, void* q_hi, void* q_lo, void* k_hi, void* k_lo, void* vt_hi, void* vt_lo,
                         int n_pad, pram_stream_t stream);
 
+/* K19: batched absolute pose, P3P + RANSAC + local optimisation + robust refinement, float64.
+ * Replaces pycolmap.absolute_pose_estimation at localization/singlemap3d.py:168-175 (and :324, :454,
+ * tracker.py:211, pose_estimator.py:213,338,452).  kpts [B][n][2] f32 pixels, matches [B][n] i64 into
+ * xyz [B][nref][3] f32 (-1 = unmatched).  Outputs qvec (wxyz) / tvec f64, inlier mask in keypoint order. */
+long long pram_ransac_workspace_bytes(int B, int cap, int num_hypotheses);
+int pram_ransac_pnp(const float* kpts, const long long* matches, const float* xyz, int B, int n, int nref, double fx,
+                    double fy, double cx, double cy, double pixel_shift, double max_error, int num_hypotheses,
+                    int lo_iters, int final_iters, int min_inliers, unsigned int seed, void* workspace, double* qvec,
+                    double* tvec, int* num_inliers, unsigned char* inliers, int* success, pram_stream_t stream);
+
 /* fp32 -> split bf16 planes: hi = bf16(x), lo = bf16(x - hi) (lo may be NULL). */
 int pram_split_bf16(const float* in, void* hi, void* lo, long long n, pram_stream_t stream);
 

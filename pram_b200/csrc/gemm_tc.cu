@@ -135,6 +135,14 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
+// per-epilogue-warp staging: padded 32x32 transpose tile + per-row output offsets
+struct EpiWarp {
+    float tile[32][33];
+    float inv[32];
+    long long pix[32];
+    long long pix_ps[32];
+};
+
 template <int BN, int SPLIT>
 struct Cfg {
     static constexpr int A_BYTES = BM * BK * 2;
@@ -142,7 +150,7 @@ struct Cfg {
     static constexpr int NPLANES = (SPLIT == 3) ? 2 : 1;
     static constexpr int STAGE_BYTES = NPLANES * (A_BYTES + B_BYTES);
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 6 ? 6 : (200 * 1024) / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * (int)sizeof(EpiWarp);
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -242,25 +250,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
         }
     } else if (warp >= 2) {
         // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
+        // tcgen05.ld hands each thread one output ROW (32 consecutive channels per chunk).  Storing that
+        // directly makes every warp-level store touch 32 different 128-byte lines; instead each warp
+        // transposes its 32x32 chunk through a padded shared-memory tile so that 8 (fp32) / 4 (bf16) lanes
+        // cover one row segment and every store instruction writes whole lines.
         const int q = warp & 3;
         const int r = q * 32 + lane;  // row of the tile == TMEM lane
+        EpiWarp& ew = reinterpret_cast<EpiWarp*>(smem + C::STAGES * C::STAGE_BYTES + 256)[q];
         int as = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int nt = tile % n_tiles, mt = tile / n_tiles;
             const int txi = mt % tiles_x, tyi = (mt / tiles_x) % tiles_y, b = mt / (tiles_x * tiles_y);
-            const int y = tyi * TH + (r >> p.tw_log2), x = txi * TW + (r & (TW - 1));
-            const bool valid = (y < p.Ho) && (x < p.Wo);
-            const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
-            const int Hp = (p.Ho + 1) >> 1, Wp = (p.Wo + 1) >> 1;
-            const long long pix_ps = (((long long)(b * 4 + (y & 1) * 2 + (x & 1))) * Hp + (y >> 1)) * Wp + (x >> 1);
+            {
+                const int y = tyi * TH + (r >> p.tw_log2), x = txi * TW + (r & (TW - 1));
+                const bool valid = (y < p.Ho) && (x < p.Wo);
+                const int Hp = (p.Ho + 1) >> 1, Wp = (p.Wo + 1) >> 1;
+                ew.pix[lane] = valid ? ((long long)b * p.Ho + y) * p.Wo + x : -1ll;
+                ew.pix_ps[lane] = (((long long)(b * 4 + (y & 1) * 2 + (x & 1))) * Hp + (y >> 1)) * Wp + (x >> 1);
+            }
             const int n0 = nt * BN;
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-            float inv_norm = 1.f;
             if (p.l2norm) {
                 float ss = 0.f;
                 for (int c = 0; c < BN; c += 32) {
+                    if (n0 + c >= p.N) break;
                     uint32_t v[32];
                     tmem_ld32(taddr + c, v);
 #pragma unroll
@@ -272,87 +287,100 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                         }
                     }
                 }
-                inv_norm = fmaxf(sqrtf(ss), 1e-12f);
+                ew.inv[lane] = fmaxf(sqrtf(ss), 1e-12f);
             }
+            __syncwarp();
             for (int c = 0; c < BN; c += 32) {
                 if (n0 + c >= p.N) break;  // warp-uniform
-                uint32_t v[32];
-                tmem_ld32(taddr + c, v);
-                if (valid) {
-                    const int nb = n0 + c;
-                    const bool full32 = (nb + 32 <= p.N);
-                    float f[32];
+                const int nb = n0 + c;
+                const bool full32 = (nb + 32 <= p.N);
+                {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float t = __uint_as_float(v[j]);
-                        if (p.bias && (full32 || nb + j < p.N)) t += __ldg(p.bias + nb + j);
-                        f[j] = t;
-                    }
-                    if (p.res) {
-                        const float* rp = p.res + pix * p.res_ld + nb;
-                        if (full32 && ((p.res_ld & 3) == 0)) {
+                    for (int j = 0; j < 32; ++j) ew.tile[lane][j] = __uint_as_float(v[j]);
+                }
+                __syncwarp();
+                // ---- pass 1 (fp32 mapping: 8 lanes per row): bias, residual, ReLU, L2 norm, fp32 store ----
+                {
+                    const int g = lane >> 3, col = (lane & 7) * 4;
+                    float bz[4];
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                float4 t = *reinterpret_cast<const float4*>(rp + j);
-                                f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
+                    for (int k = 0; k < 4; ++k) bz[k] = (p.bias && nb + col + k < p.N) ? __ldg(p.bias + nb + col + k) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = i * 4 + g;
+                        const long long pixr = ew.pix[row];
+                        float f[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) f[k] = ew.tile[row][col + k] + bz[k];
+                        if (p.res && pixr >= 0) {
+                            const float* rp = p.res + pixr * p.res_ld + nb + col;
+                            if (full32 && ((p.res_ld & 3) == 0)) {
+                                const float4 t = *reinterpret_cast<const float4*>(rp);
+                                f[0] += t.x; f[1] += t.y; f[2] += t.z; f[3] += t.w;
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) if (nb + col + k < p.N) f[k] += rp[k];
                             }
-                        } else {
+                        }
+                        if (p.relu) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) if (nb + j < p.N) f[j] += rp[j];
+                            for (int k = 0; k < 4; ++k) f[k] = fmaxf(f[k], 0.f);
+                        }
+                        if (p.l2norm) {
+                            const float d = ew.inv[row];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) f[k] = f[k] / d;
+                        }
+                        if (p.out_f32 && pixr >= 0) {
+                            float* op = p.out_f32 + pixr * p.ld_f32 + nb + col;
+                            if (full32 && ((p.ld_f32 & 3) == 0)) {
+                                *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) if (nb + col + k < p.N) op[k] = f[k];
+                            }
+                        }
+                        if (p.out_hi || p.ps_hi) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) ew.tile[row][col + k] = f[k];
                         }
                     }
-                    if (p.relu) {
+                }
+                // ---- pass 2 (bf16 mapping: 4 lanes per row): split into hi / lo planes, 16-byte stores ----
+                if (p.out_hi || p.ps_hi) {  // requires N % 32 == 0 (checked on the host)
+                    __syncwarp();
+                    const int g = lane >> 2, col = (lane & 3) * 8;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                    }
-                    if (p.l2norm) {
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = i * 8 + g;
+                        const long long pixr = ew.pix[row];
+                        uint32_t hi[4], lo[4];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = f[j] / inv_norm;
-                    }
-                    if (p.out_f32) {
-                        float* op = p.out_f32 + pix * p.ld_f32 + nb;
-                        if (full32 && ((p.ld_f32 & 3) == 0)) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) if (nb + j < p.N) op[j] = f[j];
-                        }
-                    }
-                    if (p.out_hi || p.ps_hi) {
-                        uint32_t hi[16], lo[16];
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
+                        for (int k = 0; k < 8; k += 2) {
                             __nv_bfloat16 h0, l0, h1, l1;
-                            split_bf16(f[j], h0, l0);
-                            split_bf16(f[j + 1], h1, l1);
-                            hi[j >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            lo[j >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                            split_bf16(ew.tile[row][col + k], h0, l0);
+                            split_bf16(ew.tile[row][col + k + 1], h1, l1);
+                            hi[k >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[k >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                         }
-                        // bf16 outputs require N % 32 == 0 and ld % 8 == 0 (checked on the host)
-                        if (p.out_hi) {
-                            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.ld_bf + nb);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                            if (p.out_lo) {
-                                uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.ld_bf + nb);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        if (pixr >= 0) {
+                            if (p.out_hi) {
+                                *reinterpret_cast<uint4*>(p.out_hi + pixr * p.ld_bf + nb + col) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                                if (p.out_lo)
+                                    *reinterpret_cast<uint4*>(p.out_lo + pixr * p.ld_bf + nb + col) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                             }
-                        }
-                        if (p.ps_hi) {
-                            uint4* oh = reinterpret_cast<uint4*>(p.ps_hi + pix_ps * p.ld_ps + nb);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                            if (p.ps_lo) {
-                                uint4* ol = reinterpret_cast<uint4*>(p.ps_lo + pix_ps * p.ld_ps + nb);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                            if (p.ps_hi) {
+                                const long long pp = ew.pix_ps[row];
+                                *reinterpret_cast<uint4*>(p.ps_hi + pp * p.ld_ps + nb + col) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                                if (p.ps_lo)
+                                    *reinterpret_cast<uint4*>(p.ps_lo + pp * p.ld_ps + nb + col) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                             }
                         }
                     }
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();

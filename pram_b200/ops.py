@@ -388,3 +388,29 @@ def attention_tc(q: Split, k: Split, vt: Split, b: int, heads: int, nq: int, nk:
     call('pram_attention_tc', ptr(q.hi), ptr(q.lo), ptr(k.hi), ptr(k.lo), ptr(vt.hi), ptr(vt.lo), b, heads, nq, nk, nk_pad,
          float(scale), ptr(out_f32), ptr(out_bf.hi) if out_bf is not None else None,
          ptr(out_bf.lo) if (out_bf is not None and out_bf.lo is not None) else None, out_ld, split, P_SWAP, stream_ptr())
+
+
+# ---- K19: batched PnP RANSAC -------------------------------------------------------------------------
+
+def ransac_pnp(kpts: Tensor, matches: Tensor, xyz: Tensor, fx: float, fy: float, cx: float, cy: float,
+               max_error: float, pixel_shift: float = 0.5, num_hypotheses: int = 1024, lo_iters: int = 10,
+               final_iters: int = 20, min_inliers: int = 3, seed: int = 0):
+    """kpts [B,n,2] f32, matches [B,n] i64 (index into xyz or -1), xyz [B,nref,3] f32 ->
+    dict(qvec [B,4] wxyz f64, tvec [B,3] f64, num_inliers [B] i32, inliers [B,n] bool, success [B] bool)."""
+    _lib.require_cuda(kpts, 'keypoints')
+    kpts, xyz = _f32c(kpts), _f32c(xyz)
+    matches = matches.contiguous()
+    b, n, _ = kpts.shape
+    nref = xyz.shape[1]
+    dev = kpts.device
+    nbytes = int(_lib.load().pram_ransac_workspace_bytes(b, n, num_hypotheses))
+    ws = torch.empty((nbytes + 7) // 8, device=dev, dtype=torch.float64)
+    q = torch.empty((b, 4), device=dev, dtype=torch.float64)
+    t = torch.empty((b, 3), device=dev, dtype=torch.float64)
+    ni = torch.empty((b,), device=dev, dtype=torch.int32)
+    inl = torch.empty((b, n), device=dev, dtype=torch.uint8)
+    ok = torch.empty((b,), device=dev, dtype=torch.int32)
+    call('pram_ransac_pnp', ptr(kpts), ptr(matches), ptr(xyz), b, n, nref, float(fx), float(fy), float(cx), float(cy),
+         float(pixel_shift), float(max_error), int(num_hypotheses), int(lo_iters), int(final_iters), int(min_inliers),
+         int(seed) & 0xffffffff, ptr(ws), ptr(q), ptr(t), ptr(ni), ptr(inl), ptr(ok), stream_ptr())
+    return {'qvec': q, 'tvec': t, 'num_inliers': ni, 'inliers': inl.bool(), 'success': ok.bool()}
