@@ -10,7 +10,8 @@
 //   in shared memory as a 128 x 64 K-major SWIZZLE_128B operand; W tiles are {64, BN, 1} boxes
 // * warp 1 (one lane): tcgen05.mma issuer, accumulators in TMEM, double-buffered (2 x BN columns) so
 //   the epilogue of tile i overlaps the main loop of tile i+1
-// * warps 2-5: epilogue -- tcgen05.ld -> bias / residual / ReLU -> fp32 and/or split-bf16 stores
+// * warps 2-9: epilogue -- tcgen05.ld -> smem transpose -> bias / residual / ReLU -> coalesced fp32
+//   and/or split-bf16 stores
 //   (NHWC, and optionally a 2x2 phase-split copy that feeds a following stride-2 convolution with
 //   unit-stride TMA boxes)
 // * SPLIT=3: error-compensated bf16x3 (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, all into the same fp32
@@ -25,7 +26,7 @@ namespace tc {
 constexpr int BM = 128;       // UMMA_M
 constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MAX_TAPS = 9;
 
 struct Args {
@@ -135,13 +136,13 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
-// per-epilogue-warp staging: padded 32x32 transpose tile + per-row output offsets
-struct EpiWarp {
-    float tile[32][33];
+// per-lane-quarter row table of the epilogue (output pixel index per tile row, -1 = outside the map)
+struct EpiQuarter {
+    int pix[32];
+    int pix_ps[32];
     float inv[32];
-    long long pix[32];
-    long long pix_ps[32];
 };
+constexpr int EPI_BYTES = 8 * 4096 + 4 * (int)sizeof(EpiQuarter);  // 8 swizzled 32x32 fp32 tiles + tables
 
 template <int BN, int SPLIT>
 struct Cfg {
@@ -150,7 +151,7 @@ struct Cfg {
     static constexpr int NPLANES = (SPLIT == 3) ? 2 : 1;
     static constexpr int STAGE_BYTES = NPLANES * (A_BYTES + B_BYTES);
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 6 ? 6 : (200 * 1024) / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * (int)sizeof(EpiWarp);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
         prefetch_tmap(&map_w_hi);
         if (SPLIT == 3) { prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_lo); }
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -249,30 +250,61 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     } else if (warp >= 2) {
-        // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
-        // tcgen05.ld hands each thread one output ROW (32 consecutive channels per chunk).  Storing that
-        // directly makes every warp-level store touch 32 different 128-byte lines; instead each warp
-        // transposes its 32x32 chunk through a padded shared-memory tile so that 8 (fp32) / 4 (bf16) lanes
-        // cover one row segment and every store instruction writes whole lines.
-        const int q = warp & 3;
+        // ===================== epilogue (8 warps) =====================
+        // TMEM lane quarter = warp % 4; the two warps of a quarter take alternate 32-column chunks.
+        // tcgen05.ld hands each thread one output ROW (32 consecutive channels).  Storing that directly
+        // makes every warp-level store touch 32 different 128-byte lines, so each warp transposes its
+        // 32x32 chunk through an XOR-swizzled shared-memory tile: 8 (fp32) / 4 (bf16) lanes then cover one
+        // row segment and every store / residual load moves whole lines.  Residual loads of the next
+        // chunk are issued before the current chunk is processed (latency hidden).
+        const int q = warp & 3, half = (warp - 2) >> 2;
         const int r = q * 32 + lane;  // row of the tile == TMEM lane
-        EpiWarp& ew = reinterpret_cast<EpiWarp*>(smem + C::STAGES * C::STAGE_BYTES + 256)[q];
+        uint8_t* epi_base = smem + C::STAGES * C::STAGE_BYTES + 256;
+        float* tile_s = reinterpret_cast<float*>(epi_base) + (warp - 2) * 1024;             // [32][32] swizzled
+        EpiQuarter& eq = reinterpret_cast<EpiQuarter*>(epi_base + 8 * 4096)[q];
+        const float* __restrict__ resp = p.res;
+        const float* __restrict__ biasp = p.bias;
+        const bool res_vec = ((p.res_ld & 3) == 0);
+        const int g1 = lane >> 3, col1 = (lane & 7) * 4;   // pass-1 mapping
+        const int g2 = lane >> 2, col2 = (lane & 3) * 8;   // pass-2 mapping
         int as = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int nt = tile % n_tiles, mt = tile / n_tiles;
             const int txi = mt % tiles_x, tyi = (mt / tiles_x) % tiles_y, b = mt / (tiles_x * tiles_y);
-            {
+            const int n0 = nt * BN;
+            if (half == 0) {
                 const int y = tyi * TH + (r >> p.tw_log2), x = txi * TW + (r & (TW - 1));
                 const bool valid = (y < p.Ho) && (x < p.Wo);
                 const int Hp = (p.Ho + 1) >> 1, Wp = (p.Wo + 1) >> 1;
-                ew.pix[lane] = valid ? ((long long)b * p.Ho + y) * p.Wo + x : -1ll;
-                ew.pix_ps[lane] = (((long long)(b * 4 + (y & 1) * 2 + (x & 1))) * Hp + (y >> 1)) * Wp + (x >> 1);
+                eq.pix[lane] = valid ? (int)(((long long)b * p.Ho + y) * p.Wo + x) : -1;
+                eq.pix_ps[lane] = (int)((((long long)(b * 4 + (y & 1) * 2 + (x & 1))) * Hp + (y >> 1)) * Wp + (x >> 1));
             }
-            const int n0 = nt * BN;
+            // the two warps of a quarter exchange the row table through a named barrier (id 1 + q, 64 threads)
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            auto load_res = [&](int nb, float4 (&rv)[8]) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int pixr = eq.pix[i * 4 + g1];
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (resp && pixr >= 0 && nb < p.N) {
+                        const float* rp = resp + (long long)pixr * p.res_ld + nb + col1;
+                        if (res_vec && nb + 32 <= p.N) t = __ldg(reinterpret_cast<const float4*>(rp));
+                        else {
+                            if (nb + col1 + 0 < p.N) t.x = __ldg(rp);
+                            if (nb + col1 + 1 < p.N) t.y = __ldg(rp + 1);
+                            if (nb + col1 + 2 < p.N) t.z = __ldg(rp + 2);
+                            if (nb + col1 + 3 < p.N) t.w = __ldg(rp + 3);
+                        }
+                    }
+                    rv[i] = t;
+                }
+            };
+            float4 rv[8];
+            load_res(n0 + half * 32, rv);  // independent of the accumulator: overlaps the MMA tail
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-            if (p.l2norm) {
+            if (p.l2norm) {  // both warps of the quarter scan the whole row (N <= BN <= 256)
                 float ss = 0.f;
                 for (int c = 0; c < BN; c += 32) {
                     if (n0 + c >= p.N) break;
@@ -282,15 +314,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                     for (int j = 0; j < 32; ++j) {
                         int n = n0 + c + j;
                         if (n < p.N) {
-                            float f = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + n) : 0.f);
+                            float f = __uint_as_float(v[j]) + (biasp ? __ldg(biasp + n) : 0.f);
                             ss += f * f;
                         }
                     }
                 }
-                ew.inv[lane] = fmaxf(sqrtf(ss), 1e-12f);
+                if (half == 0) eq.inv[lane] = fmaxf(sqrtf(ss), 1e-12f);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
             }
-            __syncwarp();
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = half * 32; c < BN; c += 64) {
                 if (n0 + c >= p.N) break;  // warp-uniform
                 const int nb = n0 + c;
                 const bool full32 = (nb + 32 <= p.N);
@@ -298,84 +330,77 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                     uint32_t v[32];
                     tmem_ld32(taddr + c, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) ew.tile[lane][j] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 32; ++j) tile_s[lane * 32 + (j ^ lane)] = __uint_as_float(v[j]);
                 }
+                float4 rcur[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rcur[i] = rv[i];
+                if (c + 64 < BN) load_res(nb + 64, rv);  // prefetch the next chunk's residual
                 __syncwarp();
                 // ---- pass 1 (fp32 mapping: 8 lanes per row): bias, residual, ReLU, L2 norm, fp32 store ----
                 {
-                    const int g = lane >> 3, col = (lane & 7) * 4;
                     float bz[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) bz[k] = (p.bias && nb + col + k < p.N) ? __ldg(p.bias + nb + col + k) : 0.f;
+                    for (int k = 0; k < 4; ++k) bz[k] = (biasp && nb + col1 + k < p.N) ? __ldg(biasp + nb + col1 + k) : 0.f;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int row = i * 4 + g;
-                        const long long pixr = ew.pix[row];
+                        const int row = i * 4 + g1;
+                        const int pixr = eq.pix[row];
                         float f[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) f[k] = ew.tile[row][col + k] + bz[k];
-                        if (p.res && pixr >= 0) {
-                            const float* rp = p.res + pixr * p.res_ld + nb + col;
-                            if (full32 && ((p.res_ld & 3) == 0)) {
-                                const float4 t = *reinterpret_cast<const float4*>(rp);
-                                f[0] += t.x; f[1] += t.y; f[2] += t.z; f[3] += t.w;
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) if (nb + col + k < p.N) f[k] += rp[k];
-                            }
-                        }
+                        for (int k = 0; k < 4; ++k) f[k] = tile_s[row * 32 + ((col1 + k) ^ row)] + bz[k];
+                        f[0] += rcur[i].x; f[1] += rcur[i].y; f[2] += rcur[i].z; f[3] += rcur[i].w;
                         if (p.relu) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) f[k] = fmaxf(f[k], 0.f);
                         }
                         if (p.l2norm) {
-                            const float d = ew.inv[row];
+                            const float d = eq.inv[row];
 #pragma unroll
                             for (int k = 0; k < 4; ++k) f[k] = f[k] / d;
                         }
                         if (p.out_f32 && pixr >= 0) {
-                            float* op = p.out_f32 + pixr * p.ld_f32 + nb + col;
+                            float* op = p.out_f32 + (long long)pixr * p.ld_f32 + nb + col1;
                             if (full32 && ((p.ld_f32 & 3) == 0)) {
                                 *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
                             } else {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) if (nb + col + k < p.N) op[k] = f[k];
+                                for (int k = 0; k < 4; ++k) if (nb + col1 + k < p.N) op[k] = f[k];
                             }
                         }
                         if (p.out_hi || p.ps_hi) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) ew.tile[row][col + k] = f[k];
+                            for (int k = 0; k < 4; ++k) tile_s[row * 32 + ((col1 + k) ^ row)] = f[k];
                         }
                     }
                 }
                 // ---- pass 2 (bf16 mapping: 4 lanes per row): split into hi / lo planes, 16-byte stores ----
                 if (p.out_hi || p.ps_hi) {  // requires N % 32 == 0 (checked on the host)
                     __syncwarp();
-                    const int g = lane >> 2, col = (lane & 3) * 8;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int row = i * 8 + g;
-                        const long long pixr = ew.pix[row];
+                        const int row = i * 8 + g2;
+                        const int pixr = eq.pix[row];
                         uint32_t hi[4], lo[4];
 #pragma unroll
                         for (int k = 0; k < 8; k += 2) {
                             __nv_bfloat16 h0, l0, h1, l1;
-                            split_bf16(ew.tile[row][col + k], h0, l0);
-                            split_bf16(ew.tile[row][col + k + 1], h1, l1);
+                            split_bf16(tile_s[row * 32 + ((col2 + k) ^ row)], h0, l0);
+                            split_bf16(tile_s[row * 32 + ((col2 + k + 1) ^ row)], h1, l1);
                             hi[k >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
                             lo[k >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                         }
                         if (pixr >= 0) {
                             if (p.out_hi) {
-                                *reinterpret_cast<uint4*>(p.out_hi + pixr * p.ld_bf + nb + col) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                                *reinterpret_cast<uint4*>(p.out_hi + (long long)pixr * p.ld_bf + nb + col2) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                                 if (p.out_lo)
-                                    *reinterpret_cast<uint4*>(p.out_lo + pixr * p.ld_bf + nb + col) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                                    *reinterpret_cast<uint4*>(p.out_lo + (long long)pixr * p.ld_bf + nb + col2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                             }
                             if (p.ps_hi) {
-                                const long long pp = ew.pix_ps[row];
-                                *reinterpret_cast<uint4*>(p.ps_hi + pp * p.ld_ps + nb + col) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                                const long long pp = eq.pix_ps[row];
+                                *reinterpret_cast<uint4*>(p.ps_hi + pp * p.ld_ps + nb + col2) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                                 if (p.ps_lo)
-                                    *reinterpret_cast<uint4*>(p.ps_lo + pp * p.ld_ps + nb + col) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                                    *reinterpret_cast<uint4*>(p.ps_lo + pp * p.ld_ps + nb + col2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                             }
                         }
                     }
@@ -383,7 +408,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                 __syncwarp();
             }
             tc_fence_before();
-            __syncwarp();
+            // both warps of the quarter are done with the row table and the accumulator
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
             if (lane == 0) mbar_arrive(&tempty[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }

@@ -358,85 +358,105 @@ __global__ void __launch_bounds__(FIN_THREADS) ransac_finalize_kernel(
         }
         return;
     }
-    // Gauss-Newton / LM iterations on the current inlier set.  phase 0: local optimisation (plain L2,
-    // accepted only if the inlier count does not drop); phase 1: final refinement (Cauchy-weighted).
-    const int total_iters = lo_iters + final_iters;
-    for (int it = 0; it < total_iters; ++it) {
-        const bool final_phase = it >= lo_iters;
-        double acc[28];  // 21 upper-triangular H entries, 6 gradient entries, cost
-#pragma unroll
-        for (int k = 0; k < 28; ++k) acc[k] = 0;
-        for (int i = threadIdx.x; i < m; i += FIN_THREADS) {
-            const double* c = C + (long long)i * 5;
-            const double e = rs::reproj_err2(pose, c);
-            if (!(e <= thr2)) continue;
-            const double X = c[2], Y = c[3], Z = c[4];
-            const double xr = pose.R[0] * X + pose.R[1] * Y + pose.R[2] * Z;
-            const double yr = pose.R[3] * X + pose.R[4] * Y + pose.R[5] * Z;
-            const double zr = pose.R[6] * X + pose.R[7] * Y + pose.R[8] * Z;
-            const double xc = xr + pose.t[0], yc = yr + pose.t[1], zc = zr + pose.t[2];
-            const double iz = 1.0 / zc;
-            const double rx = xc * iz - c[0], ry = yc * iz - c[1];
-            const double w = final_phase ? 1.0 / (1.0 + e / cauchy_scale2) : 1.0;
-            // d(proj)/d(Xc)
-            const double dx[3] = {iz, 0, -xc * iz * iz}, dy[3] = {0, iz, -yc * iz * iz};
-            const double Xr[3] = {xr, yr, zr};
-            double Jx[6], Jy[6];
-            // d(Xc)/d(omega) = -[Xr]_x  ->  row = Xr x d
-            Jx[0] = Xr[1] * dx[2] - Xr[2] * dx[1]; Jx[1] = Xr[2] * dx[0] - Xr[0] * dx[2]; Jx[2] = Xr[0] * dx[1] - Xr[1] * dx[0];
-            Jy[0] = Xr[1] * dy[2] - Xr[2] * dy[1]; Jy[1] = Xr[2] * dy[0] - Xr[0] * dy[2]; Jy[2] = Xr[0] * dy[1] - Xr[1] * dy[0];
-            Jx[3] = dx[0]; Jx[4] = dx[1]; Jx[5] = dx[2];
-            Jy[3] = dy[0]; Jy[4] = dy[1]; Jy[5] = dy[2];
-            int k = 0;
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-#pragma unroll
-                for (int cc = r; cc < 6; ++cc) acc[k++] += w * (Jx[r] * Jx[cc] + Jy[r] * Jy[cc]);
-#pragma unroll
-            for (int r = 0; r < 6; ++r) acc[21 + r] += w * (Jx[r] * rx + Jy[r] * ry);
-            acc[27] += final_phase ? cauchy_scale2 * log1p(e / cauchy_scale2) : e;
-        }
-        block_sum<28>(acc, red, scratch);
-        if (threadIdx.x == 0) {
-            double H[36], g[6], d[6];
-            int k = 0;
-            for (int r = 0; r < 6; ++r)
-                for (int cc = r; cc < 6; ++cc) { H[r * 6 + cc] = red[k]; H[cc * 6 + r] = red[k]; ++k; }
-            for (int r = 0; r < 6; ++r) { g[r] = -red[21 + r]; H[r * 6 + r] += s_lambda * (H[r * 6 + r] + 1e-12); }
-            s_cost = red[27];
-            trial = pose;
-            if (solve6(H, g, d)) {
-                const double th = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-                double dR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-                if (th > 1e-15) {
-                    const double kx = d[0] / th, ky = d[1] / th, kz = d[2] / th;
-                    const double s = sin(th), c1 = 1 - cos(th);
-                    const double K[9] = {0, -kz, ky, kz, 0, -kx, -ky, kx, 0};
-                    double K2[9];
-                    for (int r = 0; r < 3; ++r)
-                        for (int cc = 0; cc < 3; ++cc) K2[r * 3 + cc] = K[r * 3] * K[cc] + K[r * 3 + 1] * K[3 + cc] + K[r * 3 + 2] * K[6 + cc];
-                    for (int i = 0; i < 9; ++i) dR[i] += s * K[i] + c1 * K2[i];
-                }
-                for (int r = 0; r < 3; ++r)
-                    for (int cc = 0; cc < 3; ++cc)
-                        trial.R[r * 3 + cc] = dR[r * 3] * pose.R[cc] + dR[r * 3 + 1] * pose.R[3 + cc] + dR[r * 3 + 2] * pose.R[6 + cc];
-                trial.t[0] = pose.t[0] + d[3]; trial.t[1] = pose.t[1] + d[4]; trial.t[2] = pose.t[2] + d[5];
-            }
-        }
+    // Two refinement phases, each a Levenberg-Marquardt loop over a FIXED correspondence set (the inliers
+    // of the pose the phase starts from), steps accepted on cost decrease only:
+    //   phase 0  local optimisation: plain L2 on the RANSAC winner's inliers; the result replaces the
+    //            winner only if its support (inlier count) does not shrink            (LO-RANSAC)
+    //   phase 1  final refinement: Cauchy-weighted, always kept                       (COLMAP RefineAbsolutePose)
+    __shared__ rs::Pose ref, cur;
+    for (int phase = 0; phase < 2; ++phase) {
+        const bool robust = (phase == 1);
+        const int iters = robust ? final_iters : lo_iters;
+        if (threadIdx.x == 0) { ref = pose; cur = pose; s_lambda = 1e-4; }
         __syncthreads();
-        // evaluate the trial pose: inlier count and cost on ITS inlier set
-        double ev[2] = {0, 0};
-        for (int i = threadIdx.x; i < m; i += FIN_THREADS) {
-            const double e = rs::reproj_err2(trial, C + (long long)i * 5);
-            if (e <= thr2) { ev[0] += 1.0; ev[1] += final_phase ? cauchy_scale2 * log1p(e / cauchy_scale2) : e; }
+        for (int it = 0; it < iters; ++it) {
+            double acc[28];  // 21 upper-triangular H entries, 6 gradient entries, cost
+#pragma unroll
+            for (int k = 0; k < 28; ++k) acc[k] = 0;
+            for (int i = threadIdx.x; i < m; i += FIN_THREADS) {
+                const double* c = C + (long long)i * 5;
+                if (!(rs::reproj_err2(ref, c) <= thr2)) continue;  // fixed set
+                const double X = c[2], Y = c[3], Z = c[4];
+                const double xr = cur.R[0] * X + cur.R[1] * Y + cur.R[2] * Z;
+                const double yr = cur.R[3] * X + cur.R[4] * Y + cur.R[5] * Z;
+                const double zr = cur.R[6] * X + cur.R[7] * Y + cur.R[8] * Z;
+                const double xc = xr + cur.t[0], yc = yr + cur.t[1], zc = fmax(zr + cur.t[2], 1e-9);
+                const double iz = 1.0 / zc;
+                const double rx = xc * iz - c[0], ry = yc * iz - c[1];
+                const double e = rx * rx + ry * ry;
+                const double w = robust ? 1.0 / (1.0 + e / cauchy_scale2) : 1.0;
+                const double dx[3] = {iz, 0, -xc * iz * iz}, dy[3] = {0, iz, -yc * iz * iz};
+                const double Xr[3] = {xr, yr, zr};
+                double Jx[6], Jy[6];
+                // d(Xc)/d(omega) = -[Xr]_x  ->  row = Xr x d
+                Jx[0] = Xr[1] * dx[2] - Xr[2] * dx[1]; Jx[1] = Xr[2] * dx[0] - Xr[0] * dx[2]; Jx[2] = Xr[0] * dx[1] - Xr[1] * dx[0];
+                Jy[0] = Xr[1] * dy[2] - Xr[2] * dy[1]; Jy[1] = Xr[2] * dy[0] - Xr[0] * dy[2]; Jy[2] = Xr[0] * dy[1] - Xr[1] * dy[0];
+                Jx[3] = dx[0]; Jx[4] = dx[1]; Jx[5] = dx[2];
+                Jy[3] = dy[0]; Jy[4] = dy[1]; Jy[5] = dy[2];
+                int k = 0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+#pragma unroll
+                    for (int cc = r; cc < 6; ++cc) acc[k++] += w * (Jx[r] * Jx[cc] + Jy[r] * Jy[cc]);
+#pragma unroll
+                for (int r = 0; r < 6; ++r) acc[21 + r] += w * (Jx[r] * rx + Jy[r] * ry);
+                acc[27] += robust ? cauchy_scale2 * log1p(e / cauchy_scale2) : e;
+            }
+            block_sum<28>(acc, red, scratch);
+            if (threadIdx.x == 0) {
+                double H[36], g[6], d[6];
+                int k = 0;
+                for (int r = 0; r < 6; ++r)
+                    for (int cc = r; cc < 6; ++cc) { H[r * 6 + cc] = red[k]; H[cc * 6 + r] = red[k]; ++k; }
+                for (int r = 0; r < 6; ++r) { g[r] = -red[21 + r]; H[r * 6 + r] += s_lambda * (H[r * 6 + r] + 1e-12); }
+                s_cost = red[27];
+                trial = cur;
+                if (solve6(H, g, d)) {
+                    const double th = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                    double dR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+                    if (th > 1e-15) {
+                        const double kx = d[0] / th, ky = d[1] / th, kz = d[2] / th;
+                        const double sn = sin(th), c1 = 1 - cos(th);
+                        const double K[9] = {0, -kz, ky, kz, 0, -kx, -ky, kx, 0};
+                        double K2[9];
+                        for (int r = 0; r < 3; ++r)
+                            for (int cc = 0; cc < 3; ++cc) K2[r * 3 + cc] = K[r * 3] * K[cc] + K[r * 3 + 1] * K[3 + cc] + K[r * 3 + 2] * K[6 + cc];
+                        for (int i = 0; i < 9; ++i) dR[i] += sn * K[i] + c1 * K2[i];
+                    }
+                    for (int r = 0; r < 3; ++r)
+                        for (int cc = 0; cc < 3; ++cc)
+                            trial.R[r * 3 + cc] = dR[r * 3] * cur.R[cc] + dR[r * 3 + 1] * cur.R[3 + cc] + dR[r * 3 + 2] * cur.R[6 + cc];
+                    trial.t[0] = cur.t[0] + d[3]; trial.t[1] = cur.t[1] + d[4]; trial.t[2] = cur.t[2] + d[5];
+                }
+            }
+            __syncthreads();
+            // cost of the trial pose on the same fixed set
+            double ev[1] = {0};
+            for (int i = threadIdx.x; i < m; i += FIN_THREADS) {
+                const double* c = C + (long long)i * 5;
+                if (!(rs::reproj_err2(ref, c) <= thr2)) continue;
+                const double X = c[2], Y = c[3], Z = c[4];
+                const double zc = fmax(trial.R[6] * X + trial.R[7] * Y + trial.R[8] * Z + trial.t[2], 1e-9);
+                const double rx = (trial.R[0] * X + trial.R[1] * Y + trial.R[2] * Z + trial.t[0]) / zc - c[0];
+                const double ry = (trial.R[3] * X + trial.R[4] * Y + trial.R[5] * Z + trial.t[1]) / zc - c[1];
+                const double e = rx * rx + ry * ry;
+                ev[0] += robust ? cauchy_scale2 * log1p(e / cauchy_scale2) : e;
+            }
+            block_sum<1>(ev, red, scratch);
+            if (threadIdx.x == 0) {
+                if (red[0] < s_cost) { cur = trial; s_lambda = fmax(s_lambda * 0.3, 1e-12); }
+                else s_lambda = fmin(s_lambda * 10.0, 1e8);
+            }
+            __syncthreads();
         }
-        block_sum<2>(ev, red, scratch);
+        // support of the refined pose
+        double sv[1] = {0};
+        for (int i = threadIdx.x; i < m; i += FIN_THREADS)
+            if (rs::reproj_err2(cur, C + (long long)i * 5) <= thr2) sv[0] += 1.0;
+        block_sum<1>(sv, red, scratch);
         if (threadIdx.x == 0) {
             const int cnt = (int)(red[0] + 0.5);
-            // accept when the support does not shrink and (same support -> the cost decreased)
-            const bool accept = cnt > s_best_cnt || (cnt == s_best_cnt && red[1] < s_cost);
-            if (accept) { pose = trial; s_best_cnt = cnt; s_lambda = fmax(s_lambda * 0.3, 1e-12); }
-            else s_lambda = fmin(s_lambda * 10.0, 1e8);
+            if (robust || cnt >= s_best_cnt) { pose = cur; s_best_cnt = cnt; }
         }
         __syncthreads();
     }
