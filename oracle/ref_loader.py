@@ -177,3 +177,14 @@ def random_sfd2_state(seed=0) -> dict:
     conv('convPb', 65, 256, 1)
     conv('convDb', 128, 256, 1)
     return sd
+
+
+def calibrated_adagml_state(seed: int = 7, gain: float = 10.0, bias: float = 0.8) -> dict:
+    """Seeded AdaGML state whose pooling confidences straddle the pruning thresholds (default init sits at
+    ~0.5 < 0.56 and collapses every token set): the last pooling layer is scaled / biased so
+    that tokens are pruned over several layers before the early exit fires."""
+    sd = random_gml_state(seed=seed, ada=True)
+    for i in range(9):
+        sd[f'pooling.{i}.predict.3.weight'] = sd[f'pooling.{i}.predict.3.weight'] * gain
+        sd[f'pooling.{i}.predict.3.bias'] = torch.full((1,), bias)
+    return sd

@@ -87,6 +87,7 @@ class AdaGML(GML):
         ind1 = torch.arange(n_full, device=dev)
         m, n = m_full, n_full
         ni = 0
+        self.last_trace = []  # (layer, tokens0, tokens1) after pruning, for tests / diagnostics
         for ni in range(self.n_layers):
             seg0, seg1 = (0, 1, m), (m, 1, n)
             att = torch.empty((m + n, 2), device=dev, dtype=torch.float32)
@@ -122,6 +123,7 @@ class AdaGML(GML):
                         ws.x_bf.hi[:, :256] = xs.hi
                         if xs.lo is not None:
                             ws.x_bf.lo[:, :256] = xs.lo
+                self.last_trace.append((ni, m, n))
                 if stop:
                     break
         dist = self._distance(pk, ni, ws, 1, m, n)

@@ -42,6 +42,7 @@ class LocalizationPipeline:
         self.focal = focal
         self.max_error = ransac_max_error
         self.cfg = {'min_keypoints': 128, 'max_keypoints': max_keypoints}
+        self.num_hypotheses = 1024
 
     # -- stages -------------------------------------------------------------------------------
     def features(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -73,7 +74,17 @@ class LocalizationPipeline:
         if smap is not None:
             m = self.match(f, smap, shape)
             out.update(m)
+            out.update(self.pose(f, m, smap, shape))
         return out
+
+    def pose(self, f: Dict[str, torch.Tensor], m: Dict[str, torch.Tensor], smap: SyntheticMap, image_shape):
+        """2D-3D matches -> absolute pose per frame (reference singlemap3d.py:156-175: matched keypoints
+        + 0.5, matched xyz, ransac max_error from the config), entirely on the device."""
+        h, w = image_shape[-2:]
+        r = ops.ransac_pnp(f['keypoints'], m['matches0'], smap.xyz, self.focal, self.focal, w / 2.0, h / 2.0,
+                           self.max_error, pixel_shift=0.5, num_hypotheses=self.num_hypotheses, seed=0)
+        return {'qvec': r['qvec'], 'tvec': r['tvec'], 'num_inliers': r['num_inliers'], 'inliers': r['inliers'],
+                'pose_success': r['success']}
 
     # -- CUDA graph: one replay per batch instead of ~1000 launches + tensor-map encodes -----------------
     @torch.no_grad()
@@ -132,3 +143,35 @@ class LocalizationPipeline:
         desc = torch.where(outl[..., None], rnd_desc, desc)
         xyz = torch.where(outl[..., None], rnd_xyz, xyz)
         return SyntheticMap(desc.contiguous(), kp.contiguous(), xyz.contiguous(), perm, outl, R, t)
+
+
+# ---- frame sharding across ranks (one process per GPU) ---------------------------------------------------
+
+def shard_frames(n_frames: int, rank: int, world: int):
+    """Frame ids owned by ``rank``: round-robin, ``i -> rank i % world``.  Frames are
+    independent units, so this is the whole multi-GPU data path; no activation ever crosses ranks."""
+    return list(range(rank, n_frames, world))
+
+
+def pack_pose_records(frame_ids, qvec: torch.Tensor, tvec: torch.Tensor, num_inliers: torch.Tensor) -> torch.Tensor:
+    """[n, 9] float64 records ``[frame_id, qw,qx,qy,qz, tx,ty,tz, num_inliers]`` (72 bytes per frame)."""
+    rec = torch.zeros((len(frame_ids), 9), dtype=torch.float64, device=qvec.device)
+    rec[:, 0] = torch.as_tensor(frame_ids, dtype=torch.float64, device=qvec.device)
+    rec[:, 1:5] = qvec.double()
+    rec[:, 5:8] = tvec.double()
+    rec[:, 8] = num_inliers.double()
+    return rec
+
+
+def gather_pose_records(rec: torch.Tensor) -> torch.Tensor:
+    """The path's single collective: all_gather of the fixed-size pose records (NCCL over NVLink on GPUs,
+    gloo in the CPU tests), returned sorted by frame id.  Every rank must contribute the same number of
+    records (pad with frame_id = -1)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return rec
+    out = [torch.zeros_like(rec) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, rec)
+    allrec = torch.cat(out, 0)
+    allrec = allrec[allrec[:, 0] >= 0]
+    return allrec[torch.argsort(allrec[:, 0])]

@@ -209,3 +209,88 @@ def test_gml_random_weights_batched_vs_oracle(lib, dev, precision):
     assert torch.equal(out['matches0'].cpu()[decisive], ref['matches0'][decisive])
     with pytest.raises(ValueError):
         net({'descriptors0': d0.to(dev), 'descriptors1': d1.to(dev), 'keypoints0': k0.to(dev), 'keypoints1': k1.to(dev)})
+
+
+def _adagml_case():
+    g = torch.Generator().manual_seed(0)
+    m = n = 400
+    d0 = torch.nn.functional.normalize(torch.randn(1, m, 128, generator=g), dim=-1)
+    perm = torch.randperm(n, generator=g)
+    d1 = d0[:, perm] + 0.02 * torch.randn(1, n, 128, generator=g)
+    k0 = torch.rand(1, m, 2, generator=g) * torch.tensor([640., 480.])
+    return {'descriptors0': d0, 'descriptors1': d1, 'keypoints0': k0, 'keypoints1': k0[:, perm],
+            'scores0': torch.rand(1, m, generator=g), 'scores1': torch.rand(1, n, generator=g),
+            'image_shape0': (1, 3, 640, 480), 'image_shape1': (1, 3, 640, 480)}
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_adagml_pruning_vs_oracle(lib, dev, precision):
+    """AdaGML with calibrated pooling weights: token pruning over several layers + early exit must follow
+    the oracle's trace (data-dependent control flow), scores within tolerance."""
+    from pram_b200.nets.adagml import AdaGML
+    sd = RL.calibrated_adagml_state()
+    data = _adagml_case()
+    ref = O.adagml_forward(sd, data, return_trace=True)
+    assert len(ref['trace']) >= 3 and ref['trace'][-1][1] < 200  # the case really prunes
+    net = AdaGML({})
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).set_precision(precision)
+    out = net({k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()})
+    assert out['matches0'].shape == (1, 400) and out['matching_scores0'].shape == (1, 400)
+    if precision == 'fp32':
+        assert net.last_trace == ref['trace']
+        assert torch.allclose(out['matching_scores0'].cpu(), ref['matching_scores0'], atol=2e-3)
+        decisive = (ref['matching_scores0'] - 0.2).abs() > 5e-3
+        assert torch.equal(out['matches0'].cpu()[decisive], ref['matches0'][decisive])
+    else:  # confidences within ~1e-4 of a threshold may flip a token: allow a few tokens of slack per layer
+        assert len(net.last_trace) == len(ref['trace'])
+        for (l0, a0, b0), (l1, a1, b1) in zip(net.last_trace, ref['trace']):
+            assert l0 == l1 and abs(a0 - a1) <= 4 and abs(b0 - b1) <= 4
+    with pytest.raises(ValueError):
+        net({k: (v.to(dev).repeat(2, 1, 1) if torch.is_tensor(v) and v.dim() == 3 else v) for k, v in data.items()})
+
+
+def test_extract_sfd2_return_vs_oracle(lib, dev, golden):
+    """Offline export variant (NMS radius 3, strict threshold, score-descending, x/(w/2)-1 sampling)."""
+    if RL.weight_path(RL.SFD2_WEIGHT) is None:
+        pytest.skip('SFD2 checkpoint not staged')
+    from pram_b200.nets.sfd2 import ResNet4x, extract_sfd2_return
+    sd = RL.load_sfd2_state()
+    img = torch.from_numpy(O.polys_frame(120, 160, seed=3)).permute(2, 0, 1)[None]
+    ref = O.sfd2_extract_return(sd, img, conf_th=0.005, topK=4096)
+    net = ResNet4x()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).set_precision('fp32')
+    out = extract_sfd2_return(net, img, conf_th=0.005, topK=4096, scales=[1.0])
+    assert out['keypoints'].dtype == np.float64 and out['descriptors'].shape[1] == 128
+    ours = {(float(x), float(y)) for x, y in out['keypoints']}
+    theirs = {(float(x), float(y)) for x, y in ref['keypoints']}
+    assert len(ours & theirs) >= 0.97 * len(theirs)
+    io = {k: i for i, k in enumerate(map(tuple, out['keypoints']))}
+    ir = {k: i for i, k in enumerate(map(tuple, ref['keypoints']))}
+    for k in list(ours & theirs)[:40]:
+        assert np.abs(out['descriptors'][io[k]] - ref['descriptors'][ir[k]]).max() < 5e-4
+        assert abs(out['scores'][io[k]] - ref['scores'][ir[k]]) < 2e-5
+    assert np.all(np.diff(out['scores']) <= 1e-7)  # score-descending
+
+
+def test_feature_matching_plugin(lib, dev, golden):
+    """pose_estimator.feature_matching + the dynamic_load'ed matcher plugin (reference pose_estimator.py:45-86)."""
+    if RL.weight_path(RL.GML_WEIGHT) is None:
+        pytest.skip('GML checkpoint not staged')
+    import pram_b200.localization.matchers as matchers
+    from pram_b200.localization.base_model import dynamic_load
+    from pram_b200.localization.pose_estimator import feature_matching
+    g = golden('gml_selfmatch.npz')
+    Model = dynamic_load(matchers, 'gml')
+    model = Model({'name': 'gml', 'weight_path': str(RL.weight_path(RL.GML_WEIGHT)), 'sinkhorn_iterations': 20}).eval().to(dev)
+    kp, desc, perm = g['keypoints0'], g['descriptors0'], g['perm']
+    q = {'keypoints': kp, 'scores': np.ones(len(kp), np.float32), 'descriptors': desc, 'image_size': (160, 120)}
+    ids = np.arange(len(perm)) + 1000
+    ids[::5] = -1  # database keypoints without a 3-D point are excluded and the ids remapped
+    db = {'keypoints': kp[perm], 'scores': np.ones(len(perm), np.float32), 'descriptors': desc[perm],
+          'image_size': (160, 120), 'db_3D_ids': ids}
+    m = feature_matching(q, db, model)
+    ok = m >= 0
+    assert ok.sum() > 50
+    assert np.all(ids[m[ok]] != -1) and np.array_equal(perm[m[ok]], np.nonzero(ok)[0])
