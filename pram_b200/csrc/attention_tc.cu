@@ -6,7 +6,7 @@
 //   warp 0  : TMA producer   Q {64 x 128}, K {64 x 128}, V^T {2 x (64 keys x 64 d)} -> SWIZZLE_128B smem
 //   warp 1  : MMA issuer     S = Q K^T  (SS, fp32 in TMEM, double buffered)
 //                            O += P V   (TS: P read from TMEM as the A operand, V^T from smem)
-//   warps 2-5: softmax       one thread per query row (TMEM lane): tcgen05.ld S, running max with lazy
+//   warps 2-9: softmax       one thread per query row and half of the keys: tcgen05.ld S, running max with lazy
 //                            rescale of O (only when the max moved by > 8 in log2 units), exp2,
 //                            P packed to bf16 and written back to TMEM with tcgen05.st; epilogue O / l
 // SPLIT=3 keeps ~fp32 accuracy with bf16 tensor-core operands: Q,K,V and P are hi/lo split and each
@@ -18,7 +18,7 @@
 namespace fa {
 
 constexpr int BQ = 128, BKV = 128, HD = 64;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 8 softmax warps
 constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_PHI = 256, COL_PLO = 320, COL_O = 384, TMEM_COLS = 512;
 
 struct Args {
@@ -123,7 +123,7 @@ struct Cfg {
     static constexpr int V_BYTES = BKV * HD * 2;          // two boxes of 64 d x 64 keys
     static constexpr int KV_STAGE = NPL * (K_BYTES + V_BYTES);
     static constexpr int STAGES = 2;
-    static constexpr int SMEM_BYTES = NPL * Q_BYTES + STAGES * KV_STAGE + 1024 + 256;
+    static constexpr int SMEM_BYTES = NPL * Q_BYTES + STAGES * KV_STAGE + 1024 + 256 + 2048 /*row max/sum exchange*/;
 };
 
 template <int SPLIT>
@@ -156,9 +156,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
         mbar_init(q_full, 1); mbar_init(q_empty, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
-            mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4);
+            mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8);
         }
-        mbar_init(p_full, 4); mbar_init(o_done, 1);
+        mbar_init(p_full, 8); mbar_init(o_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -248,31 +248,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
             }
         }
     } else if (warp >= 2) {
-        // ===================== softmax + epilogue: thread <-> query row =====================
-        const int qd = warp & 3;
+        // ===================== softmax + epilogue (8 warps) =====================
+        // thread <-> query row (TMEM lane); the two warps of a lane quarter split the 128 key columns of a
+        // tile (64 each, held in registers -> single pass over S), exchange their row maxima / row sums
+        // through shared memory, and split the 64 O columns for rescaling and the epilogue.
+        const int qd = warp & 3, half = (warp - 2) >> 2;
         const int r = qd * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        float* xch = reinterpret_cast<float*>(tmem_base_s + 4);  // [2 parity][2 half][128 rows]
+        const uint32_t bar_id = 1 + qd;
         uint32_t g = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x) {
             const int bh = item / q_tiles, q0 = (item % q_tiles) * BQ;
-            float m_used = -INFINITY, l = 0.f;
+            float m_used = -INFINITY, l = 0.f;  // l: this thread's partial row sum (its 64 columns)
             for (int j = 0; j < kv_tiles; ++j, ++g) {
                 const int st = g & 1;
-                const uint32_t s_addr = tmem_base + lane_off + (st ? COL_S1 : COL_S0);
-                const int nvalid = min(BKV, p.Nk - j * BKV);
+                const uint32_t s_addr = tmem_base + lane_off + (st ? COL_S1 : COL_S0) + half * 64;
+                const int nvalid = min(BKV, p.Nk - j * BKV) - half * 64;  // valid columns of this half (may be <= 0)
                 mbar_wait(&s_full[st], (g >> 1) & 1);
                 tc_fence_after();
-                // pass 1: row max of the scaled logits over the valid keys
-                float mx = -INFINITY;
-#pragma unroll 1
-                for (int c = 0; c < BKV; c += 32) {
-                    if (c >= nvalid) break;
-                    uint32_t v[32];
-                    tmem_ld32(s_addr + c, v);
+                uint32_t v0[32], v1[32];
+                tmem_ld32(s_addr, v0);
+                tmem_ld32(s_addr + 32, v1);
+                if (nvalid < 64) {  // last, partial tile: mask the tail (warp-uniform branch)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]) * p.scale_log2);
+                    for (int i = 0; i < 32; ++i) {
+                        if (i >= nvalid) v0[i] = 0xff800000u;       // -inf
+                        if (32 + i >= nvalid) v1[i] = 0xff800000u;
+                    }
                 }
+                float mx = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+                mx *= p.scale_log2;  // scale > 0
+                float* x = xch + (g & 1) * 256;
+                x[half * 128 + r] = mx;
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                mx = fmaxf(x[r], x[128 + r]);
                 // lazy rescale: keep the stale reference max unless it moved by more than 8 (log2 units)
                 const bool need = (mx > m_used + 8.f);
                 const bool warp_need = __any_sync(0xffffffffu, need) || (j == 0);
@@ -283,66 +295,66 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                     m_used = m_new;
                     l *= corr;
                 }
+                // p = exp2(s*scale - m) for this thread's 64 columns, packed to bf16 hi / lo
+                uint32_t ph[32], pl[32];
+                float lsum = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0, p1, p2, p3;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v0[i]), p.scale_log2, -m_used)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v0[i + 1]), p.scale_log2, -m_used)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p2) : "f"(fmaf(__uint_as_float(v1[i]), p.scale_log2, -m_used)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p3) : "f"(fmaf(__uint_as_float(v1[i + 1]), p.scale_log2, -m_used)));
+                    lsum += (p0 + p1) + (p2 + p3);
+                    __nv_bfloat162 ha = p.p_swap ? __floats2bfloat162_rn(p1, p0) : __floats2bfloat162_rn(p0, p1);
+                    __nv_bfloat162 hb = p.p_swap ? __floats2bfloat162_rn(p3, p2) : __floats2bfloat162_rn(p2, p3);
+                    const uint32_t ua = *reinterpret_cast<uint32_t*>(&ha), ub = *reinterpret_cast<uint32_t*>(&hb);
+                    ph[i >> 1] = ua;
+                    ph[16 + (i >> 1)] = ub;
+                    if (SPLIT == 3) {
+                        const float a_lo = (p.p_swap ? p1 : p0) - __uint_as_float(ua << 16);
+                        const float a_hi = (p.p_swap ? p0 : p1) - __uint_as_float(ua & 0xffff0000u);
+                        const float b_lo = (p.p_swap ? p3 : p2) - __uint_as_float(ub << 16);
+                        const float b_hi = (p.p_swap ? p2 : p3) - __uint_as_float(ub & 0xffff0000u);
+                        __nv_bfloat162 la = __floats2bfloat162_rn(a_lo, a_hi), lb = __floats2bfloat162_rn(b_lo, b_hi);
+                        pl[i >> 1] = *reinterpret_cast<uint32_t*>(&la);
+                        pl[16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&lb);
+                    }
+                }
+                l += lsum;
                 // P (and O) may be touched only after the previous PV retired
                 if (j > 0) {
                     mbar_wait(o_done, (g - 1) & 1);
                     tc_fence_after();
                     if (warp_need) {
-                        const uint32_t o_addr = tmem_base + lane_off + COL_O;
-#pragma unroll 1
-                        for (int c = 0; c < HD; c += 32) {
-                            uint32_t v[32];
-                            tmem_ld32(o_addr + c, v);
+                        const uint32_t o_addr = tmem_base + lane_off + COL_O + half * 32;
+                        uint32_t o[32];
+                        tmem_ld32(o_addr, o);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * corr);
-                            tmem_st32(o_addr + c, v);
-                        }
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+                        tmem_st32(o_addr, o);
                     }
                 }
-                // pass 2: p = exp2(s*scale - m), packed bf16 (hi / lo) back into TMEM
-#pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t ph[32], pl[32];
-#pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int c = h * 64 + cc * 32;
-                        uint32_t v[32];
-                        if (c < nvalid) tmem_ld32(s_addr + c, v);
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            float p0 = 0.f, p1 = 0.f;
-                            if (c + i < nvalid) p0 = exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_used);
-                            if (c + i + 1 < nvalid) p1 = exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_used);
-                            l += p0 + p1;
-                            const __nv_bfloat16 h0 = __float2bfloat16_rn(p0), h1 = __float2bfloat16_rn(p1);
-                            const __nv_bfloat16 l0 = __float2bfloat16_rn(p0 - __bfloat162float(h0));
-                            const __nv_bfloat16 l1 = __float2bfloat16_rn(p1 - __bfloat162float(h1));
-                            uint32_t a = __bfloat16_as_ushort(h0), b = __bfloat16_as_ushort(h1);
-                            uint32_t la = __bfloat16_as_ushort(l0), lb = __bfloat16_as_ushort(l1);
-                            if (p.p_swap) { uint32_t t = a; a = b; b = t; t = la; la = lb; lb = t; }
-                            ph[cc * 16 + (i >> 1)] = a | (b << 16);
-                            pl[cc * 16 + (i >> 1)] = la | (lb << 16);
-                        }
-                    }
-                    tmem_st32(tmem_base + lane_off + COL_PHI + h * 32, ph);
-                    if (SPLIT == 3) tmem_st32(tmem_base + lane_off + COL_PLO + h * 32, pl);
-                }
+                tmem_st32(tmem_base + lane_off + COL_PHI + half * 32, ph);
+                if (SPLIT == 3) tmem_st32(tmem_base + lane_off + COL_PLO + half * 32, pl);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&s_empty[st]); mbar_arrive(p_full); }
             }
-            // epilogue: O / l
+            // epilogue: O / l (row sum = both halves), each warp stores 32 of the 64 head dims
+            float* x = xch + (g & 1) * 256;
+            x[half * 128 + r] = l;
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            const float inv = 1.f / (x[r] + x[128 + r]);
             mbar_wait(o_done, (g - 1) & 1);
             tc_fence_after();
             const int qn = q0 + r;
-            const float inv = 1.f / l;
             const int b = bh / p.heads, hh = bh - b * p.heads;
-            const long long orow = ((long long)b * p.Nq + qn) * p.out_ld + hh * HD;
-#pragma unroll 1
-            for (int c = 0; c < HD; c += 32) {
+            const long long orow = ((long long)b * p.Nq + qn) * p.out_ld + hh * HD + half * 32;
+            {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + lane_off + COL_O + c, v);
+                tmem_ld32(tmem_base + lane_off + COL_O + half * 32, v);
                 if (qn < p.Nq) {
                     float f[32];
 #pragma unroll
@@ -350,23 +362,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                     if (p.out_f32) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4)
-                            *reinterpret_cast<float4*>(p.out_f32 + orow + c + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                            *reinterpret_cast<float4*>(p.out_f32 + orow + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
                     }
                     if (p.out_hi) {
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) {
-                            const __nv_bfloat16 h0 = __float2bfloat16_rn(f[i]), h1 = __float2bfloat16_rn(f[i + 1]);
-                            const __nv_bfloat16 l0 = __float2bfloat16_rn(f[i] - __bfloat162float(h0));
-                            const __nv_bfloat16 l1 = __float2bfloat16_rn(f[i + 1] - __bfloat162float(h1));
-                            hi[i >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            lo[i >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[i], f[i + 1]);
+                            const uint32_t u = *reinterpret_cast<uint32_t*>(&h2);
+                            hi[i >> 1] = u;
+                            __nv_bfloat162 l2 = __floats2bfloat162_rn(f[i] - __uint_as_float(u << 16), f[i + 1] - __uint_as_float(u & 0xffff0000u));
+                            lo[i >> 1] = *reinterpret_cast<uint32_t*>(&l2);
                         }
-                        uint4* oh = reinterpret_cast<uint4*>(p.out_hi + orow + c);
+                        uint4* oh = reinterpret_cast<uint4*>(p.out_hi + orow);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
                         if (p.out_lo) {
-                            uint4* ol = reinterpret_cast<uint4*>(p.out_lo + orow + c);
+                            uint4* ol = reinterpret_cast<uint4*>(p.out_lo + orow);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
                         }
@@ -374,6 +386,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                 }
             }
             tc_fence_before();  // O reads ordered before the next item's first PV (gated by p_full)
+            // the partner must have read this item's row sums before the exchange slot is reused
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
         }
     }
     tc_fence_before();
