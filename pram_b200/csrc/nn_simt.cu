@@ -348,6 +348,70 @@ PRAM_API int pram_l2norm_rows(const float* in, float* out, long long rows, int C
 // ------------------------------------------------------------------------------------------
 // LayerNorm (eps 1e-5, biased variance) + exact GELU, warp per row, in place ok
 // ------------------------------------------------------------------------------------------
+// single-pass variant for C % 128 == 0 (256 / 512 / 1024): the row lives in registers (NV float4 per
+// lane), one 16-byte load and one 16-byte (fp32) / 8-byte (bf16 plane) store per element group
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_gelu_vec_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float* __restrict__ out,
+                                                                __nv_bfloat16* __restrict__ out_hi,
+                                                                __nv_bfloat16* __restrict__ out_lo, long long rows, int gelu) {
+    constexpr int C = NV * 128;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4* p = reinterpret_cast<const float4*>(in + row * C);
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        v[k] = p[lane + 32 * k];
+        s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int c4 = lane + 32 * k;
+        const float4 g = reinterpret_cast<const float4*>(gamma)[c4], bt = reinterpret_cast<const float4*>(beta)[c4];
+        float o[4] = {(v[k].x - mean) * rstd * g.x + bt.x, (v[k].y - mean) * rstd * g.y + bt.y,
+                      (v[k].z - mean) * rstd * g.z + bt.z, (v[k].w - mean) * rstd * g.w + bt.w};
+        if (gelu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = 0.5f * o[j] * (1.f + erff(o[j] * 0.70710678118654752440f));
+        }
+        if (out) reinterpret_cast<float4*>(out + row * C)[c4] = make_float4(o[0], o[1], o[2], o[3]);
+        if (out_hi) {
+            __nv_bfloat16 h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                h[j] = __float2bfloat16_rn(o[j]);
+                l[j] = __float2bfloat16_rn(o[j] - __bfloat162float(h[j]));
+            }
+            reinterpret_cast<uint2*>(out_hi + row * C)[c4] = *reinterpret_cast<uint2*>(h);
+            if (out_lo) reinterpret_cast<uint2*>(out_lo + row * C)[c4] = *reinterpret_cast<uint2*>(l);
+        }
+    }
+}
+
+static bool layernorm_vec_launch(const float* in, const float* gamma, const float* beta, float* out, void* hi, void* lo,
+                                 long long rows, int C, int gelu, cudaStream_t stream) {
+    const int grid = cdiv(rows * 32, 256);
+    __nv_bfloat16* h = (__nv_bfloat16*)hi;
+    __nv_bfloat16* l = (__nv_bfloat16*)lo;
+    switch (C) {
+        case 256: layernorm_gelu_vec_kernel<2><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu); return true;
+        case 512: layernorm_gelu_vec_kernel<4><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu); return true;
+        case 1024: layernorm_gelu_vec_kernel<8><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu); return true;
+        default: return false;
+    }
+}
+
 __global__ void layernorm_gelu_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, float* __restrict__ out,
                                       __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
@@ -377,7 +441,8 @@ __global__ void layernorm_gelu_kernel(const float* __restrict__ in, const float*
 PRAM_API int pram_layernorm_gelu(const float* in, const float* gamma, const float* beta, float* out,
                                  long long rows, int C, int gelu, cudaStream_t stream) {
     if (!in || !out || !gamma || !beta) return PRAM_ERR_ARG;
-    layernorm_gelu_kernel<<<cdiv(rows * 32, 256), 256, 0, stream>>>(in, gamma, beta, out, nullptr, nullptr, rows, C, gelu);
+    if (!layernorm_vec_launch(in, gamma, beta, out, nullptr, nullptr, rows, C, gelu, stream))
+        layernorm_gelu_kernel<<<cdiv(rows * 32, 256), 256, 0, stream>>>(in, gamma, beta, out, nullptr, nullptr, rows, C, gelu);
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
 }
@@ -386,8 +451,9 @@ PRAM_API int pram_layernorm_gelu_split(const float* in, const float* gamma, cons
                                        void* out_hi, void* out_lo, long long rows, int C, int gelu,
                                        cudaStream_t stream) {
     if (!in || !gamma || !beta || (!out_f32 && !out_hi)) return PRAM_ERR_ARG;
-    layernorm_gelu_kernel<<<cdiv(rows * 32, 256), 256, 0, stream>>>(in, gamma, beta, out_f32, (__nv_bfloat16*)out_hi,
-                                                                   (__nv_bfloat16*)out_lo, rows, C, gelu);
+    if (!layernorm_vec_launch(in, gamma, beta, out_f32, out_hi, out_lo, rows, C, gelu, stream))
+        layernorm_gelu_kernel<<<cdiv(rows * 32, 256), 256, 0, stream>>>(in, gamma, beta, out_f32, (__nv_bfloat16*)out_hi,
+                                                                       (__nv_bfloat16*)out_lo, rows, C, gelu);
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
 }
