@@ -148,12 +148,13 @@ int pram_gemm_tc(const pram_tc_args* args, pram_stream_t stream);
 
 /* K10/K12/K13 (tensor-core path): flash attention on tcgen05, head dim 64.  S = QK^T and O += PV on the
  * tensor cores (P is fed back from TMEM as the A operand), softmax on one thread per query row.
- * q/k: bf16 [B*heads][N][64]; vt: bf16 [B*heads][64][nk_pad] (keys contiguous); *_lo NULL when split == 1.
+ * q/k: bf16 [B*heads][N][64]; vt: bf16 [B*heads][64][nk_pad] (keys contiguous) when v_mn == 0, or V itself
+ * [B*heads][Nk][64] when v_mn == 1 (MN-major UMMA operand); *_lo NULL when split == 1.
  * Replaces Attention.forward, nets/segnetvit.py:73-76 and the two einsum+softmax pairs of
  * nets/gml.py:175-181. */
 int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
                       const void* vt_lo, int B, int heads, int Nq, int Nk, int nk_pad, float scale, float* out_f32,
-                      void* out_hi, void* out_lo, int out_ld, int split, int p_swap, pram_stream_t stream);
+                      void* out_hi, void* out_lo, int out_ld, int split, int p_swap, int v_mn, pram_stream_t stream);
 
 /* qkv fp32 rows -> the attention kernel's operands (rotary + scale on q,k; V transposed per head).
  * nets/segnetvit.py:98-103, nets/gml.py:169-174. */

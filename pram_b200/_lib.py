@@ -66,7 +66,7 @@ class TcArgs(C.Structure):
 
 SIGNATURES['pram_gemm_tc'] = (_I, [C.POINTER(TcArgs), _P])
 SIGNATURES['pram_split_bf16'] = (_I, [_P, _P, _P, _L, _P])
-SIGNATURES['pram_attention_tc'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I, _I, _I, _P])
+SIGNATURES['pram_attention_tc'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I, _I, _I, _I, _P])
 SIGNATURES['pram_attention_prep'] = (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P, _I, _P])
 _D = C.c_double
 SIGNATURES['pram_ransac_workspace_bytes'] = (_L, [_I, _I, _I])

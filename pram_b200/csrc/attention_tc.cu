@@ -26,6 +26,7 @@ struct Args {
     float scale_log2;  // softmax scale * log2(e)
     float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_ld;
     int p_swap;        // debug: swap the two bf16 halves of a packed P column
+    int v_mn;          // 1: V given as [BH][Nk][64] (MN-major B operand), 0: V^T [BH][64][nk_pad] (K-major)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -72,6 +73,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {  // K-major SWIZ
 }
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// MN-major SWIZZLE_128B operand (rows = K index, 64 MN elements = 128 B contiguous per row):
+// SBO = 1024 B between 8-row K groups, LBO = stride between 64-element MN blocks (single block here)
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(16384 >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
 }
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -188,19 +200,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                 mbar_expect_tx(&kv_full[st], C::KV_STAGE);
                 const int k0 = j * BKV;
                 tma_load_3d(ks, &map_k_hi, &kv_full[st], 0, k0, bh);
-                tma_load_3d(vs, &map_v_hi, &kv_full[st], k0, 0, bh);
-                tma_load_3d(vs + C::V_BYTES / 2, &map_v_hi, &kv_full[st], k0 + 64, 0, bh);
+                if (p.v_mn) {
+                    tma_load_3d(vs, &map_v_hi, &kv_full[st], 0, k0, bh);  // one {64 d x 128 keys} box
+                } else {
+                    tma_load_3d(vs, &map_v_hi, &kv_full[st], k0, 0, bh);
+                    tma_load_3d(vs + C::V_BYTES / 2, &map_v_hi, &kv_full[st], k0 + 64, 0, bh);
+                }
                 if (SPLIT == 3) {
                     tma_load_3d(ks + C::K_BYTES, &map_k_lo, &kv_full[st], 0, k0, bh);
-                    tma_load_3d(vs + C::V_BYTES, &map_v_lo, &kv_full[st], k0, 0, bh);
-                    tma_load_3d(vs + C::V_BYTES + C::V_BYTES / 2, &map_v_lo, &kv_full[st], k0 + 64, 0, bh);
+                    if (p.v_mn) {
+                        tma_load_3d(vs + C::V_BYTES, &map_v_lo, &kv_full[st], 0, k0, bh);
+                    } else {
+                        tma_load_3d(vs + C::V_BYTES, &map_v_lo, &kv_full[st], k0, 0, bh);
+                        tma_load_3d(vs + C::V_BYTES + C::V_BYTES / 2, &map_v_lo, &kv_full[st], k0 + 64, 0, bh);
+                    }
                 }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc_s = make_idesc(BQ, BKV);
-        constexpr uint32_t idesc_o = make_idesc(BQ, HD);
+        const uint32_t idesc_o = make_idesc(BQ, HD) | (p.v_mn ? (1u << 16) : 0u);  // bit 16: B is MN-major
         uint32_t g = 0, w = 0;
         const uint32_t q_hi = smem_u32(q_s), q_lo = q_hi + C::Q_BYTES;
         auto issue_S = [&](uint32_t gg) {
@@ -235,12 +255,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                 const uint32_t d = tmem_base + COL_O;
 #pragma unroll
                 for (int ks = 0; ks < BKV / 16; ++ks) {
-                    const uint32_t vo = (ks >> 2) * (C::V_BYTES / 2) + (ks & 3) * 32;
+                    const uint32_t vo = p.v_mn ? ks * 2048 : (ks >> 2) * (C::V_BYTES / 2) + (ks & 3) * 32;
                     const uint32_t a_hi = tmem_base + COL_PHI + ks * 8, a_lo = tmem_base + COL_PLO + ks * 8;
-                    umma_ts(d, a_hi, make_desc(v_hi + vo), idesc_o, (j | ks) != 0);
+                    const uint64_t bh_d = p.v_mn ? make_desc_mn(v_hi + vo) : make_desc(v_hi + vo);
+                    umma_ts(d, a_hi, bh_d, idesc_o, (j | ks) != 0);
                     if (SPLIT == 3) {
-                        umma_ts(d, a_lo, make_desc(v_hi + vo), idesc_o, 1);
-                        umma_ts(d, a_hi, make_desc(v_lo + vo), idesc_o, 1);
+                        umma_ts(d, a_lo, bh_d, idesc_o, 1);
+                        umma_ts(d, a_hi, p.v_mn ? make_desc_mn(v_lo + vo) : make_desc(v_lo + vo), idesc_o, 1);
                     }
                 }
                 umma_commit(&kv_empty[st]);
@@ -429,17 +450,18 @@ static int encode3(CUtensorMap* m, const void* base, cuuint64_t d0, cuuint64_t d
 
 }  // namespace fa
 
-// q/k: bf16 [BH][N][64]; vt: bf16 [BH][64][nk_pad] (keys contiguous, nk_pad % 8 == 0, padding zeroed);
+// q/k: bf16 [BH][N][64]; v_mn = 0: vt bf16 [BH][64][nk_pad] (keys contiguous, nk_pad % 8 == 0, padding zeroed);
+// v_mn = 1: vt is V itself, bf16 [BH][Nk][64] (consumed as an MN-major UMMA operand, no transposition);
 // *_lo may be NULL when split == 1.  out: f32 and/or split bf16 [B][Nq][out_ld] at column head*64.
 PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
                                const void* vt_lo, int B, int heads, int Nq, int Nk, int nk_pad, float scale,
                                float* out_f32, void* out_hi, void* out_lo, int out_ld, int split, int p_swap,
-                               cudaStream_t stream) {
+                               int v_mn, cudaStream_t stream) {
     using namespace fa;
     if (!q_hi || !k_hi || !vt_hi || B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return PRAM_ERR_ARG;
     if (split != 1 && split != 3) return PRAM_ERR_ARG;
     if (split == 3 && (!q_lo || !k_lo || !vt_lo)) return PRAM_ERR_ARG;
-    if ((nk_pad % 8) || nk_pad < Nk || (out_ld % 8)) return PRAM_ERR_UNSUPPORTED;
+    if ((!v_mn && ((nk_pad % 8) || nk_pad < Nk)) || (out_ld % 8)) return PRAM_ERR_UNSUPPORTED;
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
@@ -456,7 +478,8 @@ PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k
         if (rc) return rc;
         rc = encode3(&mk[i], ks[i], HD, Nk, BH, HD * 2, (cuuint64_t)Nk * HD * 2, HD, BKV);
         if (rc) return rc;
-        rc = encode3(&mv[i], vs[i], nk_pad, HD, BH, (cuuint64_t)nk_pad * 2, (cuuint64_t)nk_pad * HD * 2, 64, HD);
+        if (v_mn) rc = encode3(&mv[i], vs[i], HD, Nk, BH, HD * 2, (cuuint64_t)Nk * HD * 2, HD, BKV);
+        else rc = encode3(&mv[i], vs[i], nk_pad, HD, BH, (cuuint64_t)nk_pad * 2, (cuuint64_t)nk_pad * HD * 2, 64, HD);
         if (rc) return rc;
     }
     Args a;
@@ -464,6 +487,7 @@ PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k
     a.scale_log2 = scale * 1.4426950408889634f;
     a.out_f32 = out_f32; a.out_hi = (__nv_bfloat16*)out_hi; a.out_lo = (__nv_bfloat16*)out_lo; a.out_ld = out_ld;
     a.p_swap = p_swap;
+    a.v_mn = v_mn;
     const int total = BH * ((Nq + BQ - 1) / BQ);
     const int grid = total < num_sms ? total : num_sms;
     if (split == 3) {

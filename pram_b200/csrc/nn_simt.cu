@@ -206,7 +206,7 @@ PRAM_API int pram_linear_f32(const float* a, long long lda, const float* w, cons
 // pixels per thread so each shared-memory weight read feeds 4 FMAs.
 // weights in smem as [tap][ci][co][group].
 // ------------------------------------------------------------------------------------------
-constexpr int GC_PX = 4;
+constexpr int GC_PX = 8;   // output pixels per thread: each shared-memory weight read feeds 8 FMAs (FMA-bound)
 __global__ void __launch_bounds__(256) gconv3x3_kernel(const float* __restrict__ in,
                                                        const float* __restrict__ w,  // [9][8][8][G]
                                                        const float* __restrict__ bias,
@@ -218,73 +218,76 @@ __global__ void __launch_bounds__(256) gconv3x3_kernel(const float* __restrict__
     for (int i = threadIdx.x; i < 9 * 64 * G; i += blockDim.x) ws[i] = w[i];
     __syncthreads();
     const int g = threadIdx.x % G;
-    const int slot = threadIdx.x / G;            // which pixel-quad inside the block
+    const int slot = threadIdx.x / G;            // which pixel group inside the block
     const int quads_per_block = blockDim.x / G;  // 8 for G=32
     const int wq = cdiv(W, GC_PX);
-    long long quad = (long long)blockIdx.x * quads_per_block + slot;
-    long long total = (long long)B * H * wq;
-    if (quad >= total) return;
-    const int b = (int)(quad / ((long long)H * wq));
-    const int rem = (int)(quad - (long long)b * H * wq);
-    const int y = rem / wq, x0 = (rem - y * wq) * GC_PX;
-    float acc[GC_PX][8];
+    const long long total = (long long)B * H * wq;
+    // persistent: the 72 KB weight tile is loaded once per CTA, then the CTA strides over pixel groups
+    for (long long quad = (long long)blockIdx.x * quads_per_block + slot; quad < total;
+         quad += (long long)gridDim.x * quads_per_block) {
+        const int b = (int)(quad / ((long long)H * wq));
+        const int rem = (int)(quad - (long long)b * H * wq);
+        const int y = rem / wq, x0 = (rem - y * wq) * GC_PX;
+        float acc[GC_PX][8];
 #pragma unroll
-    for (int p = 0; p < GC_PX; ++p)
+        for (int p = 0; p < GC_PX; ++p)
 #pragma unroll
-        for (int co = 0; co < 8; ++co) acc[p][co] = 0.f;
-    for (int r = 0; r < 3; ++r) {
-        const int iy = y + r - 1;
-        if (iy < 0 || iy >= H) continue;
-        float v[GC_PX + 2][8];
+            for (int co = 0; co < 8; ++co) acc[p][co] = 0.f;
+#pragma unroll 1
+        for (int r = 0; r < 3; ++r) {
+            const int iy = y + r - 1;
+            if (iy < 0 || iy >= H) continue;
+            float v[GC_PX + 2][8];
 #pragma unroll
-        for (int q = 0; q < GC_PX + 2; ++q) {
-            const int ix = x0 + q - 1;
-            if (ix >= 0 && ix < W) {
-                const float* ip = in + (((long long)b * H + iy) * W + ix) * C + g * 8;
-                float4 a = *reinterpret_cast<const float4*>(ip);
-                float4 c = *reinterpret_cast<const float4*>(ip + 4);
-                v[q][0] = a.x; v[q][1] = a.y; v[q][2] = a.z; v[q][3] = a.w;
-                v[q][4] = c.x; v[q][5] = c.y; v[q][6] = c.z; v[q][7] = c.w;
-            } else {
+            for (int q = 0; q < GC_PX + 2; ++q) {
+                const int ix = x0 + q - 1;
+                if (ix >= 0 && ix < W) {
+                    const float* ip = in + (((long long)b * H + iy) * W + ix) * C + g * 8;
+                    float4 a = *reinterpret_cast<const float4*>(ip);
+                    float4 c = *reinterpret_cast<const float4*>(ip + 4);
+                    v[q][0] = a.x; v[q][1] = a.y; v[q][2] = a.z; v[q][3] = a.w;
+                    v[q][4] = c.x; v[q][5] = c.y; v[q][6] = c.z; v[q][7] = c.w;
+                } else {
 #pragma unroll
-                for (int ci = 0; ci < 8; ++ci) v[q][ci] = 0.f;
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < 3; ++s)
-#pragma unroll
-            for (int ci = 0; ci < 8; ++ci)
-#pragma unroll
-                for (int co = 0; co < 8; ++co) {
-                    const float wv = ws[(((r * 3 + s) * 8 + ci) * 8 + co) * G + g];
-#pragma unroll
-                    for (int p = 0; p < GC_PX; ++p) acc[p][co] = fmaf(v[p + s][ci], wv, acc[p][co]);
+                    for (int ci = 0; ci < 8; ++ci) v[q][ci] = 0.f;
                 }
-    }
+            }
 #pragma unroll
-    for (int p = 0; p < GC_PX; ++p) {
-        const int x = x0 + p;
-        if (x >= W) break;
-        float o[8];
+            for (int s = 0; s < 3; ++s)
 #pragma unroll
-        for (int co = 0; co < 8; ++co) {
-            float t = acc[p][co] + (bias ? bias[g * 8 + co] : 0.f);
-            o[co] = relu ? fmaxf(t, 0.f) : t;
+                for (int ci = 0; ci < 8; ++ci)
+#pragma unroll
+                    for (int co = 0; co < 8; ++co) {
+                        const float wv = ws[(((r * 3 + s) * 8 + ci) * 8 + co) * G + g];
+#pragma unroll
+                        for (int p = 0; p < GC_PX; ++p) acc[p][co] = fmaf(v[p + s][ci], wv, acc[p][co]);
+                    }
         }
-        const long long off = (((long long)b * H + y) * W + x) * C + g * 8;
-        if (out) {
-            *reinterpret_cast<float4*>(out + off) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(out + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
-        }
-        if (out_hi) {
-            __nv_bfloat16 h[8], l[8];
+#pragma unroll
+        for (int p = 0; p < GC_PX; ++p) {
+            const int x = x0 + p;
+            if (x >= W) break;
+            float o[8];
 #pragma unroll
             for (int co = 0; co < 8; ++co) {
-                h[co] = __float2bfloat16_rn(o[co]);
-                l[co] = __float2bfloat16_rn(o[co] - __bfloat162float(h[co]));
+                float t = acc[p][co] + (bias ? bias[g * 8 + co] : 0.f);
+                o[co] = relu ? fmaxf(t, 0.f) : t;
             }
-            *reinterpret_cast<uint4*>(out_hi + off) = *reinterpret_cast<uint4*>(h);
-            if (out_lo) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<uint4*>(l);
+            const long long off = (((long long)b * H + y) * W + x) * C + g * 8;
+            if (out) {
+                *reinterpret_cast<float4*>(out + off) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(out + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
+            if (out_hi) {
+                __nv_bfloat16 h[8], l[8];
+#pragma unroll
+                for (int co = 0; co < 8; ++co) {
+                    h[co] = __float2bfloat16_rn(o[co]);
+                    l[co] = __float2bfloat16_rn(o[co] - __bfloat162float(h[co]));
+                }
+                *reinterpret_cast<uint4*>(out_hi + off) = *reinterpret_cast<uint4*>(h);
+                if (out_lo) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<uint4*>(l);
+            }
         }
     }
 }
@@ -317,7 +320,11 @@ static int gconv_launch(const float* in, const float* w, const float* bias, floa
     }
     long long quads = (long long)B * H * cdiv(W, GC_PX);
     int qpb = 256 / groups;
-    gconv3x3_kernel<<<cdiv(quads, qpb), 256, smem, stream>>>(in, w, bias, out, (__nv_bfloat16*)out_hi,
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const long long want = cdiv(quads, qpb);
+    const int grid = (int)(want < 2LL * sms ? want : 2LL * sms);
+    gconv3x3_kernel<<<grid, 256, smem, stream>>>(in, w, bias, out, (__nv_bfloat16*)out_hi,
                                                              (__nv_bfloat16*)out_lo, B, H, W, groups, relu);
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
@@ -651,7 +658,7 @@ __global__ void __launch_bounds__(128) conv1a_kernel(const float* __restrict__ i
     if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
     const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
-    if (x >= W) return;
+    // threads beyond the row end compute on zero-padded taps and store nothing (they must reach the barrier)
     float in[27];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
@@ -681,14 +688,17 @@ __global__ void __launch_bounds__(128) conv1a_kernel(const float* __restrict__ i
     }
 #pragma unroll
     for (int co = 0; co < 64; ++co) acc[co] = fmaxf(acc[co] + bs[co], 0.f);
-    if (out_f32) {
+    if (out_f32 && x < W) {
         float* op = out_f32 + (((long long)b * H + y) * W + x) * 64;
 #pragma unroll
         for (int co = 0; co < 64; co += 4) *reinterpret_cast<float4*>(op + co) = make_float4(acc[co], acc[co + 1], acc[co + 2], acc[co + 3]);
     }
     if (ps_hi) {
-        const int Hp = (H + 1) >> 1, Wp = (W + 1) >> 1;
-        const long long off = ((((long long)(b * 4 + (y & 1) * 2 + (x & 1))) * Hp + (y >> 1)) * Wp + (x >> 1)) * 64;
+        // stage the 128 pixels x 64 channels of this block in shared memory (XOR-swizzled 16-byte chunks) so
+        // that 8 lanes write one pixel's 128-byte line together instead of one thread writing it alone
+        __shared__ __align__(16) uint4 st_hi[128 * 8];
+        __shared__ __align__(16) uint4 st_lo[128 * 8];
+        const int pl = threadIdx.x;
 #pragma unroll
         for (int co = 0; co < 64; co += 8) {
             __nv_bfloat16 h[8], l[8];
@@ -697,8 +707,22 @@ __global__ void __launch_bounds__(128) conv1a_kernel(const float* __restrict__ i
                 h[j] = __float2bfloat16_rn(acc[co + j]);
                 l[j] = __float2bfloat16_rn(acc[co + j] - __bfloat162float(h[j]));
             }
-            *reinterpret_cast<uint4*>(ps_hi + off + co) = *reinterpret_cast<uint4*>(h);
-            if (ps_lo) *reinterpret_cast<uint4*>(ps_lo + off + co) = *reinterpret_cast<uint4*>(l);
+            const int ch = (co >> 3) ^ (pl & 7);
+            st_hi[pl * 8 + ch] = *reinterpret_cast<uint4*>(h);
+            st_lo[pl * 8 + ch] = *reinterpret_cast<uint4*>(l);
+        }
+        __syncthreads();
+        const int Hp = (H + 1) >> 1, Wp = (W + 1) >> 1;
+        const int x_base = blockIdx.x * 128;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int px = it * 16 + (threadIdx.x >> 3), ch = threadIdx.x & 7;
+            const int xx = x_base + px;
+            if (xx < W) {
+                const long long off = ((((long long)(b * 4 + (y & 1) * 2 + (xx & 1))) * Hp + (y >> 1)) * Wp + (xx >> 1)) * 64 + ch * 8;
+                *reinterpret_cast<uint4*>(ps_hi + off) = st_hi[px * 8 + (ch ^ (px & 7))];
+                if (ps_lo) *reinterpret_cast<uint4*>(ps_lo + off) = st_lo[px * 8 + (ch ^ (px & 7))];
+            }
         }
     }
 }

@@ -384,10 +384,12 @@ def attention_prep(qkv: Tensor, nparts: int, b: int, n: int, heads: int, cos: Op
 
 
 def attention_tc(q: Split, k: Split, vt: Split, b: int, heads: int, nq: int, nk: int, nk_pad: int, scale: float,
-                 out_f32: Optional[Tensor], out_bf: Optional[Split], out_ld: int, split: int):
+                 out_f32: Optional[Tensor], out_bf: Optional[Split], out_ld: int, split: int, v_mn: bool = False):
+    """``vt`` is V^T [b*heads, 64, nk_pad] (v_mn=False) or V itself [b*heads, nk, 64] (v_mn=True)."""
     call('pram_attention_tc', ptr(q.hi), ptr(q.lo), ptr(k.hi), ptr(k.lo), ptr(vt.hi), ptr(vt.lo), b, heads, nq, nk, nk_pad,
          float(scale), ptr(out_f32), ptr(out_bf.hi) if out_bf is not None else None,
-         ptr(out_bf.lo) if (out_bf is not None and out_bf.lo is not None) else None, out_ld, split, P_SWAP, stream_ptr())
+         ptr(out_bf.lo) if (out_bf is not None and out_bf.lo is not None) else None, out_ld, split, P_SWAP, int(v_mn),
+         stream_ptr())
 
 
 # ---- K19: batched PnP RANSAC -------------------------------------------------------------------------

@@ -135,6 +135,12 @@ def test_attention_tc(ops, dev, split, b, nq, nk):
     tol = 2e-4 if split == 3 else 2e-2
     assert errs[0] < tol, f'P packing order: errors by p_swap = {errs}'
     assert err_bf < (tol if split == 3 else 3e-2)
+    # V consumed directly as an MN-major operand (no transposition)
+    V = ops.split_bf16(v.reshape(b * h, nk, 64).to(dev), lo)
+    out = torch.zeros(b, nq, 256, device=dev)
+    ops.attention_tc(Q, K, V, b, h, nq, nk, nk, 0.125, out, None, 256, split, v_mn=True)
+    torch.cuda.synchronize()
+    assert _relerr(out.cpu(), ref) < tol, 'MN-major V operand'
 
 
 def test_attention_prep_matches_rotary_split(ops, dev):
