@@ -143,6 +143,12 @@ typedef struct pram_tc_args {
     int l2norm;
     int split; /* 1: bf16, 3: error-compensated bf16x3 */
     int bn;    /* N tile (64/128/256), 0 = auto */
+    /* fused attention-operand epilogue: qkv_mode 1 = output columns (q|k|v), rotary on q,k (nets/segnetvit.py:98-103);
+     * 2 = (qk|v) of the cross block (nets/gml.py:165-174).  Results go to split-bf16 tensors [B][heads][n][64]
+     * (tokens < seg_split form segment 0 with n = seg_n0 per batch element, the rest segment 1 with seg_n1). */
+    int qkv_mode; const float* cosb; const float* sinb; float qk_scale;
+    void* q_hi; void* q_lo; void* k_hi; void* k_lo; void* v_hi; void* v_lo;
+    int seg_split, seg_n0, seg_n1, heads;
 } pram_tc_args;
 int pram_gemm_tc(const pram_tc_args* args, pram_stream_t stream);
 

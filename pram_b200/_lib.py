@@ -61,6 +61,9 @@ class TcArgs(C.Structure):
         ('out_hi', _P), ('out_lo', _P), ('ld_bf', _L),
         ('ps_hi', _P), ('ps_lo', _P), ('ld_ps', _L),
         ('l2norm', _I), ('split', _I), ('bn', _I),
+        ('qkv_mode', _I), ('cosb', _P), ('sinb', _P), ('qk_scale', _F),
+        ('q_hi', _P), ('q_lo', _P), ('k_hi', _P), ('k_lo', _P), ('v_hi', _P), ('v_lo', _P),
+        ('seg_split', _I), ('seg_n0', _I), ('seg_n1', _I), ('heads', _I),
     ]
 
 

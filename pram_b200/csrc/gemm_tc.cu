@@ -45,6 +45,12 @@ struct Args {
     __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; long long ld_bf;
     __nv_bfloat16* ps_hi; __nv_bfloat16* ps_lo; long long ld_ps;  // phase-split copy
     int l2norm;          // normalise each output row (requires N <= BN)
+    // fused attention-operand epilogue (qkv_mode 1: columns (q|k|v), rotary on q,k; 2: columns (qk|v)):
+    // output goes to split-bf16 tensors laid out [B][heads][n][64] per token segment instead of rows
+    int qkv_mode;
+    const float* cosb; const float* sinb; float qk_scale;
+    __nv_bfloat16* q_hi; __nv_bfloat16* q_lo; __nv_bfloat16* k_hi; __nv_bfloat16* k_lo; __nv_bfloat16* v_hi; __nv_bfloat16* v_lo;
+    int seg_split, seg_n0, seg_n1, heads;
 };
 
 // ---------------------------------------------------------------------------------------- PTX
@@ -141,6 +147,8 @@ struct EpiQuarter {
     int pix[32];
     int pix_ps[32];
     float inv[32];
+    int qbase[32];   // qkv_mode: element offset of (token, head 0, dim 0) in the [B][heads][n][64] tensors
+    int qhs[32];     // qkv_mode: element stride between heads for this token's segment (n * 64)
 };
 constexpr int EPI_BYTES = 8 * 4096 + 4 * (int)sizeof(EpiQuarter);  // 8 swizzled 32x32 fp32 tiles + tables
 
@@ -278,6 +286,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                 const int Hp = (p.Ho + 1) >> 1, Wp = (p.Wo + 1) >> 1;
                 eq.pix[lane] = valid ? (int)(((long long)b * p.Ho + y) * p.Wo + x) : -1;
                 eq.pix_ps[lane] = (int)((((long long)(b * 4 + (y & 1) * 2 + (x & 1))) * Hp + (y >> 1)) * Wp + (x >> 1));
+                if (p.qkv_mode) {  // rows are tokens (Linear): token -> (segment, batch element, position)
+                    const int t = x;
+                    const bool s1 = t >= p.seg_split;
+                    const int ns = s1 ? p.seg_n1 : p.seg_n0, tt = s1 ? t - p.seg_split : t;
+                    const int bb = tt / ns, nn = tt - bb * ns;
+                    eq.qbase[lane] = (s1 ? p.seg_split * p.heads * 64 : 0) + (bb * p.heads * ns + nn) * 64;
+                    eq.qhs[lane] = ns * 64;
+                }
             }
             // the two warps of a quarter exchange the row table through a named barrier (id 1 + q, 64 threads)
             asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
@@ -350,6 +366,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
 #pragma unroll
                         for (int k = 0; k < 4; ++k) f[k] = tile_s[row * 32 + ((col1 + k) ^ row)] + bz[k];
                         f[0] += rcur[i].x; f[1] += rcur[i].y; f[2] += rcur[i].z; f[3] += rcur[i].w;
+                        if (p.qkv_mode && pixr >= 0) {
+                            const bool is_v = (p.qkv_mode == 1) ? (nt == 2) : (nt == 1);
+                            if (!is_v) {
+                                if (p.qkv_mode == 1) {  // rotary on adjacent pairs (2i, 2i+1)
+                                    const int pr0 = ((c + col1) & 63) >> 1;
+                                    const float2 cs = __ldg(reinterpret_cast<const float2*>(p.cosb + (long long)pixr * 32 + pr0));
+                                    const float2 sn = __ldg(reinterpret_cast<const float2*>(p.sinb + (long long)pixr * 32 + pr0));
+                                    const float a0 = f[0] * cs.x + (-f[1]) * sn.x, a1 = f[1] * cs.x + f[0] * sn.x;
+                                    const float a2 = f[2] * cs.y + (-f[3]) * sn.y, a3 = f[3] * cs.y + f[2] * sn.y;
+                                    f[0] = a0; f[1] = a1; f[2] = a2; f[3] = a3;
+                                }
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) f[k] *= p.qk_scale;
+                            }
+                        }
                         if (p.relu) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) f[k] = fmaxf(f[k], 0.f);
@@ -368,15 +399,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                                 for (int k = 0; k < 4; ++k) if (nb + col1 + k < p.N) op[k] = f[k];
                             }
                         }
-                        if (p.out_hi || p.ps_hi) {
+                        if (p.out_hi || p.ps_hi || p.qkv_mode) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) tile_s[row * 32 + ((col1 + k) ^ row)] = f[k];
                         }
                     }
                 }
                 // ---- pass 2 (bf16 mapping: 4 lanes per row): split into hi / lo planes, 16-byte stores ----
-                if (p.out_hi || p.ps_hi) {  // requires N % 32 == 0 (checked on the host)
+                if (p.out_hi || p.ps_hi || p.qkv_mode) {  // requires N % 32 == 0 (checked on the host)
                     __syncwarp();
+                    __nv_bfloat16* qh = nullptr; __nv_bfloat16* ql = nullptr;
+                    if (p.qkv_mode) {  // BN == 256: the N tile index is the part (q | k | v) or (qk | v)
+                        const bool is_v = (p.qkv_mode == 1) ? (nt == 2) : (nt == 1);
+                        qh = is_v ? p.v_hi : (nt == 0 ? p.q_hi : p.k_hi);
+                        ql = is_v ? p.v_lo : (nt == 0 ? p.q_lo : p.k_lo);
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int row = i * 8 + g2;
@@ -389,6 +426,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                             split_bf16(tile_s[row * 32 + ((col2 + k + 1) ^ row)], h1, l1);
                             hi[k >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
                             lo[k >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        if (pixr >= 0 && qh) {
+                            const long long qo = (long long)eq.qbase[row] + (long long)(c >> 6) * eq.qhs[row] + (c & 63) + col2;
+                            *reinterpret_cast<uint4*>(qh + qo) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            if (ql) *reinterpret_cast<uint4*>(ql + qo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
                         if (pixr >= 0) {
                             if (p.out_hi) {
@@ -491,6 +533,10 @@ struct pram_tc_args {
     int l2norm;
     int split;                            // 1: bf16, 3: error-compensated bf16x3
     int bn;                               // 0 = auto
+    // fused attention-operand epilogue (see tc::Args)
+    int qkv_mode; const float* cosb; const float* sinb; float qk_scale;
+    void* q_hi; void* q_lo; void* k_hi; void* k_lo; void* v_hi; void* v_lo;
+    int seg_split, seg_n0, seg_n1, heads;
 };
 
 PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
@@ -542,6 +588,15 @@ PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
     k.out_hi = (__nv_bfloat16*)a->out_hi; k.out_lo = (__nv_bfloat16*)a->out_lo; k.ld_bf = a->ld_bf;
     k.ps_hi = (__nv_bfloat16*)a->ps_hi; k.ps_lo = (__nv_bfloat16*)a->ps_lo; k.ld_ps = a->ld_ps;
     k.l2norm = a->l2norm;
+    k.qkv_mode = a->qkv_mode; k.cosb = a->cosb; k.sinb = a->sinb; k.qk_scale = a->qk_scale;
+    k.q_hi = (__nv_bfloat16*)a->q_hi; k.q_lo = (__nv_bfloat16*)a->q_lo; k.k_hi = (__nv_bfloat16*)a->k_hi;
+    k.k_lo = (__nv_bfloat16*)a->k_lo; k.v_hi = (__nv_bfloat16*)a->v_hi; k.v_lo = (__nv_bfloat16*)a->v_lo;
+    k.seg_split = a->seg_split; k.seg_n0 = a->seg_n0; k.seg_n1 = a->seg_n1; k.heads = a->heads;
+    if (a->qkv_mode) {
+        if (bn != 256 || a->heads * 64 != 256 || !a->q_hi || !a->v_hi) return PRAM_ERR_UNSUPPORTED;
+        if ((a->qkv_mode == 1 && (a->N != 768 || !a->k_hi || !a->cosb || !a->sinb)) || (a->qkv_mode == 2 && a->N != 512)) return PRAM_ERR_ARG;
+        if (a->seg_n0 <= 0 || a->seg_n1 <= 0) return PRAM_ERR_ARG;
+    }
     const int tiles_x = (a->Wo + TW - 1) / TW, tiles_y = (a->Ho + TH - 1) / TH;
     const int total = a->B * tiles_x * tiles_y * ((a->N + bn - 1) / bn);
     if (a->split == 3) {

@@ -103,6 +103,10 @@ class Workspace:
             lo = split == 3
             self.cat_bf = [ops.empty_split((tokens, 2 * D), device, lo), ops.empty_split((tokens, 2 * D), device, lo)]
             self.ctx_bf = ops.empty_split((tokens, D), device, lo)
+            # attention operands written directly by the qkv GEMM epilogue, [B, heads, n, 64] per segment
+            self.q_bf = ops.empty_split((tokens, D), device, lo)
+            self.k_bf = ops.empty_split((tokens, D), device, lo)
+            self.v_bf = ops.empty_split((tokens, D), device, lo)
             self.hid_bf = ops.empty_split((tokens, 2 * D), device, lo)
         self.cat = [e(tokens, 2 * D), e(tokens, 2 * D)]
         self.cur = 0
@@ -165,15 +169,22 @@ def self_block(ws: Workspace, pk: Dict[str, torch.Tensor], segments: Sequence[Tu
     attention is computed independently inside each (segment, batch element).
     Reference nets/segnetvit.py:97-106 == nets/gml.py:128-137."""
     T = ws.T
-    linear(ws, ws.x, ws.x_bf if ws.split else None, 2 * D, T, D, 3 * D, pk, 'qkv', out_f32=ws.qkv, ld_f32=3 * D)
     use_tc = bool(ws.split) and colmeans is None
     ws.ctx_in_bf = use_tc
+    if use_tc:
+        # qkv GEMM with the fused epilogue: bias, rotary on q/k, split-bf16 Q/K/V in [B, heads, n, 64]
+        seg_split = segments[1][0] if len(segments) > 1 else T
+        qkv = {'mode': 1, 'scale': 1.0, 'cos': cos, 'sin': sin, 'q': ws.q_bf, 'k': ws.k_bf, 'v': ws.v_bf,
+               'seg_split': seg_split, 'seg_n0': segments[0][2], 'seg_n1': segments[-1][2]}
+        ops.linear_tc(ws.x_bf, 2 * D, T, D, pk['qkv.tc'], 3 * D, pk['qkv.b'], split=ws.split, bn=256, qkv=qkv)
+        for off, b, n in segments:
+            ops.attention_tc(ops.split_rows(ws.q_bf, off), ops.split_rows(ws.k_bf, off), ops.split_rows(ws.v_bf, off), b, HEADS,
+                             n, n, n, HDIM ** -0.5, None, ops.split_rows(ws.ctx_bf, off), D, ws.split, v_mn=True)
+        _finish_block(ws, pk)
+        return
+    linear(ws, ws.x, ws.x_bf if ws.split else None, 2 * D, T, D, 3 * D, pk, 'qkv', out_f32=ws.qkv, ld_f32=3 * D)
     for si, (off, b, n) in enumerate(segments):
         sl = slice(off, off + b * n)
-        if use_tc:
-            q, k, vt, n_pad = ops.attention_prep(ws.qkv[sl], 3, b, n, HEADS, cos[sl], sin[sl], 1.0, ws.split)
-            ops.attention_tc(q, k, vt, b, HEADS, n, n, n_pad, HDIM ** -0.5, None, ops.split_rows(ws.ctx_bf, off), D, ws.split)
-            continue
         ops.rotary_split(ws.qkv[sl], 3, b, n, HEADS, cos[sl], sin[sl], 1.0, ws.q[sl], ws.k[sl], ws.v[sl])
         ops.attention_f32(ws.q[sl], ws.k[sl], ws.v[sl], b, HEADS, n, n, HDIM ** -0.5, ws.ctx[sl], D,
                           None if colmeans is None else colmeans[si])
@@ -187,20 +198,22 @@ def cross_block(ws: Workspace, pk: Dict[str, torch.Tensor], seg0: Tuple[int, int
     sim^T).  Reference nets/gml.py:164-186.  ``colmeans`` = [mean attn10 over queries -> per token of
     set 0, mean attn01 -> per token of set 1] (reference nets/adagml.py:229)."""
     T = ws.T
-    qkv = ws.qkv.view(-1)[:T * 2 * D].view(T, 2 * D)  # (qk | v) rows, 512 wide
-    linear(ws, ws.x, ws.x_bf if ws.split else None, 2 * D, T, D, 2 * D, pk, 'qkv', out_f32=qkv, ld_f32=2 * D)
     (o0, b, m), (o1, _, n) = seg0, seg1
     s0, s1 = slice(o0, o0 + b * m), slice(o1, o1 + b * n)
     sc = (HDIM ** -0.5) ** 0.5  # applied to both qk0 and qk1 (nets/gml.py:174)
     use_tc = bool(ws.split) and colmeans is None
     ws.ctx_in_bf = use_tc
     if use_tc:
-        q0, _, vt0, mp = ops.attention_prep(qkv[s0], 2, b, m, HEADS, None, None, sc, ws.split)
-        q1, _, vt1, np_ = ops.attention_prep(qkv[s1], 2, b, n, HEADS, None, None, sc, ws.split)
-        ops.attention_tc(q0, q1, vt1, b, HEADS, m, n, np_, 1.0, None, ops.split_rows(ws.ctx_bf, o0), D, ws.split)
-        ops.attention_tc(q1, q0, vt0, b, HEADS, n, m, mp, 1.0, None, ops.split_rows(ws.ctx_bf, o1), D, ws.split)
+        fused = {'mode': 2, 'scale': sc, 'q': ws.q_bf, 'v': ws.v_bf, 'seg_split': o1, 'seg_n0': m, 'seg_n1': n}
+        ops.linear_tc(ws.x_bf, 2 * D, T, D, pk['qkv.tc'], 2 * D, pk['qkv.b'], split=ws.split, bn=256, qkv=fused)
+        q0, q1 = ops.split_rows(ws.q_bf, o0), ops.split_rows(ws.q_bf, o1)
+        v0, v1 = ops.split_rows(ws.v_bf, o0), ops.split_rows(ws.v_bf, o1)
+        ops.attention_tc(q0, q1, v1, b, HEADS, m, n, n, 1.0, None, ops.split_rows(ws.ctx_bf, o0), D, ws.split, v_mn=True)
+        ops.attention_tc(q1, q0, v0, b, HEADS, n, m, m, 1.0, None, ops.split_rows(ws.ctx_bf, o1), D, ws.split, v_mn=True)
         _finish_block(ws, pk)
         return
+    qkv = ws.qkv.view(-1)[:T * 2 * D].view(T, 2 * D)  # (qk | v) rows, 512 wide
+    linear(ws, ws.x, ws.x_bf if ws.split else None, 2 * D, T, D, 2 * D, pk, 'qkv', out_f32=qkv, ld_f32=2 * D)
     ops.rotary_split(qkv[s0], 2, b, m, HEADS, None, None, sc, ws.q[s0], None, ws.v[s0])
     ops.rotary_split(qkv[s1], 2, b, n, HEADS, None, None, sc, ws.q[s1], None, ws.v[s1])
     # m0 = softmax_rows(sim) v1 ; the column mean of attn01 indexes tokens of set 1

@@ -263,7 +263,7 @@ def gemm_tc(a: Split, a_ld: int, in_w: int, in_h: int, in_planes: int, cin: int,
             w_batch_mult: int = 0, bias: Optional[Tensor] = None, res: Optional[Tensor] = None, res_ld: int = 0,
             relu: bool = False, out_f32: Optional[Tensor] = None, ld_f32: int = 0, out_bf: Optional[Split] = None,
             ld_bf: int = 0, out_ps: Optional[Split] = None, ld_ps: int = 0, l2norm: bool = False, split: int = 3,
-            bn: int = 0):
+            bn: int = 0, qkv: Optional[dict] = None):
     """Raw launch of the tcgen05 implicit-GEMM kernel (see include/pram_b200.h: pram_gemm_tc)."""
     A = _lib.TcArgs()
     A.a_hi, A.a_lo, A.a_ld = a.hi.data_ptr(), (a.lo.data_ptr() if a.lo is not None else None), a_ld
@@ -283,6 +283,16 @@ def gemm_tc(a: Split, a_ld: int, in_w: int, in_h: int, in_planes: int, cin: int,
     if out_ps is not None:
         A.ps_hi, A.ps_lo, A.ld_ps = out_ps.hi.data_ptr(), (out_ps.lo.data_ptr() if out_ps.lo is not None else None), ld_ps
     A.l2norm, A.split, A.bn = int(l2norm), split, bn
+    if qkv is not None:
+        A.qkv_mode, A.qk_scale, A.heads = qkv['mode'], float(qkv['scale']), qkv.get('heads', 4)
+        A.cosb = qkv['cos'].data_ptr() if qkv.get('cos') is not None else None
+        A.sinb = qkv['sin'].data_ptr() if qkv.get('sin') is not None else None
+        for name in ('q', 'k', 'v'):
+            sp = qkv.get(name)
+            if sp is not None:
+                setattr(A, name + '_hi', sp.hi.data_ptr())
+                setattr(A, name + '_lo', sp.lo.data_ptr() if sp.lo is not None else None)
+        A.seg_split, A.seg_n0, A.seg_n1 = qkv['seg_split'], qkv['seg_n0'], qkv['seg_n1']
     import ctypes
     call('pram_gemm_tc', ctypes.byref(A), stream_ptr())
 
@@ -328,11 +338,11 @@ def conv_tc(x: Split, w: Split, bias: Optional[Tensor], ksize: int, stride: int,
 def linear_tc(a: Split, lda: int, rows: int, k: int, w: Split, n: int, bias: Optional[Tensor] = None,
               res: Optional[Tensor] = None, ldres: int = 0, relu: bool = False, out_f32: Optional[Tensor] = None,
               ld_f32: int = 0, out_bf: Optional[Split] = None, ld_bf: int = 0, split: int = 3, batch: int = 1,
-              w_batched: bool = False, bn: int = 0):
+              w_batched: bool = False, bn: int = 0, qkv: Optional[dict] = None):
     """out[rows, n] = a[rows, k] @ w[n, k]^T on tensor cores (row strides allow column slices of wider
     buffers).  batch > 1: a is [batch, rows, lda], w is [batch, n, k] when ``w_batched``."""
     gemm_tc(a, lda, rows, 1, batch, k, w, (batch if w_batched else 1), batch, 1, rows, n, [(0, 0, 0)], 1, 7,
-            1 if w_batched else 0, bias, res, ldres, relu, out_f32, ld_f32, out_bf, ld_bf, None, 0, False, split, bn)
+            1 if w_batched else 0, bias, res, ldres, relu, out_f32, ld_f32, out_bf, ld_bf, None, 0, False, split, bn, qkv)
 
 
 def conv1a(image_nchw: Tensor, w: Tensor, bias: Tensor, split: int, want_f32: bool = False):
