@@ -147,8 +147,9 @@ struct EpiQuarter {
     int pix[32];
     int pix_ps[32];
     float inv[32];
-    int qbase[32];   // qkv_mode: element offset of (token, head 0, dim 0) in the [B][heads][n][64] tensors
-    int qhs[32];     // qkv_mode: element stride between heads for this token's segment (n * 64)
+    // qkv_mode (never combined with the phase-split copy or the L2 norm) reuses two of the tables:
+    //   pix_ps -> element offset of (token, head 0, dim 0) in the [B][heads][n][64] tensors
+    //   inv    -> (as int) element stride between heads for this token's segment (n * 64)
 };
 constexpr int EPI_BYTES = 8 * 4096 + 4 * (int)sizeof(EpiQuarter);  // 8 swizzled 32x32 fp32 tiles + tables
 
@@ -160,10 +161,12 @@ struct Cfg {
     static constexpr int STAGE_BYTES = NPLANES * (A_BYTES + B_BYTES);
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 6 ? 6 : (200 * 1024) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
+    static_assert(SMEM_BYTES <= 227 * 1024, "dynamic shared memory budget of sm_100a exceeded");
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
-template <int BN, int SPLIT>
+// MODE (epilogue specialisation, keeps registers down): 0 plain, 1 residual add, 2 fused attention operands
+template <int BN, int SPLIT, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
     const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const Args p) {
@@ -286,18 +289,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                 const int Hp = (p.Ho + 1) >> 1, Wp = (p.Wo + 1) >> 1;
                 eq.pix[lane] = valid ? (int)(((long long)b * p.Ho + y) * p.Wo + x) : -1;
                 eq.pix_ps[lane] = (int)((((long long)(b * 4 + (y & 1) * 2 + (x & 1))) * Hp + (y >> 1)) * Wp + (x >> 1));
-                if (p.qkv_mode) {  // rows are tokens (Linear): token -> (segment, batch element, position)
+                if (MODE == 2) {  // rows are tokens (Linear): token -> (segment, batch element, position)
                     const int t = x;
                     const bool s1 = t >= p.seg_split;
                     const int ns = s1 ? p.seg_n1 : p.seg_n0, tt = s1 ? t - p.seg_split : t;
                     const int bb = tt / ns, nn = tt - bb * ns;
-                    eq.qbase[lane] = (s1 ? p.seg_split * p.heads * 64 : 0) + (bb * p.heads * ns + nn) * 64;
-                    eq.qhs[lane] = ns * 64;
+                    eq.pix_ps[lane] = (s1 ? p.seg_split * p.heads * 64 : 0) + (bb * p.heads * ns + nn) * 64;
+                    eq.inv[lane] = __int_as_float(ns * 64);
                 }
             }
             // the two warps of a quarter exchange the row table through a named barrier (id 1 + q, 64 threads)
             asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-            auto load_res = [&](int nb, float4 (&rv)[8]) {
+            auto load_res = [&](int nb, float4 (&rv)[MODE == 1 ? 8 : 1]) {
+                if constexpr (MODE != 1) return;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int pixr = eq.pix[i * 4 + g1];
@@ -315,8 +319,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                     rv[i] = t;
                 }
             };
-            float4 rv[8];
-            load_res(n0 + half * 32, rv);  // independent of the accumulator: overlaps the MMA tail
+            float4 rv[MODE == 1 ? 8 : 1];
+            if constexpr (MODE == 1) load_res(n0 + half * 32, rv);  // independent of the accumulator: overlaps the MMA tail
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
@@ -348,10 +352,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
 #pragma unroll
                     for (int j = 0; j < 32; ++j) tile_s[lane * 32 + (j ^ lane)] = __uint_as_float(v[j]);
                 }
-                float4 rcur[8];
+                float4 rcur[MODE == 1 ? 8 : 1];
+                if constexpr (MODE == 1) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) rcur[i] = rv[i];
-                if (c + 64 < BN) load_res(nb + 64, rv);  // prefetch the next chunk's residual
+                    for (int i = 0; i < 8; ++i) rcur[i] = rv[i];
+                    if (c + 64 < BN) load_res(nb + 64, rv);  // prefetch the next chunk's residual
+                }
                 __syncwarp();
                 // ---- pass 1 (fp32 mapping: 8 lanes per row): bias, residual, ReLU, L2 norm, fp32 store ----
                 {
@@ -365,8 +371,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                         float f[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) f[k] = tile_s[row * 32 + ((col1 + k) ^ row)] + bz[k];
-                        f[0] += rcur[i].x; f[1] += rcur[i].y; f[2] += rcur[i].z; f[3] += rcur[i].w;
-                        if (p.qkv_mode && pixr >= 0) {
+                        if constexpr (MODE == 1) { f[0] += rcur[i].x; f[1] += rcur[i].y; f[2] += rcur[i].z; f[3] += rcur[i].w; }
+                        if (MODE == 2 && pixr >= 0) {
                             const bool is_v = (p.qkv_mode == 1) ? (nt == 2) : (nt == 1);
                             if (!is_v) {
                                 if (p.qkv_mode == 1) {  // rotary on adjacent pairs (2i, 2i+1)
@@ -399,17 +405,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                                 for (int k = 0; k < 4; ++k) if (nb + col1 + k < p.N) op[k] = f[k];
                             }
                         }
-                        if (p.out_hi || p.ps_hi || p.qkv_mode) {
+                        if (MODE == 2 || p.out_hi || p.ps_hi) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) tile_s[row * 32 + ((col1 + k) ^ row)] = f[k];
                         }
                     }
                 }
                 // ---- pass 2 (bf16 mapping: 4 lanes per row): split into hi / lo planes, 16-byte stores ----
-                if (p.out_hi || p.ps_hi || p.qkv_mode) {  // requires N % 32 == 0 (checked on the host)
+                if (MODE == 2 || p.out_hi || p.ps_hi) {  // requires N % 32 == 0 (checked on the host)
                     __syncwarp();
                     __nv_bfloat16* qh = nullptr; __nv_bfloat16* ql = nullptr;
-                    if (p.qkv_mode) {  // BN == 256: the N tile index is the part (q | k | v) or (qk | v)
+                    if (MODE == 2) {  // BN == 256: the N tile index is the part (q | k | v) or (qk | v)
                         const bool is_v = (p.qkv_mode == 1) ? (nt == 2) : (nt == 1);
                         qh = is_v ? p.v_hi : (nt == 0 ? p.q_hi : p.k_hi);
                         ql = is_v ? p.v_lo : (nt == 0 ? p.q_lo : p.k_lo);
@@ -427,8 +433,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                             hi[k >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
                             lo[k >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                         }
-                        if (pixr >= 0 && qh) {
-                            const long long qo = (long long)eq.qbase[row] + (long long)(c >> 6) * eq.qhs[row] + (c & 63) + col2;
+                        if (MODE == 2 && pixr >= 0 && qh) {
+                            const long long qo = (long long)eq.pix_ps[row] + (long long)(c >> 6) * __float_as_int(eq.inv[row]) + (c & 63) + col2;
                             *reinterpret_cast<uint4*>(qh + qo) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                             if (ql) *reinterpret_cast<uint4*>(ql + qo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
@@ -495,11 +501,11 @@ static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
 
 static int g_num_sms = 0;
 
-template <int BN, int SPLIT>
-static int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
-                  const Args& a, int total_tiles, cudaStream_t stream) {
+template <int BN, int SPLIT, int MODE>
+static int launch_mode(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
+                       const Args& a, int total_tiles, cudaStream_t stream) {
     using C = Cfg<BN, SPLIT>;
-    auto kern = gemm_tc_kernel<BN, SPLIT>;
+    auto kern = gemm_tc_kernel<BN, SPLIT, MODE>;
     static bool attr = false;
     if (!attr) {
         PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -509,6 +515,17 @@ static int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMa
     kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ah, al, wh, wl, a);
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
+}
+
+template <int BN, int SPLIT>
+static int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
+                  const Args& a, int total_tiles, cudaStream_t stream) {
+    if (a.qkv_mode) {
+        if constexpr (BN == 256) return launch_mode<BN, SPLIT, 2>(ah, al, wh, wl, a, total_tiles, stream);
+        else return PRAM_ERR_UNSUPPORTED;
+    }
+    if (a.res) return launch_mode<BN, SPLIT, 1>(ah, al, wh, wl, a, total_tiles, stream);
+    return launch_mode<BN, SPLIT, 0>(ah, al, wh, wl, a, total_tiles, stream);
 }
 
 }  // namespace tc
@@ -593,7 +610,7 @@ PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
     k.k_lo = (__nv_bfloat16*)a->k_lo; k.v_hi = (__nv_bfloat16*)a->v_hi; k.v_lo = (__nv_bfloat16*)a->v_lo;
     k.seg_split = a->seg_split; k.seg_n0 = a->seg_n0; k.seg_n1 = a->seg_n1; k.heads = a->heads;
     if (a->qkv_mode) {
-        if (bn != 256 || a->heads * 64 != 256 || !a->q_hi || !a->v_hi) return PRAM_ERR_UNSUPPORTED;
+        if (bn != 256 || a->heads * 64 != 256 || !a->q_hi || !a->v_hi || a->ps_hi || a->l2norm) return PRAM_ERR_UNSUPPORTED;
         if ((a->qkv_mode == 1 && (a->N != 768 || !a->k_hi || !a->cosb || !a->sinb)) || (a->qkv_mode == 2 && a->N != 512)) return PRAM_ERR_ARG;
         if (a->seg_n0 <= 0 || a->seg_n1 <= 0) return PRAM_ERR_ARG;
     }
