@@ -349,8 +349,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                 {
                     uint32_t v[32];
                     tmem_ld32(taddr + c, v);
+                    float4* trow = reinterpret_cast<float4*>(tile_s + lane * 32);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) tile_s[lane * 32 + (j ^ lane)] = __uint_as_float(v[j]);
+                    for (int j4 = 0; j4 < 8; ++j4)  // 16-byte chunk j4 of row `lane` lives at chunk position j4 ^ (lane & 7)
+                        trow[j4 ^ (lane & 7)] = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
+                                                            __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
                 }
                 float4 rcur[MODE == 1 ? 8 : 1];
                 if constexpr (MODE == 1) {
@@ -368,9 +371,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                     for (int i = 0; i < 8; ++i) {
                         const int row = i * 4 + g1;
                         const int pixr = eq.pix[row];
-                        float f[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) f[k] = tile_s[row * 32 + ((col1 + k) ^ row)] + bz[k];
+                        float4* tp = reinterpret_cast<float4*>(tile_s + row * 32) + ((col1 >> 2) ^ (row & 7));
+                        const float4 tv = *tp;
+                        float f[4] = {tv.x + bz[0], tv.y + bz[1], tv.z + bz[2], tv.w + bz[3]};
                         if constexpr (MODE == 1) { f[0] += rcur[i].x; f[1] += rcur[i].y; f[2] += rcur[i].z; f[3] += rcur[i].w; }
                         if (MODE == 2 && pixr >= 0) {
                             const bool is_v = (p.qkv_mode == 1) ? (nt == 2) : (nt == 1);
@@ -405,10 +408,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                                 for (int k = 0; k < 4; ++k) if (nb + col1 + k < p.N) op[k] = f[k];
                             }
                         }
-                        if (MODE == 2 || p.out_hi || p.ps_hi) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) tile_s[row * 32 + ((col1 + k) ^ row)] = f[k];
-                        }
+                        if (MODE == 2 || p.out_hi || p.ps_hi) *tp = make_float4(f[0], f[1], f[2], f[3]);
                     }
                 }
                 // ---- pass 2 (bf16 mapping: 4 lanes per row): split into hi / lo planes, 16-byte stores ----
@@ -425,13 +425,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                         const int row = i * 8 + g2;
                         const int pixr = eq.pix[row];
                         uint32_t hi[4], lo[4];
+                        {
+                            const float4* tr = reinterpret_cast<const float4*>(tile_s + row * 32);
+                            const float4 a = tr[(col2 >> 2) ^ (row & 7)], bq = tr[((col2 >> 2) + 1) ^ (row & 7)];
+                            const float fv[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
-                        for (int k = 0; k < 8; k += 2) {
-                            __nv_bfloat16 h0, l0, h1, l1;
-                            split_bf16(tile_s[row * 32 + ((col2 + k) ^ row)], h0, l0);
-                            split_bf16(tile_s[row * 32 + ((col2 + k + 1) ^ row)], h1, l1);
-                            hi[k >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            lo[k >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                            for (int k = 0; k < 8; k += 2) {
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(fv[k], fv[k + 1]);
+                                const uint32_t u = *reinterpret_cast<uint32_t*>(&h2);
+                                __nv_bfloat162 l2 = __floats2bfloat162_rn(fv[k] - __uint_as_float(u << 16),
+                                                                          fv[k + 1] - __uint_as_float(u & 0xffff0000u));
+                                hi[k >> 1] = u;
+                                lo[k >> 1] = *reinterpret_cast<uint32_t*>(&l2);
+                            }
                         }
                         if (MODE == 2 && pixr >= 0 && qh) {
                             const long long qo = (long long)eq.pix_ps[row] + (long long)(c >> 6) * __float_as_int(eq.inv[row]) + (c & 63) + col2;
