@@ -178,6 +178,21 @@ int pram_ransac_pnp(const float* kpts, const long long* matches, const float* xy
                     int lo_iters, int final_iters, int min_inliers, unsigned int seed, void* workspace, double* qvec,
                     double* tvec, int* num_inliers, unsigned char* inliers, int* success, pram_stream_t stream);
 
+/* ---- "next" rows ---- */
+/* Frame.add_segmentations (localization/frame.py:96-121): softmax, background probability, argmax-1, pre-filter mask. */
+int pram_segmentation(const float* logits, int T, int C, float bg_threshold, float* probs, float* bg_prob, int* seg_id,
+                      unsigned char* non_bg, pram_stream_t stream);
+/* MultiMap3D.process_segmentations (localization/multimap3d.py:348-379): greedy landmark ranking, one CTA per frame. */
+int pram_rank_landmarks(const float* logits, const unsigned char* keep, int B, int N, int C, int topk, int max_ranks,
+                        int* entry_sid, int* entry_rank, int* entry_count, float* entry_score, int* n_entries,
+                        int* label_at_rank, pram_stream_t stream);
+/* K18, SingleMap3D.refine_pose_by_projection (localization/singlemap3d.py:405-440): projection + masked top-2. */
+int pram_project_points(const float* xyz, int n, const double* pose, double fx, double fy, double cx, double cy,
+                        double width, double height, float* uv, unsigned char* valid, pram_stream_t stream);
+int pram_projection_top2(const float* sim, int ld, int M, int N, const float* kpts, const float* uv,
+                         const unsigned char* valid, float window, float ratio, long long* match, float* d0, float* d1,
+                         pram_stream_t stream);
+
 /* fp32 -> split bf16 planes: hi = bf16(x), lo = bf16(x - hi) (lo may be NULL). */
 int pram_split_bf16(const float* in, void* hi, void* lo, long long n, pram_stream_t stream);
 

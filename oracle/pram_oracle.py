@@ -722,3 +722,62 @@ def frame_tensor(h: int = 480, w: int = 640, seed: int = 0) -> Tensor:
     mean = torch.tensor(RGB_MEAN).view(1, 3, 1, 1)
     std = torch.tensor(RGB_STD).view(1, 3, 1, 1)
     return ((img - mean) / std).contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# "next" rows: recognition -> matching glue and projection refinement
+# --------------------------------------------------------------------------------------------
+
+def add_segmentations(logits: Tensor, filtering_threshold: float):
+    """Reference localization/frame.py:96-121 for one frame ([N,C] logits): softmax, background pre-filter
+    (kept only when at least 40 % of the keypoints survive), seg ids = argmax - 1.
+    Returns (keep mask [N] over the ORIGINAL keypoints, seg_scores of the kept, seg_ids of the kept)."""
+    scores = torch.softmax(logits, dim=-1)
+    keep = torch.ones(logits.shape[0], dtype=torch.bool)
+    if filtering_threshold > 0:
+        non_bg = scores[:, 0] < filtering_threshold
+        if non_bg.sum() >= 0.4 * scores.shape[0]:
+            keep = non_bg
+    return keep, scores[keep], logits[keep].max(dim=-1)[1] - 1
+
+
+def process_segmentations(segs: Tensor, topk: int = 10):
+    """Reference localization/multimap3d.py:348-379: [(sid, keypoint ids, score), ...]."""
+    vals, ids = torch.topk(segs, k=segs.shape[-1], largest=True, dim=-1)
+    vals, ids = vals.numpy(), ids.numpy()
+    out, used = [], []
+    for k in range(segs.shape[-1]):
+        vk, ik = vals[:, k], ids[:, k]
+        cand = []
+        for sid in np.unique(ik):
+            if sid == 0 or sid in used:
+                continue
+            used.append(sid)
+            sel = np.where(ik == sid)[0]
+            cand.append((sel.shape[0], sid, sel, np.mean(vk[sel])))
+        for c in sorted(cand, key=lambda item: item[0], reverse=True):
+            out.append((c[1], c[2], c[3]))
+            if len(out) >= topk:
+                return out
+    return out
+
+
+def match_by_projection(q_kpts: np.ndarray, q_descs: np.ndarray, xyz: np.ndarray, descs: np.ndarray, R: np.ndarray,
+                        t: np.ndarray, K: np.ndarray, width: int, height: int, threshold: float):
+    """Reference localization/singlemap3d.py:405-440: project map points, mask by visibility, descriptor
+    distance sqrt(2-2qd+1e-6) (+100 outside a 2*threshold window), top-2, ratio 0.995.
+    Returns (matched keypoint ids, matched map-point indices into ``xyz``)."""
+    Xc = xyz @ R.T + t
+    proj = (K @ Xc.T)
+    u, v, z = proj[0] / proj[2], proj[1] / proj[2], proj[2]
+    mask = (z > 0) & (z < 100) & (u >= 0) & (u < width) & (v >= 0) & (v < height)
+    idx = np.nonzero(mask)[0]
+    uv = np.stack([u[mask], v[mask]], 0)
+    err = torch.sqrt(((torch.from_numpy(q_kpts)[..., None] - torch.from_numpy(uv)[None]) ** 2).sum(1))
+    oor = err >= 2 * threshold
+    dd = torch.sqrt(2 - 2 * torch.from_numpy(q_descs).float() @ torch.from_numpy(descs[mask]).float().t() + 1e-6)
+    dd[oor] = dd[oor] + 100
+    d, ids = torch.topk(dd, k=2, largest=False, dim=1)
+    ok = ((d[:, 0] / d[:, 1]) <= 0.995) & (d[:, 0] < 100)
+    ok = ok.numpy()
+    return np.where(ok)[0], idx[ids.numpy()[ok, 0]], d.numpy()

@@ -75,6 +75,10 @@ _D = C.c_double
 SIGNATURES['pram_ransac_workspace_bytes'] = (_L, [_I, _I, _I])
 SIGNATURES['pram_ransac_pnp'] = (_I, [_P, _P, _P, _I, _I, _I, _D, _D, _D, _D, _D, _D, _I, _I, _I, _I, C.c_uint, _P, _P, _P, _P,
                                       _P, _P, _P])
+SIGNATURES['pram_segmentation'] = (_I, [_P, _I, _I, _F, _P, _P, _P, _P, _P])
+SIGNATURES['pram_rank_landmarks'] = (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P])
+SIGNATURES['pram_project_points'] = (_I, [_P, _I, _P, _D, _D, _D, _D, _D, _D, _P, _P, _P])
+SIGNATURES['pram_projection_top2'] = (_I, [_P, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _P, _P])
 SIGNATURES['pram_gconv3x3_split'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P])
 SIGNATURES['pram_conv1a'] = (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P])
 SIGNATURES['pram_layernorm_gelu_split'] = (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _P])

@@ -1,0 +1,218 @@
+// "Next" rows of SURVEY.md section 8f: the device-side glue between recognition and matching, and the
+// projection-based pose refinement (K18).
+//   segmentation_kernel   : Frame.add_segmentations (reference localization/frame.py:96-121): softmax over the
+//                           landmark logits, background probability, arg-max label - 1, background pre-filter mask
+//   rank_landmarks_kernel : MultiMap3D.process_segmentations (reference localization/multimap3d.py:348-379):
+//                           greedy ranking of candidate landmarks by (rank of the label in each keypoint's
+//                           sorted logits, number of keypoints voting for it), mean logit as score
+//   project_points_kernel + proj_top2_kernel : SingleMap3D.refine_pose_by_projection (reference
+//                           localization/singlemap3d.py:405-440): project the covisible map points with the
+//                           current pose, descriptor distance sqrt(2 - 2 q.d + 1e-6) (+100 outside a 2*th
+//                           reprojection window), top-2 + ratio test.  The M x N similarity comes from the
+//                           tcgen05 GEMM; this kernel fuses mask + distance + top-2 + ratio (no M x N temporaries).
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// one warp per keypoint; logits [T][C]
+// ------------------------------------------------------------------------------------------
+__global__ void segmentation_kernel(const float* __restrict__ logits, int T, int C, float bg_th,
+                                    float* __restrict__ probs /*optional [T][C]*/, float* __restrict__ bg_prob,
+                                    int* __restrict__ seg_id, unsigned char* __restrict__ non_bg) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= T) return;
+    const float* p = logits + (long long)t * C;
+    float mx = -INFINITY;
+    int am = 0;
+    for (int c = lane; c < C; c += 32) {
+        const float v = p[c];
+        if (v > mx) { mx = v; am = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+        if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
+    }
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(p[c] - mx);
+    s = warp_sum(s);
+    if (probs)
+        for (int c = lane; c < C; c += 32) probs[(long long)t * C + c] = expf(p[c] - mx) / s;
+    if (lane == 0) {
+        const float b = expf(p[0] - mx) / s;
+        bg_prob[t] = b;
+        seg_id[t] = am - 1;  // labels start from 0, class 0 is background (frame.py:121)
+        non_bg[t] = b < bg_th;
+    }
+}
+
+PRAM_API int pram_segmentation(const float* logits, int T, int C, float bg_threshold, float* probs, float* bg_prob,
+                               int* seg_id, unsigned char* non_bg, cudaStream_t stream) {
+    if (!logits || !bg_prob || !seg_id || !non_bg || T <= 0 || C <= 0) return PRAM_ERR_ARG;
+    segmentation_kernel<<<cdiv((long long)T * 32, 256), 256, 0, stream>>>(logits, T, C, bg_threshold, probs, bg_prob, seg_id, non_bg);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// process_segmentations: one CTA per frame.  rank k = 0,1,...: every keypoint's k-th best class (value
+// descending, class index ascending among equal values); classes seen at this rank that are not background and
+// not yet used are appended in order of (vote count descending, class id ascending) until topk entries exist.
+// Outputs: entry_sid / entry_rank / entry_count / entry_score [topk], n_entries, and label_at_rank [max_ranks][N]
+// (so that the keypoint ids of entry e are { i : label_at_rank[entry_rank[e]][i] == entry_sid[e] }).
+// ------------------------------------------------------------------------------------------
+constexpr int RK_THREADS = 256;
+constexpr int RK_MAXC = 1024;
+
+__global__ void __launch_bounds__(RK_THREADS) rank_landmarks_kernel(
+    const float* __restrict__ logits, const unsigned char* __restrict__ keep /*optional [B][N]*/, int N, int C, int topk,
+    int max_ranks, int* __restrict__ entry_sid, int* __restrict__ entry_rank, int* __restrict__ entry_count,
+    float* __restrict__ entry_score, int* __restrict__ n_entries, int* __restrict__ label_at_rank) {
+    __shared__ int cnt[RK_MAXC];
+    __shared__ float sum[RK_MAXC];
+    __shared__ unsigned char used[RK_MAXC];
+    __shared__ int s_n, s_best, s_done;
+    const int b = blockIdx.x;
+    const float* L = logits + (long long)b * N * C;
+    for (int c = threadIdx.x; c < C; c += RK_THREADS) used[c] = 0;
+    if (threadIdx.x == 0) { s_n = 0; s_done = 0; }
+    __syncthreads();
+    // per-thread state for the keypoints it owns (strided): previous selection (value, class)
+    constexpr int MAXOWN = 32;  // N <= RK_THREADS * MAXOWN = 8192
+    float pv[MAXOWN];
+    int pc[MAXOWN];
+#pragma unroll
+    for (int i = 0; i < MAXOWN; ++i) { pv[i] = INFINITY; pc[i] = -1; }
+    for (int k = 0; k < max_ranks && k < C; ++k) {
+        for (int c = threadIdx.x; c < C; c += RK_THREADS) { cnt[c] = 0; sum[c] = 0.f; }
+        __syncthreads();
+        int own = 0;
+        for (int i = threadIdx.x; i < N && own < MAXOWN; i += RK_THREADS, ++own) {
+            const bool kept = !keep || keep[(long long)b * N + i];
+            // next class in (value desc, class asc) order after (pv, pc)
+            float bv = -INFINITY;
+            int bc = -1;
+            const float* p = L + (long long)i * C;
+            for (int c = 0; c < C; ++c) {
+                const float v = p[c];
+                const bool after = (v < pv[own]) || (v == pv[own] && c > pc[own]);
+                if (after && (v > bv || bc < 0)) { bv = v; bc = c; }
+            }
+            pv[own] = bv; pc[own] = bc;
+            label_at_rank[((long long)b * max_ranks + k) * N + i] = kept ? bc : -1;
+            if (kept && bc >= 0) { atomicAdd(&cnt[bc], 1); atomicAdd(&sum[bc], bv); }
+        }
+        __syncthreads();
+        // append unused, non-background classes of this rank by (count desc, class asc)
+        while (true) {
+            if (threadIdx.x == 0) {
+                int best = -1;
+                for (int c = 1; c < C; ++c)
+                    if (cnt[c] > 0 && !used[c] && (best < 0 || cnt[c] > cnt[best])) best = c;
+                s_best = best;
+                if (best >= 0) {
+                    const int e = s_n;
+                    entry_sid[(long long)b * topk + e] = best;
+                    entry_rank[(long long)b * topk + e] = k;
+                    entry_count[(long long)b * topk + e] = cnt[best];
+                    entry_score[(long long)b * topk + e] = sum[best] / (float)cnt[best];
+                    used[best] = 1;
+                    s_n = e + 1;
+                    if (s_n >= topk) s_done = 1;
+                }
+            }
+            __syncthreads();
+            if (s_best < 0 || s_done) break;
+        }
+        if (s_done) break;
+    }
+    if (threadIdx.x == 0) n_entries[b] = s_n;
+}
+
+PRAM_API int pram_rank_landmarks(const float* logits, const unsigned char* keep, int B, int N, int C, int topk,
+                                 int max_ranks, int* entry_sid, int* entry_rank, int* entry_count, float* entry_score,
+                                 int* n_entries, int* label_at_rank, cudaStream_t stream) {
+    if (!logits || !entry_sid || !entry_rank || !entry_count || !entry_score || !n_entries || !label_at_rank) return PRAM_ERR_ARG;
+    if (C > RK_MAXC || N > RK_THREADS * 32 || topk <= 0 || max_ranks <= 0) return PRAM_ERR_UNSUPPORTED;
+    rank_landmarks_kernel<<<B, RK_THREADS, 0, stream>>>(logits, keep, N, C, topk, max_ranks, entry_sid, entry_rank,
+                                                       entry_count, entry_score, n_entries, label_at_rank);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K18: projection of map points (float64, like the reference's numpy/cuda double path)
+//   uv = K (R X + t); valid = 0 < z < 100 and 0 <= u < width and 0 <= v < height
+// ------------------------------------------------------------------------------------------
+__global__ void project_points_kernel(const float* __restrict__ xyz, int n, const double* __restrict__ pose /*R[9],t[3]*/,
+                                      double fx, double fy, double cx, double cy, double width, double height,
+                                      float* __restrict__ uv, unsigned char* __restrict__ valid) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double X = xyz[3 * (long long)j], Y = xyz[3 * (long long)j + 1], Z = xyz[3 * (long long)j + 2];
+    const double xc = pose[0] * X + pose[1] * Y + pose[2] * Z + pose[9];
+    const double yc = pose[3] * X + pose[4] * Y + pose[5] * Z + pose[10];
+    const double zc = pose[6] * X + pose[7] * Y + pose[8] * Z + pose[11];
+    const double u = (fx * xc + cx * zc) / zc, v = (fy * yc + cy * zc) / zc;
+    const bool ok = (zc > 0) && (zc < 100) && (u >= 0) && (u < width) && (v >= 0) && (v < height);
+    uv[2 * (long long)j] = (float)u;
+    uv[2 * (long long)j + 1] = (float)v;
+    valid[j] = ok;
+}
+
+// one warp per query keypoint: top-2 of the masked descriptor distance over all valid map points
+__global__ void __launch_bounds__(256) proj_top2_kernel(const float* __restrict__ sim /*[M][ld]*/, int ld, int M, int N,
+                                                        const float* __restrict__ kpts, const float* __restrict__ uv,
+                                                        const unsigned char* __restrict__ valid, float window,
+                                                        float ratio, long long* __restrict__ match,
+                                                        float* __restrict__ d0_out, float* __restrict__ d1_out) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= M) return;
+    const float kx = kpts[2 * (long long)i], ky = kpts[2 * (long long)i + 1];
+    float b0 = INFINITY, b1 = INFINITY;
+    int j0 = -1;
+    const float* s = sim + (long long)i * ld;
+    for (int j = lane; j < N; j += 32) {
+        if (!valid[j]) continue;
+        const float dx = kx - uv[2 * (long long)j], dy = ky - uv[2 * (long long)j + 1];
+        const float err = sqrtf(dx * dx + dy * dy);
+        float d = sqrtf(2.f - 2.f * s[j] + 1e-6f);
+        if (err >= window) d += 100.f;
+        if (d < b0) { b1 = b0; b0 = d; j0 = j; }
+        else if (d < b1) b1 = d;
+    }
+    // merge the per-lane top-2 lists (ties: lower index first)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob0 = __shfl_xor_sync(0xffffffffu, b0, o), ob1 = __shfl_xor_sync(0xffffffffu, b1, o);
+        const int oj0 = __shfl_xor_sync(0xffffffffu, j0, o);
+        if (ob0 < b0 || (ob0 == b0 && oj0 >= 0 && (j0 < 0 || oj0 < j0))) {
+            b1 = fminf(b0, ob1); b0 = ob0; j0 = oj0;
+        } else {
+            b1 = fminf(b1, ob0);
+        }
+    }
+    if (lane == 0) {
+        const bool ok = (j0 >= 0) && (b0 / b1 <= ratio) && (b0 < 100.f);
+        match[i] = ok ? (long long)j0 : -1ll;
+        d0_out[i] = b0;
+        d1_out[i] = b1;
+    }
+}
+
+PRAM_API int pram_project_points(const float* xyz, int n, const double* pose, double fx, double fy, double cx, double cy,
+                                 double width, double height, float* uv, unsigned char* valid, cudaStream_t stream) {
+    if (!xyz || !pose || !uv || !valid || n <= 0) return PRAM_ERR_ARG;
+    project_points_kernel<<<cdiv(n, 256), 256, 0, stream>>>(xyz, n, pose, fx, fy, cx, cy, width, height, uv, valid);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+PRAM_API int pram_projection_top2(const float* sim, int ld, int M, int N, const float* kpts, const float* uv,
+                                  const unsigned char* valid, float window, float ratio, long long* match, float* d0,
+                                  float* d1, cudaStream_t stream) {
+    if (!sim || !kpts || !uv || !valid || !match || !d0 || !d1 || M <= 0 || N <= 0) return PRAM_ERR_ARG;
+    proj_top2_kernel<<<cdiv((long long)M * 32, 256), 256, 0, stream>>>(sim, ld, M, N, kpts, uv, valid, window, ratio, match, d0, d1);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}

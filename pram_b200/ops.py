@@ -426,3 +426,57 @@ def ransac_pnp(kpts: Tensor, matches: Tensor, xyz: Tensor, fx: float, fy: float,
          float(pixel_shift), float(max_error), int(num_hypotheses), int(lo_iters), int(final_iters), int(min_inliers),
          int(seed) & 0xffffffff, ptr(ws), ptr(q), ptr(t), ptr(ni), ptr(inl), ptr(ok), stream_ptr())
     return {'qvec': q, 'tvec': t, 'num_inliers': ni, 'inliers': inl.bool(), 'success': ok.bool()}
+
+
+# ---- "next" rows: recognition -> matching glue, projection refinement ------------------------------------
+
+def segmentation(logits: Tensor, bg_threshold: float, want_probs: bool = False):
+    """logits [T,C] -> (bg_prob [T], seg_id [T] (argmax-1), non_bg [T] bool [, probs [T,C]]);
+    reference localization/frame.py:96-121."""
+    logits = _f32c(logits)
+    t, c = logits.shape
+    dev = logits.device
+    probs = torch.empty_like(logits) if want_probs else None
+    bg = torch.empty((t,), device=dev, dtype=torch.float32)
+    sid = torch.empty((t,), device=dev, dtype=torch.int32)
+    nb = torch.empty((t,), device=dev, dtype=torch.uint8)
+    call('pram_segmentation', ptr(logits), t, c, float(bg_threshold), ptr(probs), ptr(bg), ptr(sid), ptr(nb), stream_ptr())
+    return (bg, sid, nb.bool(), probs) if want_probs else (bg, sid, nb.bool())
+
+
+def rank_landmarks(logits: Tensor, keep: Optional[Tensor], topk: int, max_ranks: int = 8):
+    """logits [B,N,C], keep [B,N] bool or None -> dict(sid, rank, count, score [B,topk], n [B],
+    label_at_rank [B,max_ranks,N]); reference localization/multimap3d.py:348-379."""
+    logits = _f32c(logits)
+    b, n, c = logits.shape
+    dev = logits.device
+    k8 = keep.to(torch.uint8).contiguous() if keep is not None else None
+    mk = lambda dt: torch.zeros((b, topk), device=dev, dtype=dt)
+    sid, rank, cnt, score = mk(torch.int32), mk(torch.int32), mk(torch.int32), mk(torch.float32)
+    ne = torch.empty((b,), device=dev, dtype=torch.int32)
+    lab = torch.full((b, max_ranks, n), -1, device=dev, dtype=torch.int32)
+    call('pram_rank_landmarks', ptr(logits), ptr(k8), b, n, c, topk, max_ranks, ptr(sid), ptr(rank), ptr(cnt), ptr(score),
+         ptr(ne), ptr(lab), stream_ptr())
+    return {'sid': sid, 'rank': rank, 'count': cnt, 'score': score, 'n': ne, 'label_at_rank': lab}
+
+
+def match_by_projection(q_kpts: Tensor, q_descs: Tensor, xyz: Tensor, descs: Tensor, R, t, fx, fy, cx, cy, width, height,
+                        threshold: float, ratio: float = 0.995, split: int = 3):
+    """K18: q_kpts [M,2], q_descs [M,128], xyz [N,3], descs [N,128] (device fp32), pose (R [3,3], t [3]) ->
+    (match [M] i64 index into xyz or -1, d0 [M], d1 [M]).  The M x N similarity runs on the tcgen05 GEMM."""
+    dev = q_kpts.device
+    m, n = q_kpts.shape[0], xyz.shape[0]
+    pose = torch.cat([torch.as_tensor(R, dtype=torch.float64).reshape(9), torch.as_tensor(t, dtype=torch.float64).reshape(3)]).to(dev)
+    uv = torch.empty((n, 2), device=dev, dtype=torch.float32)
+    valid = torch.empty((n,), device=dev, dtype=torch.uint8)
+    call('pram_project_points', ptr(_f32c(xyz)), n, ptr(pose), float(fx), float(fy), float(cx), float(cy), float(width),
+         float(height), ptr(uv), ptr(valid), stream_ptr())
+    sim = torch.empty((m, n), device=dev, dtype=torch.float32)
+    linear_tc(split_bf16(_f32c(q_descs), split == 3), q_descs.shape[1], m, q_descs.shape[1],
+              split_bf16(_f32c(descs), split == 3), n, out_f32=sim, ld_f32=n, split=split)
+    match = torch.empty((m,), device=dev, dtype=torch.int64)
+    d0 = torch.empty((m,), device=dev, dtype=torch.float32)
+    d1 = torch.empty((m,), device=dev, dtype=torch.float32)
+    call('pram_projection_top2', ptr(sim), n, m, n, ptr(_f32c(q_kpts)), ptr(uv), ptr(valid), float(2 * threshold),
+         float(ratio), ptr(match), ptr(d0), ptr(d1), stream_ptr())
+    return match, d0, d1

@@ -133,3 +133,41 @@ def test_pose_oracle_known_answer():
     gt_inl = np.ones(n, bool)
     gt_inl[out_idx] = False
     assert (ret['inliers'] == gt_inl).mean() > 0.98
+
+
+@needs_ref
+def test_next_row_oracles_vs_reference_methods():
+    """add_segmentations / process_segmentations restatements vs the reference's own methods, imported with
+    stub modules for the dependencies that are absent here (pycolmap, h5py, ...)."""
+    import sys
+    import types
+    RL.import_reference()
+    class _Any(types.ModuleType):  # stub module: any attribute resolves to a dummy class
+        def __getattr__(self, item):
+            if item.startswith('__'):
+                raise AttributeError(item)
+            return type(item, (), {})
+    for name in ('pycolmap', 'h5py', 'progressbar', 'open3d', 'tensorboardX', 'pypangolin', 'OpenGL', 'OpenGL.GL'):
+        sys.modules.setdefault(name, _Any(name))
+    try:
+        from localization.frame import Frame
+        from localization.multimap3d import MultiMap3D
+    except Exception as e:  # noqa: BLE001 -- the reference pulls many optional dependencies
+        pytest.skip(f'reference localization modules not importable here: {e!r}')
+    g = torch.Generator().manual_seed(1)
+    logits = torch.randn(500, 113, generator=g) * 3
+    logits[:200, 0] += 9
+    fr = Frame.__new__(Frame)
+    fr.keypoints = np.zeros((500, 3), np.float32)
+    fr.descriptors = np.zeros((500, 128), np.float32)
+    fr.initialize_localization_variables = lambda: None
+    fr.add_segmentations(logits, 0.95)
+    keep, scores, ids = O.add_segmentations(logits, 0.95)
+    assert fr.keypoints.shape[0] == int(keep.sum())
+    assert np.array_equal(fr.seg_ids, ids.numpy()) and np.allclose(fr.seg_scores, scores.numpy())
+    mm = MultiMap3D.__new__(MultiMap3D)
+    ref = mm.process_segmentations(torch.from_numpy(fr.segmentations), topk=20)
+    ours = O.process_segmentations(torch.from_numpy(fr.segmentations), topk=20)
+    assert len(ref) == len(ours)
+    for (s0, i0, v0), (s1, i1, v1) in zip(ref, ours):
+        assert s0 == s1 and np.array_equal(i0, i1) and v0 == v1
