@@ -133,9 +133,12 @@ struct Cfg {
     static constexpr int Q_BYTES = BQ * HD * 2;           // 16 KB per plane
     static constexpr int K_BYTES = BKV * HD * 2;          // 16 KB per plane
     static constexpr int V_BYTES = BKV * HD * 2;          // two boxes of 64 d x 64 keys
-    static constexpr int KV_STAGE = NPL * (K_BYTES + V_BYTES);
-    static constexpr int STAGES = 2;
-    static constexpr int SMEM_BYTES = NPL * Q_BYTES + STAGES * KV_STAGE + 1024 + 256 + 2048 /*row max/sum exchange*/;
+    // K and V live in separate rings: K_{g+1} is needed (for S_{g+1}) while V_{g-1} / V_g are still being consumed
+    // by the PV MMAs, so K gets 3 stages and is prefetched one tile ahead of V (2 stages)
+    static constexpr int K_STAGES = 3, V_STAGES = 2;
+    static constexpr int K_STAGE = NPL * K_BYTES, V_STAGE = NPL * V_BYTES;
+    static constexpr int SMEM_BYTES = NPL * Q_BYTES + K_STAGES * K_STAGE + V_STAGES * V_STAGE + 1024 + 256 + 2048 /*row max/sum exchange*/;
+    static_assert(SMEM_BYTES <= 227 * 1024, "dynamic shared memory budget of sm_100a exceeded");
 };
 
 template <int SPLIT>
@@ -147,17 +150,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* q_s = smem;                                  // [NPL][16 KB]
-    uint8_t* kv_s = smem + C::NPL * C::Q_BYTES;           // [STAGES][K planes | V planes]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(kv_s + C::STAGES * C::KV_STAGE);
+    uint8_t* k_s = smem + C::NPL * C::Q_BYTES;            // [K_STAGES][planes]
+    uint8_t* v_s = k_s + C::K_STAGES * C::K_STAGE;        // [V_STAGES][planes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + C::V_STAGES * C::V_STAGE);
     uint64_t* q_full = bars + 0;
     uint64_t* q_empty = bars + 1;
-    uint64_t* kv_full = bars + 2;   // [2]
-    uint64_t* kv_empty = bars + 4;  // [2]
-    uint64_t* s_full = bars + 6;    // [2]
-    uint64_t* s_empty = bars + 8;   // [2]
-    uint64_t* p_full = bars + 10;
-    uint64_t* o_done = bars + 11;
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* k_full = bars + 2;    // [3]
+    uint64_t* k_empty = bars + 5;   // [3]
+    uint64_t* v_full = bars + 8;    // [2]
+    uint64_t* v_empty = bars + 10;  // [2]
+    uint64_t* s_full = bars + 12;   // [2]
+    uint64_t* s_empty = bars + 14;  // [2]
+    uint64_t* p_full = bars + 16;
+    uint64_t* o_done = bars + 17;
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tiles = (p.Nq + BQ - 1) / BQ;
@@ -166,8 +172,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1); mbar_init(q_empty, 1);
+        for (int s = 0; s < 3; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+            mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
             mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8);
         }
         mbar_init(p_full, 8); mbar_init(o_done, 1);
@@ -185,36 +192,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
 
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
-        uint32_t g = 0, w = 0;  // global kv-tile counter, work-item counter
-        for (int item = blockIdx.x; item < total; item += gridDim.x, ++w) {
-            const int bh = item / q_tiles, q0 = (item % q_tiles) * BQ;
-            mbar_wait(q_empty, (w & 1) ^ 1);
+        // this CTA's tiles in issue order: t -> (local item t / kv_tiles, key tile t % kv_tiles)
+        const int n_items = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int n_tiles = n_items * kv_tiles;
+        auto item_of = [&](int li) { return (int)blockIdx.x + li * (int)gridDim.x; };
+        auto load_q = [&](int li) {
+            const int item = item_of(li), bh = item / q_tiles, q0 = (item % q_tiles) * BQ;
+            mbar_wait(q_empty, (li & 1) ^ 1);
             mbar_expect_tx(q_full, C::NPL * C::Q_BYTES);
             tma_load_3d(q_s, &map_q_hi, q_full, 0, q0, bh);
             if (SPLIT == 3) tma_load_3d(q_s + C::Q_BYTES, &map_q_lo, q_full, 0, q0, bh);
-            for (int j = 0; j < kv_tiles; ++j, ++g) {
-                const int st = g & 1;
-                mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
-                uint8_t* ks = kv_s + st * C::KV_STAGE;
-                uint8_t* vs = ks + C::NPL * C::K_BYTES;
-                mbar_expect_tx(&kv_full[st], C::KV_STAGE);
-                const int k0 = j * BKV;
-                tma_load_3d(ks, &map_k_hi, &kv_full[st], 0, k0, bh);
-                if (p.v_mn) {
-                    tma_load_3d(vs, &map_v_hi, &kv_full[st], 0, k0, bh);  // one {64 d x 128 keys} box
-                } else {
-                    tma_load_3d(vs, &map_v_hi, &kv_full[st], k0, 0, bh);
-                    tma_load_3d(vs + C::V_BYTES / 2, &map_v_hi, &kv_full[st], k0 + 64, 0, bh);
-                }
+        };
+        auto load_k = [&](int t) {
+            const int bh = item_of(t / kv_tiles) / q_tiles, k0 = (t % kv_tiles) * BKV;
+            const int st = t % C::K_STAGES;
+            mbar_wait(&k_empty[st], ((t / C::K_STAGES) & 1) ^ 1);
+            uint8_t* ks = k_s + st * C::K_STAGE;
+            mbar_expect_tx(&k_full[st], C::K_STAGE);
+            tma_load_3d(ks, &map_k_hi, &k_full[st], 0, k0, bh);
+            if (SPLIT == 3) tma_load_3d(ks + C::K_BYTES, &map_k_lo, &k_full[st], 0, k0, bh);
+        };
+        auto load_v = [&](int t) {
+            const int bh = item_of(t / kv_tiles) / q_tiles, k0 = (t % kv_tiles) * BKV;
+            const int st = t & 1;
+            mbar_wait(&v_empty[st], ((t >> 1) & 1) ^ 1);
+            uint8_t* vs = v_s + st * C::V_STAGE;
+            mbar_expect_tx(&v_full[st], C::V_STAGE);
+            if (p.v_mn) {
+                tma_load_3d(vs, &map_v_hi, &v_full[st], 0, k0, bh);  // one {64 d x 128 keys} box
+                if (SPLIT == 3) tma_load_3d(vs + C::V_BYTES, &map_v_lo, &v_full[st], 0, k0, bh);
+            } else {
+                tma_load_3d(vs, &map_v_hi, &v_full[st], k0, 0, bh);
+                tma_load_3d(vs + C::V_BYTES / 2, &map_v_hi, &v_full[st], k0 + 64, 0, bh);
                 if (SPLIT == 3) {
-                    tma_load_3d(ks + C::K_BYTES, &map_k_lo, &kv_full[st], 0, k0, bh);
-                    if (p.v_mn) {
-                        tma_load_3d(vs + C::V_BYTES, &map_v_lo, &kv_full[st], 0, k0, bh);
-                    } else {
-                        tma_load_3d(vs + C::V_BYTES, &map_v_lo, &kv_full[st], k0, 0, bh);
-                        tma_load_3d(vs + C::V_BYTES + C::V_BYTES / 2, &map_v_lo, &kv_full[st], k0 + 64, 0, bh);
-                    }
+                    tma_load_3d(vs + C::V_BYTES, &map_v_lo, &v_full[st], k0, 0, bh);
+                    tma_load_3d(vs + C::V_BYTES + C::V_BYTES / 2, &map_v_lo, &v_full[st], k0 + 64, 0, bh);
                 }
+            }
+        };
+        if (n_tiles > 0) {
+            load_q(0);
+            load_k(0);
+            for (int t = 0; t < n_tiles; ++t) {
+                if (t + 1 < n_tiles) load_k(t + 1);  // K runs one tile ahead of V
+                load_v(t);
+                if ((t + 1) % kv_tiles == 0 && t + 1 < n_tiles) load_q((t + 1) / kv_tiles);
             }
         }
     } else if (warp == 1 && lane == 0) {
@@ -224,11 +246,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
         uint32_t g = 0, w = 0;
         const uint32_t q_hi = smem_u32(q_s), q_lo = q_hi + C::Q_BYTES;
         auto issue_S = [&](uint32_t gg) {
-            const int st = gg & 1;
-            mbar_wait(&kv_full[st], (gg >> 1) & 1);
+            const int st = gg & 1, kst = gg % C::K_STAGES;
+            mbar_wait(&k_full[kst], (gg / C::K_STAGES) & 1);
             mbar_wait(&s_empty[st], ((gg >> 1) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t k_hi = smem_u32(kv_s + st * C::KV_STAGE), k_lo = k_hi + C::K_BYTES;
+            const uint32_t k_hi = smem_u32(k_s + kst * C::K_STAGE), k_lo = k_hi + C::K_BYTES;
             const uint32_t d = tmem_base + (st ? COL_S1 : COL_S0);
 #pragma unroll
             for (int k = 0; k < HD / 16; ++k) {
@@ -239,6 +261,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                     umma_ss(d, make_desc(q_hi + ko), make_desc(k_lo + ko), idesc_s, 1);
                 }
             }
+            umma_commit(&k_empty[kst]);  // K slot frees when these MMAs retire
             umma_commit(&s_full[st]);
         };
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++w) {
@@ -251,7 +274,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                 mbar_wait(p_full, g & 1);
                 tc_fence_after();
                 const int st = g & 1;
-                const uint32_t v_hi = smem_u32(kv_s + st * C::KV_STAGE + C::NPL * C::K_BYTES), v_lo = v_hi + C::V_BYTES;
+                mbar_wait(&v_full[st], (g >> 1) & 1);
+                tc_fence_after();
+                const uint32_t v_hi = smem_u32(v_s + st * C::V_STAGE), v_lo = v_hi + C::V_BYTES;
                 const uint32_t d = tmem_base + COL_O;
 #pragma unroll
                 for (int ks = 0; ks < BKV / 16; ++ks) {
@@ -264,7 +289,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                         umma_ts(d, a_hi, p.v_mn ? make_desc_mn(v_lo + vo) : make_desc(v_lo + vo), idesc_o, 1);
                     }
                 }
-                umma_commit(&kv_empty[st]);
+                umma_commit(&v_empty[st]);
                 umma_commit(o_done);
             }
         }

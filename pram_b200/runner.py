@@ -43,6 +43,8 @@ class LocalizationPipeline:
         self.max_error = ransac_max_error
         self.cfg = {'min_keypoints': 128, 'max_keypoints': max_keypoints}
         self.num_hypotheses = 1024
+        self.pre_filtering_th = 0.95  # configs/config_train_7scenes_sfd2.yaml: pre_filtering_th
+        self.seg_k = 20               # configs/config_train_7scenes_sfd2.yaml: seg_k
 
     # -- stages -------------------------------------------------------------------------------
     def features(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -71,6 +73,11 @@ class LocalizationPipeline:
         out = {'keypoints': f['keypoints'], 'num_keypoints': f['num_keypoints'],
                'prediction': self.recognize(f, shape)}
         out['labels'] = out['prediction'].argmax(-1)
+        # recognition -> matching glue (reference frame.py:96-121, multimap3d.py:348-379), kept on the device
+        b, k, c = out['prediction'].shape
+        bg, sid, non_bg = ops.segmentation(out['prediction'].reshape(b * k, c), self.pre_filtering_th)
+        out['seg_ids'], out['non_bg'] = sid.view(b, k), non_bg.view(b, k)
+        out['landmarks'] = ops.rank_landmarks(out['prediction'], out['non_bg'], self.seg_k, max_ranks=8)
         if smap is not None:
             m = self.match(f, smap, shape)
             out.update(m)
