@@ -3,6 +3,7 @@
 // Replaces reference nets/sfd2.py:294-329 (score map, simple_nms :20-35, threshold/border/top-k
 // :306-329).  All HBM-bound: coalesced vector loads, shared-memory staging, no host sync.
 #include "common.cuh"
+#include "nms_tile.cuh"
 
 // ------------------------------------------------------------------------------------------
 // K5: softmax over 65 detector channels, drop the dustbin, 8x8 pixel shuffle.
@@ -102,133 +103,129 @@ PRAM_API int pram_resize_bilinear(const float* in, int B, int Hi, int Wi, float*
 // with warp-aggregated atomics; the number of pixels >= th_hi is counted for the reference's
 // "too few keypoints -> halve the threshold" rule (nets/sfd2.py:311-315).
 // ------------------------------------------------------------------------------------------
-constexpr int NMS_TW = 64, NMS_TH = 32, NMS_MAXR = 4;
-constexpr int NMS_THREADS = 512;
+// Implementation: nms_tile.cuh (phase functions shared with the host emulation in tests/nms_host.cu).
+// ------------------------------------------------------------------------------------------
+constexpr int NMS_MAXR = 4;
+constexpr int NMS_THREADS = 384;
 
-struct NmsSmem {
-    // sized for the largest halo (r = 4 -> 20)
-    static constexpr int HALO = 5 * NMS_MAXR;
-    static constexpr int SW = NMS_TW + 2 * HALO, SH = NMS_TH + 2 * HALO;
-    float S[SH * SW];
-    float T[SH * SW];
-    unsigned char keep[SH * SW];
-    unsigned char supp[SH * SW];
-    unsigned char tb[SH * SW];
-    int block_count;
-    int block_base;
-    int block_hi;
-};
-
+template <int R, int TH>
 __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
-    const float* __restrict__ score, int H, int W, int r, float th_lo, float th_hi,
+    const float* __restrict__ score, int H, int W, float th_lo, float th_hi,
     float* __restrict__ nms_out, unsigned long long* __restrict__ cand, int cap,
     int* __restrict__ cand_count, int* __restrict__ count_hi) {
+    using G = NmsGeom<R, TH>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    NmsSmem& sm = *reinterpret_cast<NmsSmem*>(smem_raw);
-    const int halo = 5 * r;
-    const int SW = NMS_TW + 2 * halo, SH = NMS_TH + 2 * halo;
-    const int n = SW * SH;
+    __shared__ int block_count, block_base, block_hi;
+    NmsTile t;
+    t.S = reinterpret_cast<float*>(smem_raw);
+    t.T = t.S + G::S_FLOATS;
+    t.keep = reinterpret_cast<unsigned char*>(t.T + G::T_FLOATS);
+    t.supp = t.keep + G::MASK_BYTES;
+    t.tmpb = t.supp + G::MASK_BYTES;
+    t.x0 = blockIdx.x * G::TW - G::HALO;
+    t.y0 = blockIdx.y * G::TH - G::HALO;
+    t.H = H; t.W = W;
     const int b = blockIdx.z;
-    const int x0 = blockIdx.x * NMS_TW - halo, y0 = blockIdx.y * NMS_TH - halo;
-    const float* sc = score + (long long)b * H * W;
-    const float NEG = -INFINITY;
-    if (threadIdx.x == 0) { sm.block_count = 0; sm.block_hi = 0; }
-    for (int i = threadIdx.x; i < n; i += NMS_THREADS) {
-        int ly = i / SW, lx = i - ly * SW;
-        int gy = y0 + ly, gx = x0 + lx;
-        sm.S[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? sc[(long long)gy * W + gx] : NEG;
-    }
+    t.score = score + (long long)b * H * W;
+    const int tid = threadIdx.x;
+    if (tid == 0) { block_count = 0; block_hi = 0; }
+    constexpr int N_INIT = (8 * G::SW / 4 > G::MASK_BYTES / 4) ? 8 * G::SW / 4 : G::MASK_BYTES / 4;
+    for (int i = tid; i < N_INIT; i += NMS_THREADS) nms_init<G>(t, i);
+    for (int i = tid; i < G::SH * (G::NG + 2); i += NMS_THREADS) nms_load<G>(t, i);
     __syncthreads();
-    // ---- keep0 ----
-    for (int i = threadIdx.x; i < n; i += NMS_THREADS) {
-        int ly = i / SW, lx = i - ly * SW;
-        int a = max(lx - r, 0), e = min(lx + r, SW - 1);
-        float m = NEG;
-        for (int x = a; x <= e; ++x) m = fmaxf(m, sm.S[ly * SW + x]);
-        sm.T[i] = m;
-    }
+    for (int i = tid; i < G::SH * (G::SW / 8); i += NMS_THREADS) nms_rowmax<G, R, false>(t, i);
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += NMS_THREADS) {
-        int ly = i / SW, lx = i - ly * SW;
-        int a = max(ly - r, 0), e = min(ly + r, SH - 1);
-        float m = NEG;
-        for (int y = a; y <= e; ++y) m = fmaxf(m, sm.T[y * SW + lx]);
-        float s = sm.S[i];
-        sm.keep[i] = (s == m) && (s > NEG);
-    }
+    for (int i = tid; i < (G::SH / 8) * G::NG; i += NMS_THREADS) nms_colmax<G, R, false>(t, i);
     __syncthreads();
+#pragma unroll 1
     for (int round = 0; round < 2; ++round) {
-        // dilate keep -> supp
-        for (int i = threadIdx.x; i < n; i += NMS_THREADS) {
-            int ly = i / SW, lx = i - ly * SW;
-            int a = max(lx - r, 0), e = min(lx + r, SW - 1);
-            unsigned char v = 0;
-            for (int x = a; x <= e; ++x) v |= sm.keep[ly * SW + x];
-            sm.tb[i] = v;
-        }
+        for (int i = tid; i < G::SH * G::NG; i += NMS_THREADS) nms_dilate_h<G, R>(t, i);
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += NMS_THREADS) {
-            int ly = i / SW, lx = i - ly * SW;
-            int a = max(ly - r, 0), e = min(ly + r, SH - 1);
-            unsigned char v = 0;
-            for (int y = a; y <= e; ++y) v |= sm.tb[y * SW + lx];
-            sm.supp[i] = v;
-        }
+        for (int i = tid; i < G::SH * (G::GW / 4); i += NMS_THREADS) nms_dilate_v<G, R>(t, i);
         __syncthreads();
-        // rest = supp ? 0 : s  (outside the image stays -inf); row max
-        for (int i = threadIdx.x; i < n; i += NMS_THREADS) {
-            int ly = i / SW, lx = i - ly * SW;
-            int a = max(lx - r, 0), e = min(lx + r, SW - 1);
-            float m = NEG;
-            for (int x = a; x <= e; ++x) {
-                float s = sm.S[ly * SW + x];
-                float rest = (sm.supp[ly * SW + x] && s > NEG) ? 0.f : s;
-                m = fmaxf(m, rest);
+        for (int i = tid; i < G::SH * (G::SW / 8); i += NMS_THREADS) nms_rowmax<G, R, true>(t, i);
+        __syncthreads();
+        for (int i = tid; i < (G::SH / 8) * G::NG; i += NMS_THREADS) nms_colmax<G, R, true>(t, i);
+        __syncthreads();
+    }
+    // ---- epilogue over the inner tile: nms map, counts, candidate emission (two passes over the nibbles) ----
+    int my_n = 0, my_hi = 0;
+    for (int i = tid; i < G::TH * 32; i += NMS_THREADS) {
+        int gy, gx;
+        const float4 v4 = nms_result<G>(t, i, gy, gx);
+        if (gy >= H || gx >= W) continue;
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+        if (nms_out) {
+            float* op = nms_out + ((long long)b * H + gy) * W + gx;
+            if (gx + 3 < W && (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+                *reinterpret_cast<float4*>(op) = v4;
+            } else {
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+                    if (gx + x < W) op[x] = v[x];
             }
-            sm.T[i] = m;
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += NMS_THREADS) {
-            int ly = i / SW, lx = i - ly * SW;
-            int a = max(ly - r, 0), e = min(ly + r, SH - 1);
-            float m = NEG;
-            for (int y = a; y <= e; ++y) m = fmaxf(m, sm.T[y * SW + lx]);
-            float s = sm.S[i];
-            bool sp = sm.supp[i];
-            float rest = (sp && s > NEG) ? 0.f : s;
-            if ((rest == m) && !sp && (s > NEG)) sm.keep[i] = 1;
-        }
-        __syncthreads();
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+            if (gx + x < W) {
+                my_hi += (v[x] >= th_hi);
+                my_n += (v[x] >= th_lo && v[x] > 0.f);
+            }
     }
-    // ---- epilogue over the inner tile: nms map, candidate emission, counts ----
-    int my_hi = 0;
-    unsigned long long my_keys[(NMS_TW * NMS_TH + NMS_THREADS - 1) / NMS_THREADS];
-    int my_n = 0;
-    for (int i = threadIdx.x; i < NMS_TW * NMS_TH; i += NMS_THREADS) {
-        int ty = i / NMS_TW, tx = i - ty * NMS_TW;
-        int gy = blockIdx.y * NMS_TH + ty, gx = blockIdx.x * NMS_TW + tx;
-        if (gy < H && gx < W) {
-            int li = (ty + halo) * SW + tx + halo;
-            float v = sm.keep[li] ? sm.S[li] : 0.f;
-            if (nms_out) nms_out[((long long)b * H + gy) * W + gx] = v;
-            if (v >= th_hi) ++my_hi;
-            if (v >= th_lo && v > 0.f)
-                my_keys[my_n++] = ((unsigned long long)__float_as_uint(v) << 32) |
-                                  (unsigned int)(gy * W + gx);
-        }
-    }
-    if (my_hi) atomicAdd(&sm.block_hi, my_hi);
-    int my_off = my_n ? atomicAdd(&sm.block_count, my_n) : 0;
+    if (my_hi) atomicAdd(&block_hi, my_hi);
+    int my_off = my_n ? atomicAdd(&block_count, my_n) : 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        sm.block_base = sm.block_count ? atomicAdd(&cand_count[b], sm.block_count) : 0;
-        if (sm.block_hi) atomicAdd(&count_hi[b], sm.block_hi);
+    if (tid == 0) {
+        block_base = block_count ? atomicAdd(&cand_count[b], block_count) : 0;
+        if (block_hi) atomicAdd(&count_hi[b], block_hi);
     }
     __syncthreads();
-    for (int k = 0; k < my_n; ++k) {
-        int pos = sm.block_base + my_off + k;
-        if (pos < cap) cand[(long long)b * cap + pos] = my_keys[k];
+    if (my_n) {
+        int pos = block_base + my_off;
+        for (int i = tid; i < G::TH * 32; i += NMS_THREADS) {
+            int gy, gx;
+            const float4 v4 = nms_result<G>(t, i, gy, gx);
+            if (gy >= H || gx >= W) continue;
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+                if (gx + x < W && v[x] >= th_lo && v[x] > 0.f) {
+                    if (pos < cap)
+                        cand[(long long)b * cap + pos] = ((unsigned long long)__float_as_uint(v[x]) << 32) |
+                                                        (unsigned int)(gy * W + gx + x);
+                    ++pos;
+                }
+        }
     }
+}
+
+template <int R, int TH>
+static int nms_launch(const float* score, int B, int H, int W, float th_lo, float th_hi, float* nms_out,
+                      unsigned long long* cand, int cap, int* cand_count, int* count_hi, cudaStream_t stream) {
+    using G = NmsGeom<R, TH>;
+    auto kern = nms_kernel<R, TH>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        attr_set = true;
+    }
+    dim3 grid(cdiv(W, G::TW), cdiv(H, G::TH), B);
+    kern<<<grid, NMS_THREADS, G::SMEM, stream>>>(score, H, W, th_lo, th_hi, nms_out, cand, cap, cand_count, count_hi);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+template <int R>
+static int nms_dispatch(const float* score, int B, int H, int W, float th_lo, float th_hi, float* nms_out,
+                        unsigned long long* cand, int cap, int* cand_count, int* count_hi, cudaStream_t stream) {
+    // tall tiles (1.9x halo redundancy, 1 CTA/SM) once they fill the GPU twice over; short tiles (2 CTAs/SM,
+    // 4x more CTAs) for small batches / single-frame latency
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const long long tall = (long long)cdiv(W, 128) * cdiv(H, 96) * B;
+    if (tall >= 2LL * sms)
+        return nms_launch<R, 96>(score, B, H, W, th_lo, th_hi, nms_out, cand, cap, cand_count, count_hi, stream);
+    return nms_launch<R, 24>(score, B, H, W, th_lo, th_hi, nms_out, cand, cap, cand_count, count_hi, stream);
 }
 
 PRAM_API int pram_nms_candidates(const float* score, int B, int H, int W, int radius, float th_lo,
@@ -236,19 +233,15 @@ PRAM_API int pram_nms_candidates(const float* score, int B, int H, int W, int ra
                                  int* cand_count, int* count_hi, cudaStream_t stream) {
     if (!score || !cand || !cand_count || !count_hi || B <= 0 || radius < 0 || radius > NMS_MAXR)
         return PRAM_ERR_ARG;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PRAM_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(NmsSmem)));
-        attr_set = true;
-    }
     PRAM_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int) * B, stream));
     PRAM_CUDA(cudaMemsetAsync(count_hi, 0, sizeof(int) * B, stream));
-    dim3 grid(cdiv(W, NMS_TW), cdiv(H, NMS_TH), B);
-    nms_kernel<<<grid, NMS_THREADS, sizeof(NmsSmem), stream>>>(score, H, W, radius, th_lo, th_hi,
-                                                              nms_out, cand, cap, cand_count, count_hi);
-    PRAM_CHECK_LAUNCH();
-    return PRAM_OK;
+    switch (radius) {
+        case 0: return nms_dispatch<0>(score, B, H, W, th_lo, th_hi, nms_out, cand, cap, cand_count, count_hi, stream);
+        case 1: return nms_dispatch<1>(score, B, H, W, th_lo, th_hi, nms_out, cand, cap, cand_count, count_hi, stream);
+        case 2: return nms_dispatch<2>(score, B, H, W, th_lo, th_hi, nms_out, cand, cap, cand_count, count_hi, stream);
+        case 3: return nms_dispatch<3>(score, B, H, W, th_lo, th_hi, nms_out, cand, cap, cand_count, count_hi, stream);
+        default: return nms_dispatch<4>(score, B, H, W, th_lo, th_hi, nms_out, cand, cap, cand_count, count_hi, stream);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
