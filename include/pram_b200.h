@@ -88,6 +88,12 @@ int pram_gconv3x3_f32(const float* in, const float* w, const float* bias, float*
 int pram_gconv3x3_split(const float* in, const float* w, const float* bias, float* out_f32, void* out_hi,
                         void* out_lo, int B, int H, int W, int groups, int relu, pram_stream_t stream);
 
+/* same convolution on tensor cores (warp-level bf16 MMA, m16n8k16 = 16 pixels x one 8-channel group x two taps),
+ * split-bf16 NHWC planes in and out; replaces the cuDNN grouped convolution of nets/sfd2.py:100-124 (ResBlock.conv2,
+ * groups = 32).  w fp32 [9][8 ci][8 co][C/8], C % 64 == 0, lo planes NULL when split == 1. */
+int pram_gconv3x3_tc(const void* in_hi, const void* in_lo, const float* w, const float* bias, void* out_hi, void* out_lo,
+                     int B, int H, int W, int C, int relu, int split, pram_stream_t stream);
+
 /* K1 first layer: conv1a 3->64 + BN + ReLU straight from the NCHW image, output as split-bf16 NHWC in
  * the 2x2 phase-split layout consumed by the stride-2 conv1b (and/or fp32 NHWC).  nets/sfd2.py:141.
  * w[27][64] (tap-major (r,s,c)), bias[64]. */

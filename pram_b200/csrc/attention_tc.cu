@@ -25,7 +25,6 @@ struct Args {
     int BH, heads, Nq, Nk;
     float scale_log2;  // softmax scale * log2(e)
     float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_ld;
-    int p_swap;        // debug: swap the two bf16 halves of a packed P column
     int v_mn;          // 1: V given as [BH][Nk][64] (MN-major B operand), 0: V^T [BH][64][nk_pad] (K-major)
 };
 
@@ -352,16 +351,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p2) : "f"(fmaf(__uint_as_float(v1[i]), p.scale_log2, -m_used)));
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p3) : "f"(fmaf(__uint_as_float(v1[i + 1]), p.scale_log2, -m_used)));
                     lsum += (p0 + p1) + (p2 + p3);
-                    __nv_bfloat162 ha = p.p_swap ? __floats2bfloat162_rn(p1, p0) : __floats2bfloat162_rn(p0, p1);
-                    __nv_bfloat162 hb = p.p_swap ? __floats2bfloat162_rn(p3, p2) : __floats2bfloat162_rn(p2, p3);
+                    __nv_bfloat162 ha = __floats2bfloat162_rn(p0, p1);
+                    __nv_bfloat162 hb = __floats2bfloat162_rn(p2, p3);
                     const uint32_t ua = *reinterpret_cast<uint32_t*>(&ha), ub = *reinterpret_cast<uint32_t*>(&hb);
                     ph[i >> 1] = ua;
                     ph[16 + (i >> 1)] = ub;
                     if (SPLIT == 3) {
-                        const float a_lo = (p.p_swap ? p1 : p0) - __uint_as_float(ua << 16);
-                        const float a_hi = (p.p_swap ? p0 : p1) - __uint_as_float(ua & 0xffff0000u);
-                        const float b_lo = (p.p_swap ? p3 : p2) - __uint_as_float(ub << 16);
-                        const float b_hi = (p.p_swap ? p2 : p3) - __uint_as_float(ub & 0xffff0000u);
+                        const float a_lo = p0 - __uint_as_float(ua << 16);
+                        const float a_hi = p1 - __uint_as_float(ua & 0xffff0000u);
+                        const float b_lo = p2 - __uint_as_float(ub << 16);
+                        const float b_hi = p3 - __uint_as_float(ub & 0xffff0000u);
                         __nv_bfloat162 la = __floats2bfloat162_rn(a_lo, a_hi), lb = __floats2bfloat162_rn(b_lo, b_hi);
                         pl[i >> 1] = *reinterpret_cast<uint32_t*>(&la);
                         pl[16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&lb);
@@ -485,6 +484,7 @@ PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k
     using namespace fa;
     if (!q_hi || !k_hi || !vt_hi || B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return PRAM_ERR_ARG;
     if (split != 1 && split != 3) return PRAM_ERR_ARG;
+    if (p_swap) return PRAM_ERR_UNSUPPORTED;  // former debug knob of the P packing order; kept in the ABI, must be 0
     if (split == 3 && (!q_lo || !k_lo || !vt_lo)) return PRAM_ERR_ARG;
     if ((!v_mn && ((nk_pad % 8) || nk_pad < Nk)) || (out_ld % 8)) return PRAM_ERR_UNSUPPORTED;
     static int num_sms = 0;
@@ -511,7 +511,6 @@ PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k
     a.BH = BH; a.heads = heads; a.Nq = Nq; a.Nk = Nk;
     a.scale_log2 = scale * 1.4426950408889634f;
     a.out_f32 = out_f32; a.out_hi = (__nv_bfloat16*)out_hi; a.out_lo = (__nv_bfloat16*)out_lo; a.out_ld = out_ld;
-    a.p_swap = p_swap;
     a.v_mn = v_mn;
     const int total = BH * ((Nq + BQ - 1) / BQ);
     const int grid = total < num_sms ? total : num_sms;

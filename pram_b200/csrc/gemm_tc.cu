@@ -321,6 +321,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
             };
             float4 rv[MODE == 1 ? 8 : 1];
             if constexpr (MODE == 1) load_res(n0 + half * 32, rv);  // independent of the accumulator: overlaps the MMA tail
+            // MODE 2: the rotary factors of a row depend on (token, dim pair) only -- not on the head -- and this
+            // warp's chunks (c = half*32 + 64 m) all cover dims half*32..+31 of head m: ONE load per tile serves
+            // all four chunks and is issued before the accumulator wait (latency hidden behind the MMA).
+            float2 rot_c[MODE == 2 ? 8 : 1], rot_s[MODE == 2 ? 8 : 1];
+            if constexpr (MODE == 2) {
+                const bool rot = (p.qkv_mode == 1) && (nt != 2);
+                const int pr0 = (half * 32 + col1) >> 1;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int pixr = eq.pix[i * 4 + g1];
+                    rot_c[i] = make_float2(1.f, 1.f);
+                    rot_s[i] = make_float2(0.f, 0.f);
+                    if (rot && pixr >= 0) {
+                        rot_c[i] = __ldg(reinterpret_cast<const float2*>(p.cosb + (long long)pixr * 32 + pr0));
+                        rot_s[i] = __ldg(reinterpret_cast<const float2*>(p.sinb + (long long)pixr * 32 + pr0));
+                    }
+                }
+            }
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
@@ -379,9 +397,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                             const bool is_v = (p.qkv_mode == 1) ? (nt == 2) : (nt == 1);
                             if (!is_v) {
                                 if (p.qkv_mode == 1) {  // rotary on adjacent pairs (2i, 2i+1)
-                                    const int pr0 = ((c + col1) & 63) >> 1;
-                                    const float2 cs = __ldg(reinterpret_cast<const float2*>(p.cosb + (long long)pixr * 32 + pr0));
-                                    const float2 sn = __ldg(reinterpret_cast<const float2*>(p.sinb + (long long)pixr * 32 + pr0));
+                                    const float2 cs = rot_c[i], sn = rot_s[i];
                                     const float a0 = f[0] * cs.x + (-f[1]) * sn.x, a1 = f[1] * cs.x + f[0] * sn.x;
                                     const float a2 = f[2] * cs.y + (-f[3]) * sn.y, a3 = f[3] * cs.y + f[2] * sn.y;
                                     f[0] = a0; f[1] = a1; f[2] = a2; f[3] = a3;

@@ -55,19 +55,60 @@ PRAM_API int pram_segmentation(const float* logits, int T, int C, float bg_thres
 }
 
 // ------------------------------------------------------------------------------------------
-// process_segmentations: one CTA per frame.  rank k = 0,1,...: every keypoint's k-th best class (value
-// descending, class index ascending among equal values); classes seen at this rank that are not background and
-// not yet used are appended in order of (vote count descending, class id ascending) until topk entries exist.
-// Outputs: entry_sid / entry_rank / entry_count / entry_score [topk], n_entries, and label_at_rank [max_ranks][N]
-// (so that the keypoint ids of entry e are { i : label_at_rank[entry_rank[e]][i] == entry_sid[e] }).
+// process_segmentations, two launches.
+//  (1) top_classes_kernel: one warp per keypoint reads its C logits once (coalesced, register-resident) and
+//      extracts its max_ranks best classes in (value descending, class index ascending) order ->
+//      label_at_rank [max_ranks][N] (-1 for keypoints filtered out by the background mask).
+//  (2) rank_entries_kernel: one CTA per frame.  rank k = 0,1,...: votes per class at this rank (count, sum of the
+//      logits); classes that are not background and not yet used are appended in order of (vote count
+//      descending, class id ascending) until topk entries exist.
+// Outputs: entry_sid / entry_rank / entry_count / entry_score [topk], n_entries, and label_at_rank
+// (the keypoint ids of entry e are { i : label_at_rank[entry_rank[e]][i] == entry_sid[e] }).
 // ------------------------------------------------------------------------------------------
 constexpr int RK_THREADS = 256;
 constexpr int RK_MAXC = 1024;
 
-__global__ void __launch_bounds__(RK_THREADS) rank_landmarks_kernel(
-    const float* __restrict__ logits, const unsigned char* __restrict__ keep /*optional [B][N]*/, int N, int C, int topk,
-    int max_ranks, int* __restrict__ entry_sid, int* __restrict__ entry_rank, int* __restrict__ entry_count,
-    float* __restrict__ entry_score, int* __restrict__ n_entries, int* __restrict__ label_at_rank) {
+template <int NV>  // classes per lane: C <= 32 * NV
+__global__ void __launch_bounds__(256) top_classes_kernel(const float* __restrict__ logits,
+                                                          const unsigned char* __restrict__ keep /*optional [B][N]*/, int N,
+                                                          int C, int max_ranks, int* __restrict__ label_at_rank) {
+    const int b = blockIdx.y;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= N) return;
+    const float* p = logits + ((long long)b * N + i) * C;
+    float v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = lane + 32 * j;
+        v[j] = (c < C) ? p[c] : -INFINITY;
+    }
+    const bool kept = !keep || keep[(long long)b * N + i];
+    unsigned taken = 0;  // bit j: class lane + 32 j already emitted
+    for (int k = 0; k < max_ranks; ++k) {
+        float bv = -INFINITY;
+        int bc = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            if (c < C && !((taken >> j) & 1u) && (bc == 0x7fffffff || v[j] > bv)) { bv = v[j]; bc = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            const bool better = (oc != 0x7fffffff) && (bc == 0x7fffffff || ov > bv || (ov == bv && oc < bc));
+            if (better) { bv = ov; bc = oc; }
+        }
+        if (bc == 0x7fffffff) bc = -1;  // fewer than k+1 classes
+        if (bc >= 0 && (bc & 31) == lane) taken |= 1u << (bc >> 5);
+        if (lane == 0) label_at_rank[((long long)b * max_ranks + k) * N + i] = kept ? bc : -1;
+    }
+}
+
+__global__ void __launch_bounds__(RK_THREADS) rank_entries_kernel(
+    const float* __restrict__ logits, int N, int C, int topk, int max_ranks, int* __restrict__ entry_sid,
+    int* __restrict__ entry_rank, int* __restrict__ entry_count, float* __restrict__ entry_score, int* __restrict__ n_entries,
+    const int* __restrict__ label_at_rank) {
     __shared__ int cnt[RK_MAXC];
     __shared__ float sum[RK_MAXC];
     __shared__ unsigned char used[RK_MAXC];
@@ -77,52 +118,44 @@ __global__ void __launch_bounds__(RK_THREADS) rank_landmarks_kernel(
     for (int c = threadIdx.x; c < C; c += RK_THREADS) used[c] = 0;
     if (threadIdx.x == 0) { s_n = 0; s_done = 0; }
     __syncthreads();
-    // per-thread state for the keypoints it owns (strided): previous selection (value, class)
-    constexpr int MAXOWN = 32;  // N <= RK_THREADS * MAXOWN = 8192
-    float pv[MAXOWN];
-    int pc[MAXOWN];
-#pragma unroll
-    for (int i = 0; i < MAXOWN; ++i) { pv[i] = INFINITY; pc[i] = -1; }
     for (int k = 0; k < max_ranks && k < C; ++k) {
         for (int c = threadIdx.x; c < C; c += RK_THREADS) { cnt[c] = 0; sum[c] = 0.f; }
         __syncthreads();
-        int own = 0;
-        for (int i = threadIdx.x; i < N && own < MAXOWN; i += RK_THREADS, ++own) {
-            const bool kept = !keep || keep[(long long)b * N + i];
-            // next class in (value desc, class asc) order after (pv, pc)
-            float bv = -INFINITY;
-            int bc = -1;
-            const float* p = L + (long long)i * C;
-            for (int c = 0; c < C; ++c) {
-                const float v = p[c];
-                const bool after = (v < pv[own]) || (v == pv[own] && c > pc[own]);
-                if (after && (v > bv || bc < 0)) { bv = v; bc = c; }
-            }
-            pv[own] = bv; pc[own] = bc;
-            label_at_rank[((long long)b * max_ranks + k) * N + i] = kept ? bc : -1;
-            if (kept && bc >= 0) { atomicAdd(&cnt[bc], 1); atomicAdd(&sum[bc], bv); }
+        const int* lab = label_at_rank + ((long long)b * max_ranks + k) * N;
+        for (int i = threadIdx.x; i < N; i += RK_THREADS) {
+            const int c = lab[i];
+            if (c >= 0) { atomicAdd(&cnt[c], 1); atomicAdd(&sum[c], L[(long long)i * C + c]); }
         }
         __syncthreads();
-        // append unused, non-background classes of this rank by (count desc, class asc)
+        // append unused, non-background classes of this rank by (count desc, class asc); warp 0 does the arg-max
         while (true) {
-            if (threadIdx.x == 0) {
-                int best = -1;
-                for (int c = 1; c < C; ++c)
-                    if (cnt[c] > 0 && !used[c] && (best < 0 || cnt[c] > cnt[best])) best = c;
-                s_best = best;
-                if (best >= 0) {
-                    const int e = s_n;
-                    entry_sid[(long long)b * topk + e] = best;
-                    entry_rank[(long long)b * topk + e] = k;
-                    entry_count[(long long)b * topk + e] = cnt[best];
-                    entry_score[(long long)b * topk + e] = sum[best] / (float)cnt[best];
-                    used[best] = 1;
-                    s_n = e + 1;
-                    if (s_n >= topk) s_done = 1;
+            if (threadIdx.x < 32) {
+                int best = -1, bcnt = 0;
+                for (int c = 1 + threadIdx.x; c < C; c += 32)
+                    if (cnt[c] > 0 && !used[c] && cnt[c] > bcnt) { best = c; bcnt = cnt[c]; }  // ascending c: first wins ties
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const int ob = __shfl_xor_sync(0xffffffffu, best, o), oc = __shfl_xor_sync(0xffffffffu, bcnt, o);
+                    if (ob >= 0 && (best < 0 || oc > bcnt || (oc == bcnt && ob < best))) { best = ob; bcnt = oc; }
+                }
+                if (threadIdx.x == 0) {
+                    s_best = best;
+                    if (best >= 0) {
+                        const int e = s_n;
+                        entry_sid[(long long)b * topk + e] = best;
+                        entry_rank[(long long)b * topk + e] = k;
+                        entry_count[(long long)b * topk + e] = bcnt;
+                        entry_score[(long long)b * topk + e] = sum[best] / (float)bcnt;
+                        used[best] = 1;
+                        s_n = e + 1;
+                        if (s_n >= topk) s_done = 1;
+                    }
                 }
             }
             __syncthreads();
-            if (s_best < 0 || s_done) break;
+            const bool stop = (s_best < 0 || s_done);
+            __syncthreads();  // everyone has read s_best before warp 0 overwrites it
+            if (stop) break;
         }
         if (s_done) break;
     }
@@ -133,9 +166,15 @@ PRAM_API int pram_rank_landmarks(const float* logits, const unsigned char* keep,
                                  int max_ranks, int* entry_sid, int* entry_rank, int* entry_count, float* entry_score,
                                  int* n_entries, int* label_at_rank, cudaStream_t stream) {
     if (!logits || !entry_sid || !entry_rank || !entry_count || !entry_score || !n_entries || !label_at_rank) return PRAM_ERR_ARG;
-    if (C > RK_MAXC || N > RK_THREADS * 32 || topk <= 0 || max_ranks <= 0) return PRAM_ERR_UNSUPPORTED;
-    rank_landmarks_kernel<<<B, RK_THREADS, 0, stream>>>(logits, keep, N, C, topk, max_ranks, entry_sid, entry_rank,
-                                                       entry_count, entry_score, n_entries, label_at_rank);
+    if (C > RK_MAXC || topk <= 0 || max_ranks <= 0) return PRAM_ERR_UNSUPPORTED;
+    dim3 grid(cdiv((long long)N * 32, 256), B);
+    if (C <= 128) top_classes_kernel<4><<<grid, 256, 0, stream>>>(logits, keep, N, C, max_ranks, label_at_rank);
+    else if (C <= 256) top_classes_kernel<8><<<grid, 256, 0, stream>>>(logits, keep, N, C, max_ranks, label_at_rank);
+    else if (C <= 512) top_classes_kernel<16><<<grid, 256, 0, stream>>>(logits, keep, N, C, max_ranks, label_at_rank);
+    else top_classes_kernel<32><<<grid, 256, 0, stream>>>(logits, keep, N, C, max_ranks, label_at_rank);
+    PRAM_CHECK_LAUNCH();
+    rank_entries_kernel<<<B, RK_THREADS, 0, stream>>>(logits, N, C, topk, max_ranks, entry_sid, entry_rank, entry_count,
+                                                     entry_score, n_entries, label_at_rank);
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
 }

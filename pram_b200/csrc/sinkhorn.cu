@@ -253,7 +253,15 @@ PRAM_API int pram_sinkhorn_match(const float* dist, int B, int M, int N, const f
                                  cudaStream_t stream) {
     if (!dist || !bin_score || !pws || !iws || !fws || !matches0 || !mscores0 || B <= 0 || M <= 0 || N <= 0)
         return PRAM_ERR_ARG;
-    int G = cluster <= 0 ? SK_MAXG : cluster;
+    int G = cluster;
+    if (G <= 0) {
+        // largest cluster that still runs all B problems in ONE wave of CTAs (a second, partial wave costs a full
+        // 20-iteration pass); a single problem keeps the portable maximum of 8 CTAs
+        static int sms = 0;
+        if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+        G = SK_MAXG;
+        while (G > 1 && (long long)B * G > sms) G >>= 1;
+    }
     if (G > SK_MAXG || (G & (G - 1))) return PRAM_ERR_ARG;
     const int ldp = (N + 1 + 3) / 4 * 4;
     int* idx0 = iws;

@@ -188,7 +188,7 @@ class ResNet4x(nn.Module):
     def _trunk_tc(self, image: torch.Tensor, pk, split: int) -> Dict[str, torch.Tensor]:
         """Tensor-core conv stack: tcgen05 implicit GEMMs fed by TMA, activations as split-bf16 NHWC planes
         (phase-split in front of the three stride-2 convolutions); CUDA cores only for conv1a (Cin=3,
-        HBM-bound) and the 32-group 3x3 convolutions (1.6 % of the FLOPs)."""
+        HBM-bound); the 32-group 3x3 convolutions run on warp-level bf16 MMAs (gconv_mma.cu)."""
         b, _, h, w = image.shape
         ct = ops.conv_tc
         T = lambda n: pk[n + '.tc']
@@ -204,8 +204,8 @@ class ResNet4x(nn.Module):
         o3b_bf = cur_bf
         last = None
         for i in range(3):
-            t = ct(cur_bf, T(f'conv4.{i}.c1'), pk[f'conv4.{i}.c1.b'], 1, 1, True, split, want_f32=True, want_bf=False)['f32']
-            t = ops.gconv3x3_split(t, pk[f'conv4.{i}.c2.w'], pk[f'conv4.{i}.c2.b'], True, split)
+            t = ct(cur_bf, T(f'conv4.{i}.c1'), pk[f'conv4.{i}.c1.b'], 1, 1, True, split)['bf']
+            t = ops.gconv3x3_tc(t, pk[f'conv4.{i}.c2.w'], pk[f'conv4.{i}.c2.b'], True, split)
             last = ct(t, T(f'conv4.{i}.c3'), pk[f'conv4.{i}.c3.b'], 1, 1, True, split, res=cur_f32, want_f32=True,
                       want_ps=(i == 2))
             cur_bf, cur_f32 = last['bf'], last['f32']

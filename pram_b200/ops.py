@@ -365,6 +365,15 @@ def gconv3x3_split(x_nhwc: Tensor, w: Tensor, bias: Tensor, relu: bool, split: i
     return out
 
 
+def gconv3x3_tc(x: Split, w: Tensor, bias: Tensor, relu: bool, split: int) -> Split:
+    """Grouped 3x3 conv (groups of 8 channels) on tensor cores: split-bf16 NHWC planes in and out."""
+    b, h, wd, c = x.shape
+    out = empty_split((b, h, wd, c), x.hi.device, with_lo=(split == 3))
+    call('pram_gconv3x3_tc', ptr(x.hi), ptr(x.lo), ptr(w), ptr(bias), ptr(out.hi), ptr(out.lo), b, h, wd, c, int(relu), split,
+         stream_ptr())
+    return out
+
+
 def layernorm_gelu_split(x: Tensor, gamma: Tensor, beta: Tensor, c: int, out: Split, gelu: bool = True):
     rows = x.numel() // c
     call('pram_layernorm_gelu_split', ptr(x), ptr(gamma), ptr(beta), None, ptr(out.hi), ptr(out.lo), rows, c, int(gelu),

@@ -158,3 +158,25 @@ def test_attention_prep_matches_rotary_split(ops, dev):
     vref = v.view(b, h, n, 64).transpose(-1, -2)
     assert torch.allclose(VT.float().view(b, h, 64, n_pad)[..., :n], vref, atol=1e-5, rtol=1e-5)
     assert (VT.float().view(b, h, 64, n_pad)[..., n:] == 0).all()
+
+
+@pytest.mark.parametrize('split', [1, 3])
+@pytest.mark.parametrize('b,h,w', [(2, 16, 64), (1, 30, 40), (3, 9, 33), (1, 120, 160)])
+def test_gconv3x3_tc(ops, dev, split, b, h, w):
+    """32-group 3x3 convolution on warp-level bf16 MMAs (ResBlock.conv2, reference nets/sfd2.py:100-124) vs
+    torch-CPU fp32 grouped conv2d; ragged tiles (h % 8, w % 32 != 0) exercise the zero-filled halo."""
+    c, groups = 256, 32
+    g = torch.Generator().manual_seed(h * w + split)
+    x = torch.randn(b, c, h, w, generator=g)
+    wt = torch.randn(c, 8, 3, 3, generator=g) / 72 ** 0.5
+    bias = torch.randn(c, generator=g)
+    ref = torch.relu(torch.nn.functional.conv2d(x, wt, bias, padding=1, groups=groups))
+    # same packing as ResNet4x.prepare(): [tap][ci][co][group]
+    wp = wt.view(groups, 8, 8, 3, 3).permute(3, 4, 2, 1, 0).reshape(9, 8, 8, groups).contiguous().to(dev)
+    X = ops.split_bf16(x.permute(0, 2, 3, 1).contiguous().to(dev), split == 3)
+    out = ops.gconv3x3_tc(X, wp, bias.to(dev), True, split)
+    torch.cuda.synchronize()
+    assert _relerr(out.float().permute(0, 3, 1, 2).cpu(), ref) < (TOL[split] if split == 3 else 3e-2)
+    # and against the fp32 CUDA-core kernel on the same (quantised) input
+    simt = ops.gconv3x3_f32(X.float(), wp, bias.to(dev), True)
+    assert _relerr(out.float(), simt) < (TOL[split] if split == 3 else 3e-2)
