@@ -383,7 +383,7 @@ def layernorm_gelu_split(x: Tensor, gamma: Tensor, beta: Tensor, c: int, out: Sp
 
 # ---- tensor-core flash attention ---------------------------------------------------------------------
 
-P_SWAP = 0  # debug knob for the bf16 packing order of P inside a TMEM column
+P_SWAP = 0  # reserved ABI argument of pram_attention_tc (former debug knob); must stay 0
 
 
 def attention_prep(qkv: Tensor, nparts: int, b: int, n: int, heads: int, cos: Optional[Tensor], sin: Optional[Tensor],

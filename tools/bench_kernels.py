@@ -107,6 +107,10 @@ bg = torch.randn(256, device=dev)
 report('gconv3x3_kernel (32 groups x 8, 256 ch @120x160)', timeit(lambda: ops.gconv3x3_split(xg, wg, bg, True, 3)),
        nbytes=B * 120 * 160 * 256 * (4 + 4), flops=B * 2.0 * 9 * 8 * 256 * 120 * 160)
 
+xgs = ops.split_bf16(xg, True)
+report('gconv_mma_kernel (32 groups x 8, 256 ch @120x160, bf16x3 mma.sync)', timeit(lambda: ops.gconv3x3_tc(xgs, wg, bg, True, 3)),
+       nbytes=B * 120 * 160 * 256 * (4 + 4), flops=B * 2.0 * 9 * 8 * 256 * 120 * 160)
+
 # ---- score map, NMS, selection --------------------------------------------------------------------------------
 logits = torch.randn(B, H // 8, W // 8, 65, device=dev) * 3
 report('score_map_kernel', timeit(lambda: ops.score_map(logits)), nbytes=B * 4 * (65 * H * W // 64 + H * W))
@@ -150,6 +154,10 @@ report('sample_kernel (mid features 256 ch)', timeit(lambda: ops.sample_features
        nbytes=B * K * 256 * (4 * 4 + 4))
 wr = torch.randn(32, 2, device=dev)
 report('posenc_kernel', timeit(lambda: ops.posenc(kp, W, H, wr)), nbytes=B * K * (8 + 2 * 32 * 4), bound='latency')
+
+lg = torch.randn(B, K, 113, device=dev)
+report('top_classes_kernel + rank_entries_kernel (process_segmentations, 113 classes)', timeit(lambda: ops.rank_landmarks(lg, None, 20, 8)),
+       nbytes=B * K * 113 * 4, bound='latency')
 
 # ---- LayerNorm + GELU -------------------------------------------------------------------------------------------
 xl = torch.randn(B * K, 512, device=dev)
