@@ -155,6 +155,7 @@ typedef struct pram_tc_args {
     int qkv_mode; const float* cosb; const float* sinb; float qk_scale;
     void* q_hi; void* q_lo; void* k_hi; void* k_lo; void* v_hi; void* v_lo;
     int seg_split, seg_n0, seg_n1, heads;
+    int cluster;                          /* 0 = auto, 1 = single CTAs, 2 = 2-CTA clusters, weight tile TMA-multicast */
 } pram_tc_args;
 int pram_gemm_tc(const pram_tc_args* args, pram_stream_t stream);
 

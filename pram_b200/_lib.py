@@ -64,6 +64,7 @@ class TcArgs(C.Structure):
         ('qkv_mode', _I), ('cosb', _P), ('sinb', _P), ('qk_scale', _F),
         ('q_hi', _P), ('q_lo', _P), ('k_hi', _P), ('k_lo', _P), ('v_hi', _P), ('v_lo', _P),
         ('seg_split', _I), ('seg_n0', _I), ('seg_n1', _I), ('heads', _I),
+        ('cluster', _I),
     ]
 
 

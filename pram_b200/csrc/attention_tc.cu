@@ -6,7 +6,7 @@
 //   warp 0  : TMA producer   Q {64 x 128}, K {64 x 128}, V^T {2 x (64 keys x 64 d)} -> SWIZZLE_128B smem
 //   warp 1  : MMA issuer     S = Q K^T  (SS, fp32 in TMEM, double buffered)
 //                            O += P V   (TS: P read from TMEM as the A operand, V^T from smem)
-//   warps 2-9: softmax       one thread per query row and half of the keys: tcgen05.ld S, running max with lazy
+//   warps 2-17: softmax      one thread per query row and a quarter of the keys: tcgen05.ld S, running max with lazy
 //                            rescale of O (only when the max moved by > 8 in log2 units), exp2,
 //                            P packed to bf16 and written back to TMEM with tcgen05.st; epilogue O / l
 // SPLIT=3 keeps ~fp32 accuracy with bf16 tensor-core operands: Q,K,V and P are hi/lo split and each
@@ -18,7 +18,12 @@
 namespace fa {
 
 constexpr int BQ = 128, BKV = 128, HD = 64;
-constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 8 softmax warps
+constexpr int NPART = 4;                       // softmax warps per TMEM lane quarter: each takes BKV / NPART key columns
+constexpr int CPT = BKV / NPART;               // 32 key columns per thread
+constexpr int OPT = HD / NPART;                // 16 O columns per thread (rescale + epilogue)
+constexpr int NUM_SM_WARPS = 4 * NPART;        // 16 softmax warps: 4 per SMSP, so the exp / pack chains of one warp hide
+                                               // the tcgen05.ld / barrier latencies of the others
+constexpr int NUM_THREADS = 64 + 32 * NUM_SM_WARPS;  // TMA warp, MMA warp, softmax warps
 constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_PHI = 256, COL_PLO = 320, COL_O = 384, TMEM_COLS = 512;
 
 struct Args {
@@ -86,18 +91,19 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
 }
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -122,6 +128,23 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -136,7 +159,7 @@ struct Cfg {
     // by the PV MMAs, so K gets 3 stages and is prefetched one tile ahead of V (2 stages)
     static constexpr int K_STAGES = 3, V_STAGES = 2;
     static constexpr int K_STAGE = NPL * K_BYTES, V_STAGE = NPL * V_BYTES;
-    static constexpr int SMEM_BYTES = NPL * Q_BYTES + K_STAGES * K_STAGE + V_STAGES * V_STAGE + 1024 + 256 + 2048 /*row max/sum exchange*/;
+    static constexpr int SMEM_BYTES = NPL * Q_BYTES + K_STAGES * K_STAGE + V_STAGES * V_STAGE + 1024 + 256 + 2 * NPART * 128 * 4 /*row max/sum exchange*/;
     static_assert(SMEM_BYTES <= 227 * 1024, "dynamic shared memory budget of sm_100a exceeded");
 };
 
@@ -174,9 +197,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
         for (int s = 0; s < 3; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-            mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8);
+            mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NUM_SM_WARPS);
         }
-        mbar_init(p_full, 8); mbar_init(o_done, 1);
+        mbar_init(p_full, NUM_SM_WARPS); mbar_init(o_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -238,8 +261,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                 if ((t + 1) % kv_tiles == 0 && t + 1 < n_tiles) load_q((t + 1) / kv_tiles);
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1) {
+        // ===================== MMA issuer (whole warp, one elected lane per instruction; see gemm_tc.cu) =====================
         constexpr uint32_t idesc_s = make_idesc(BQ, BKV);
         const uint32_t idesc_o = make_idesc(BQ, HD) | (p.v_mn ? (1u << 16) : 0u);  // bit 16: B is MN-major
         uint32_t g = 0, w = 0;
@@ -293,43 +316,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
             }
         }
     } else if (warp >= 2) {
-        // ===================== softmax + epilogue (8 warps) =====================
-        // thread <-> query row (TMEM lane); the two warps of a lane quarter split the 128 key columns of a
-        // tile (64 each, held in registers -> single pass over S), exchange their row maxima / row sums
-        // through shared memory, and split the 64 O columns for rescaling and the epilogue.
-        const int qd = warp & 3, half = (warp - 2) >> 2;
+        // ===================== softmax + epilogue (16 warps) =====================
+        // thread <-> query row (TMEM lane) x one quarter of the 128 key columns of a tile (32 scores held in
+        // registers -> single pass over S).  The four warps of a lane quarter exchange their row maxima / row sums
+        // through shared memory and split the 64 O columns for rescaling and the epilogue.
+        const int qd = warp & 3, part = (warp - 2) >> 2;
         const int r = qd * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        float* xch = reinterpret_cast<float*>(tmem_base_s + 4);  // [2 parity][2 half][128 rows]
+        float* xch = reinterpret_cast<float*>(tmem_base_s + 4);  // [2 parity][NPART][128 rows]
         const uint32_t bar_id = 1 + qd;
         uint32_t g = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x) {
             const int bh = item / q_tiles, q0 = (item % q_tiles) * BQ;
-            float m_used = -INFINITY, l = 0.f;  // l: this thread's partial row sum (its 64 columns)
+            float m_used = -INFINITY, l = 0.f;  // l: this thread's partial row sum (its 32 columns)
             for (int j = 0; j < kv_tiles; ++j, ++g) {
                 const int st = g & 1;
-                const uint32_t s_addr = tmem_base + lane_off + (st ? COL_S1 : COL_S0) + half * 64;
-                const int nvalid = min(BKV, p.Nk - j * BKV) - half * 64;  // valid columns of this half (may be <= 0)
+                const uint32_t s_addr = tmem_base + lane_off + (st ? COL_S1 : COL_S0) + part * CPT;
+                const int nvalid = min(BKV, p.Nk - j * BKV) - part * CPT;  // valid columns of this part (may be <= 0)
                 mbar_wait(&s_full[st], (g >> 1) & 1);
                 tc_fence_after();
-                uint32_t v0[32], v1[32];
+                uint32_t v0[32];
                 tmem_ld32(s_addr, v0);
-                tmem_ld32(s_addr + 32, v1);
-                if (nvalid < 64) {  // last, partial tile: mask the tail (warp-uniform branch)
+                if (nvalid < CPT) {  // last, partial tile: mask the tail (warp-uniform branch)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (i >= nvalid) v0[i] = 0xff800000u;       // -inf
-                        if (32 + i >= nvalid) v1[i] = 0xff800000u;
-                    }
+                    for (int i = 0; i < 32; ++i)
+                        if (i >= nvalid) v0[i] = 0xff800000u;  // -inf
                 }
-                float mx = -INFINITY;
+                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+                for (int i = 0; i < 32; i += 4) {
+                    mx4[0] = fmaxf(mx4[0], __uint_as_float(v0[i]));
+                    mx4[1] = fmaxf(mx4[1], __uint_as_float(v0[i + 1]));
+                    mx4[2] = fmaxf(mx4[2], __uint_as_float(v0[i + 2]));
+                    mx4[3] = fmaxf(mx4[3], __uint_as_float(v0[i + 3]));
+                }
+                float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
                 mx *= p.scale_log2;  // scale > 0
-                float* x = xch + (g & 1) * 256;
-                x[half * 128 + r] = mx;
-                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-                mx = fmaxf(x[r], x[128 + r]);
+                float* x = xch + (g & 1) * (NPART * 128);
+                x[part * 128 + r] = mx;
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NPART) : "memory");
+                mx = fmaxf(fmaxf(x[r], x[128 + r]), fmaxf(x[256 + r], x[384 + r]));
                 // lazy rescale: keep the stale reference max unless it moved by more than 8 (log2 units)
                 const bool need = (mx > m_used + 8.f);
                 const bool warp_need = __any_sync(0xffffffffu, need) || (j == 0);
@@ -340,79 +366,70 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                     m_used = m_new;
                     l *= corr;
                 }
-                // p = exp2(s*scale - m) for this thread's 64 columns, packed to bf16 hi / lo
-                uint32_t ph[32], pl[32];
-                float lsum = 0.f;
+                // p = exp2(s*scale - m) for this thread's 32 columns, packed to bf16 hi / lo
+                uint32_t ph[16], pl[16];
+                float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    float p0, p1, p2, p3;
+                    float p0, p1;
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v0[i]), p.scale_log2, -m_used)));
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v0[i + 1]), p.scale_log2, -m_used)));
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p2) : "f"(fmaf(__uint_as_float(v1[i]), p.scale_log2, -m_used)));
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p3) : "f"(fmaf(__uint_as_float(v1[i + 1]), p.scale_log2, -m_used)));
-                    lsum += (p0 + p1) + (p2 + p3);
+                    ls0 += p0; ls1 += p1;
                     __nv_bfloat162 ha = __floats2bfloat162_rn(p0, p1);
-                    __nv_bfloat162 hb = __floats2bfloat162_rn(p2, p3);
-                    const uint32_t ua = *reinterpret_cast<uint32_t*>(&ha), ub = *reinterpret_cast<uint32_t*>(&hb);
+                    const uint32_t ua = *reinterpret_cast<uint32_t*>(&ha);
                     ph[i >> 1] = ua;
-                    ph[16 + (i >> 1)] = ub;
                     if (SPLIT == 3) {
-                        const float a_lo = p0 - __uint_as_float(ua << 16);
-                        const float a_hi = p1 - __uint_as_float(ua & 0xffff0000u);
-                        const float b_lo = p2 - __uint_as_float(ub << 16);
-                        const float b_hi = p3 - __uint_as_float(ub & 0xffff0000u);
-                        __nv_bfloat162 la = __floats2bfloat162_rn(a_lo, a_hi), lb = __floats2bfloat162_rn(b_lo, b_hi);
+                        __nv_bfloat162 la = __floats2bfloat162_rn(p0 - __uint_as_float(ua << 16), p1 - __uint_as_float(ua & 0xffff0000u));
                         pl[i >> 1] = *reinterpret_cast<uint32_t*>(&la);
-                        pl[16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&lb);
                     }
                 }
-                l += lsum;
+                l += ls0 + ls1;
                 // P (and O) may be touched only after the previous PV retired
                 if (j > 0) {
                     mbar_wait(o_done, (g - 1) & 1);
                     tc_fence_after();
                     if (warp_need) {
-                        const uint32_t o_addr = tmem_base + lane_off + COL_O + half * 32;
-                        uint32_t o[32];
-                        tmem_ld32(o_addr, o);
+                        const uint32_t o_addr = tmem_base + lane_off + COL_O + part * OPT;
+                        uint32_t o[16];
+                        tmem_ld16(o_addr, o);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-                        tmem_st32(o_addr, o);
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+                        tmem_st16(o_addr, o);
                     }
                 }
-                tmem_st32(tmem_base + lane_off + COL_PHI + half * 32, ph);
-                if (SPLIT == 3) tmem_st32(tmem_base + lane_off + COL_PLO + half * 32, pl);
+                tmem_st16(tmem_base + lane_off + COL_PHI + part * (CPT / 2), ph);
+                if (SPLIT == 3) tmem_st16(tmem_base + lane_off + COL_PLO + part * (CPT / 2), pl);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&s_empty[st]); mbar_arrive(p_full); }
             }
-            // epilogue: O / l (row sum = both halves), each warp stores 32 of the 64 head dims
-            float* x = xch + (g & 1) * 256;
-            x[half * 128 + r] = l;
-            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-            const float inv = 1.f / (x[r] + x[128 + r]);
+            // epilogue: O / l (row sum over the four parts), each warp stores 16 of the 64 head dims
+            float* x = xch + (g & 1) * (NPART * 128);
+            x[part * 128 + r] = l;
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NPART) : "memory");
+            const float inv = 1.f / ((x[r] + x[128 + r]) + (x[256 + r] + x[384 + r]));
             mbar_wait(o_done, (g - 1) & 1);
             tc_fence_after();
             const int qn = q0 + r;
             const int b = bh / p.heads, hh = bh - b * p.heads;
-            const long long orow = ((long long)b * p.Nq + qn) * p.out_ld + hh * HD + half * 32;
+            const long long orow = ((long long)b * p.Nq + qn) * p.out_ld + hh * HD + part * OPT;
             {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + lane_off + COL_O + half * 32, v);
+                uint32_t v[16];
+                tmem_ld16(tmem_base + lane_off + COL_O + part * OPT, v);
                 if (qn < p.Nq) {
-                    float f[32];
+                    float f[16];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * inv;
+                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * inv;
                     if (p.out_f32) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
+                        for (int i = 0; i < 16; i += 4)
                             *reinterpret_cast<float4*>(p.out_f32 + orow + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
                     }
                     if (p.out_hi) {
-                        uint32_t hi[16], lo[16];
+                        uint32_t hi[8], lo[8];
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
+                        for (int i = 0; i < 16; i += 2) {
                             __nv_bfloat162 h2 = __floats2bfloat162_rn(f[i], f[i + 1]);
                             const uint32_t u = *reinterpret_cast<uint32_t*>(&h2);
                             hi[i >> 1] = u;
@@ -421,18 +438,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                         }
                         uint4* oh = reinterpret_cast<uint4*>(p.out_hi + orow);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                        for (int i = 0; i < 2; ++i) oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
                         if (p.out_lo) {
                             uint4* ol = reinterpret_cast<uint4*>(p.out_lo + orow);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                            for (int i = 0; i < 2; ++i) ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
                         }
                     }
                 }
             }
             tc_fence_before();  // O reads ordered before the next item's first PV (gated by p_full)
-            // the partner must have read this item's row sums before the exchange slot is reused
-            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            // the partners must have read this item's row sums before the exchange slot is reused
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NPART) : "memory");
         }
     }
     tc_fence_before();

@@ -95,6 +95,21 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// multicast variants for 2-CTA clusters: the box lands at the same CTA-relative offset in every CTA of `mask`
+// and completes bytes on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6}], [%2], %3;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -113,14 +128,25 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// The MMA-issuing WARP runs its loops convergently and elects one lane per instruction (elect.sync): operands that
+// are warp-uniform then stay in uniform registers and each MMA costs a handful of uniform-datapath instructions.
+// Issued from inside an `if (lane == 0)` region instead, the compiler wraps every tcgen05.mma in an
+// elect / R2UR / branch loop (~10 dependent instructions, ~100 cycles per MMA -- measured with ncu: the issue
+// thread, not the tensor pipe, bounded every kernel whose MMAs are shorter than that).
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -166,7 +192,12 @@ struct Cfg {
 };
 
 // MODE (epilogue specialisation, keeps registers down): 0 plain, 1 residual add, 2 fused attention operands
-template <int BN, int SPLIT, int MODE>
+// CL = 2: the kernel runs as 2-CTA clusters.  The pair works on two neighbouring M tiles of the SAME N tile, so the
+// weight tile is identical for both: each CTA fetches one half of it (BN/2 rows) and TMA-multicasts it into both
+// shared memories -- per-CTA L2->SM operand traffic drops from A + W to A + W/2 (the kernel is L2-bandwidth bound:
+// 96 KB per k-block at bf16x3 / BN = 256).  A stage of a CTA is written by the peer too, so the "slot free" barrier
+// collects the MMA commits of BOTH CTAs (tcgen05.commit.multicast).
+template <int BN, int SPLIT, int MODE, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
     const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const Args p) {
@@ -185,14 +216,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
     const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int m_tiles = p.B * tiles_y * tiles_x;
-    const int total = m_tiles * n_tiles;
+    const int crank = (CL == 2) ? (int)cluster_ctarank() : 0;
+    const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;          // cluster index / number of clusters
+    const int total = ((m_tiles + CL - 1) / CL) * n_tiles;           // work items per cluster: (M-tile group, N tile)
     const int num_kb = p.ntaps * p.kblocks;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_a_hi);
         prefetch_tmap(&map_w_hi);
         if (SPLIT == 3) { prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_lo); }
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -203,14 +236,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
 
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
         int stage = 0; uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-            const int nt = tile % n_tiles, mt = tile / n_tiles;
+        for (int tile = cid; tile < total; tile += ncl) {
+            const int nt = tile % n_tiles, mt = (tile / n_tiles) * CL + crank;  // mt >= m_tiles: all-zero A (OOB fill)
             const int txi = mt % tiles_x, tyi = (mt / tiles_x) % tiles_y, b = mt / (tiles_x * tiles_y);
             const int x0 = txi * TW, y0 = tyi * TH, n0 = nt * BN;
             for (int kb = 0; kb < num_kb; ++kb) {
@@ -222,20 +256,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                 const int ap = b * p.planes_per_image + p.tap_plane[tap];
                 const int wp = tap + b * p.w_batch_mult;
                 tma_load_4d(st, &map_a_hi, &full[stage], kc * BK, ax, ay, ap);
-                tma_load_3d(st + C::NPLANES * C::A_BYTES, &map_w_hi, &full[stage], kc * BK, n0, wp);
-                if (SPLIT == 3) {
-                    tma_load_4d(st + C::A_BYTES, &map_a_lo, &full[stage], kc * BK, ax, ay, ap);
-                    tma_load_3d(st + 2 * C::A_BYTES + C::B_BYTES, &map_w_lo, &full[stage], kc * BK, n0, wp);
+                if (SPLIT == 3) tma_load_4d(st + C::A_BYTES, &map_a_lo, &full[stage], kc * BK, ax, ay, ap);
+                if (CL == 1) {
+                    tma_load_3d(st + C::NPLANES * C::A_BYTES, &map_w_hi, &full[stage], kc * BK, n0, wp);
+                    if (SPLIT == 3) tma_load_3d(st + 2 * C::A_BYTES + C::B_BYTES, &map_w_lo, &full[stage], kc * BK, n0, wp);
+                } else {  // this CTA's half of the weight tile, multicast into both CTAs of the pair
+                    const int hb = crank * (C::B_BYTES / 2), hn = n0 + crank * (BN / 2);
+                    tma_load_3d_mc(st + C::NPLANES * C::A_BYTES + hb, &map_w_hi, &full[stage], kc * BK, hn, wp, (uint16_t)3);
+                    if (SPLIT == 3)
+                        tma_load_3d_mc(st + 2 * C::A_BYTES + C::B_BYTES + hb, &map_w_lo, &full[stage], kc * BK, hn, wp, (uint16_t)3);
                 }
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1) {
+        // ===================== MMA issuer (whole warp, one elected lane per instruction) =====================
         constexpr uint32_t idesc = make_idesc(BM, BN);
         int stage = 0; uint32_t phase = 0;
         int as = 0; uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        for (int tile = cid; tile < total; tile += ncl) {
             mbar_wait(&tempty[as], aphase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -254,7 +293,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                         umma(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), idesc, 1);
                     }
                 }
-                umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+                // frees the smem slot when these MMAs retire (in both CTAs of a pair: the peer writes half of W here)
+                if (CL == 1) umma_commit(&empty[stage]);
+                else umma_commit_mc(&empty[stage], (uint16_t)3);
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
             umma_commit(&tfull[as]);  // accumulator ready for the epilogue
@@ -279,13 +320,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
         const int g1 = lane >> 3, col1 = (lane & 7) * 4;   // pass-1 mapping
         const int g2 = lane >> 2, col2 = (lane & 3) * 8;   // pass-2 mapping
         int as = 0; uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-            const int nt = tile % n_tiles, mt = tile / n_tiles;
+        for (int tile = cid; tile < total; tile += ncl) {
+            const int nt = tile % n_tiles, mt = (tile / n_tiles) * CL + crank;
             const int txi = mt % tiles_x, tyi = (mt / tiles_x) % tiles_y, b = mt / (tiles_x * tiles_y);
             const int n0 = nt * BN;
             if (half == 0) {
                 const int y = tyi * TH + (r >> p.tw_log2), x = txi * TW + (r & (TW - 1));
-                const bool valid = (y < p.Ho) && (x < p.Wo);
+                const bool valid = (y < p.Ho) && (x < p.Wo) && (mt < m_tiles);
                 const int Hp = (p.Ho + 1) >> 1, Wp = (p.Wo + 1) >> 1;
                 eq.pix[lane] = valid ? (int)(((long long)b * p.Ho + y) * p.Wo + x) : -1;
                 eq.pix_ps[lane] = (int)((((long long)(b * 4 + (y & 1) * 2 + (x & 1))) * Hp + (y >> 1)) * Wp + (x >> 1));
@@ -486,6 +527,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();  // no CTA exits while the peer may still multicast into it / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS));
@@ -523,31 +565,53 @@ static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
 
 static int g_num_sms = 0;
 
-template <int BN, int SPLIT, int MODE>
+template <int BN, int SPLIT, int MODE, int CL>
 static int launch_mode(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
-                       const Args& a, int total_tiles, cudaStream_t stream) {
+                       const Args& a, int m_tiles, int n_tiles, cudaStream_t stream) {
     using C = Cfg<BN, SPLIT>;
-    auto kern = gemm_tc_kernel<BN, SPLIT, MODE>;
+    auto kern = gemm_tc_kernel<BN, SPLIT, MODE, CL>;
     static bool attr = false;
+    static int max_clusters = 0;
     if (!attr) {
         PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr = true;
     }
-    int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
-    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ah, al, wh, wl, a);
+    const int items = ((m_tiles + CL - 1) / CL) * n_tiles;
+    if (CL == 1) {
+        int grid = items < g_num_sms ? items : g_num_sms;
+        kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ah, al, wh, wl, a);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cfg.stream = stream;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (!max_clusters) {
+            cfg.gridDim = dim3(g_num_sms / CL * CL, 1, 1);
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = g_num_sms / CL; }
+            max_clusters = n;
+        }
+        const int ncl = items < max_clusters ? items : max_clusters;
+        cfg.gridDim = dim3(ncl * CL, 1, 1);
+        PRAM_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, wh, wl, a));
+    }
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
 }
 
-template <int BN, int SPLIT>
+template <int BN, int SPLIT, int CL>
 static int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
-                  const Args& a, int total_tiles, cudaStream_t stream) {
+                  const Args& a, int m_tiles, int n_tiles, cudaStream_t stream) {
     if (a.qkv_mode) {
-        if constexpr (BN == 256) return launch_mode<BN, SPLIT, 2>(ah, al, wh, wl, a, total_tiles, stream);
+        if constexpr (BN == 256) return launch_mode<BN, SPLIT, 2, CL>(ah, al, wh, wl, a, m_tiles, n_tiles, stream);
         else return PRAM_ERR_UNSUPPORTED;
     }
-    if (a.res) return launch_mode<BN, SPLIT, 1>(ah, al, wh, wl, a, total_tiles, stream);
-    return launch_mode<BN, SPLIT, 0>(ah, al, wh, wl, a, total_tiles, stream);
+    if (a.res) return launch_mode<BN, SPLIT, 1, CL>(ah, al, wh, wl, a, m_tiles, n_tiles, stream);
+    return launch_mode<BN, SPLIT, 0, CL>(ah, al, wh, wl, a, m_tiles, n_tiles, stream);
 }
 
 }  // namespace tc
@@ -576,6 +640,7 @@ struct pram_tc_args {
     int qkv_mode; const float* cosb; const float* sinb; float qk_scale;
     void* q_hi; void* q_lo; void* k_hi; void* k_lo; void* v_hi; void* v_lo;
     int seg_split, seg_n0, seg_n1, heads;
+    int cluster;                          // 0 = auto, 1 = single CTAs, 2 = 2-CTA clusters with a multicast weight tile
 };
 
 PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
@@ -596,6 +661,12 @@ PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
     const int TW = 1 << a->tw_log2, TH = BM >> a->tw_log2;
     if (TW > 256 || TH < 1) return PRAM_ERR_ARG;
 
+    // 2-CTA clusters with a multicast weight tile: shared weights (no per-batch weight planes), at least one full
+    // wave of tiles, and a weight tile whose halves are whole swizzle atoms
+    const int tiles_x = (a->Wo + TW - 1) / TW, tiles_y = (a->Ho + TH - 1) / TH;
+    const int m_tiles = a->B * tiles_x * tiles_y, n_tiles = (a->N + bn - 1) / bn;
+    int cl = 1;  // measured on B200 (profiles/README.md): no gain from the multicast pair -- the kernel is tensor-issue bound, not L2 bound
+    if (a->cluster == 1 || a->cluster == 2) cl = (a->w_batch_mult == 0 && bn >= 128) ? a->cluster : 1;
     CUtensorMap ah, al, wh, wl;
     {
         cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->in_W, (cuuint64_t)a->in_H, (cuuint64_t)a->in_planes};
@@ -610,7 +681,7 @@ PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
     {
         cuuint64_t dims[3] = {(cuuint64_t)a->Cin, (cuuint64_t)a->N, (cuuint64_t)a->w_planes};
         cuuint64_t str[2] = {(cuuint64_t)a->Cin * 2, (cuuint64_t)a->Cin * 2 * a->N};
-        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 1};
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(bn / cl), 1};
         int rc = encode(&wh, a->w_hi, 3, dims, str, box);
         if (rc) return rc;
         rc = encode(&wl, a->w_lo ? a->w_lo : a->w_hi, 3, dims, str, box);
@@ -636,16 +707,14 @@ PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
         if ((a->qkv_mode == 1 && (a->N != 768 || !a->k_hi || !a->cosb || !a->sinb)) || (a->qkv_mode == 2 && a->N != 512)) return PRAM_ERR_ARG;
         if (a->seg_n0 <= 0 || a->seg_n1 <= 0) return PRAM_ERR_ARG;
     }
-    const int tiles_x = (a->Wo + TW - 1) / TW, tiles_y = (a->Ho + TH - 1) / TH;
-    const int total = a->B * tiles_x * tiles_y * ((a->N + bn - 1) / bn);
     if (a->split == 3) {
-        if (bn == 256) return launch<256, 3>(ah, al, wh, wl, k, total, stream);
-        if (bn == 128) return launch<128, 3>(ah, al, wh, wl, k, total, stream);
-        return launch<64, 3>(ah, al, wh, wl, k, total, stream);
+        if (bn == 256) return cl == 2 ? launch<256, 3, 2>(ah, al, wh, wl, k, m_tiles, n_tiles, stream) : launch<256, 3, 1>(ah, al, wh, wl, k, m_tiles, n_tiles, stream);
+        if (bn == 128) return cl == 2 ? launch<128, 3, 2>(ah, al, wh, wl, k, m_tiles, n_tiles, stream) : launch<128, 3, 1>(ah, al, wh, wl, k, m_tiles, n_tiles, stream);
+        return launch<64, 3, 1>(ah, al, wh, wl, k, m_tiles, n_tiles, stream);
     }
-    if (bn == 256) return launch<256, 1>(ah, al, wh, wl, k, total, stream);
-    if (bn == 128) return launch<128, 1>(ah, al, wh, wl, k, total, stream);
-    return launch<64, 1>(ah, al, wh, wl, k, total, stream);
+    if (bn == 256) return cl == 2 ? launch<256, 1, 2>(ah, al, wh, wl, k, m_tiles, n_tiles, stream) : launch<256, 1, 1>(ah, al, wh, wl, k, m_tiles, n_tiles, stream);
+    if (bn == 128) return cl == 2 ? launch<128, 1, 2>(ah, al, wh, wl, k, m_tiles, n_tiles, stream) : launch<128, 1, 1>(ah, al, wh, wl, k, m_tiles, n_tiles, stream);
+    return launch<64, 1, 1>(ah, al, wh, wl, k, m_tiles, n_tiles, stream);
 }
 
 // fp32 -> split bf16 planes (hi = bf16(x), lo = bf16(x - hi)); used for weights (once) and for tensors

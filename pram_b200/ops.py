@@ -252,6 +252,8 @@ def empty_split(shape, device, with_lo: bool = True, zero: bool = False) -> Spli
     return Split(hi, mk(shape, device=device, dtype=torch.bfloat16) if with_lo else None)
 
 
+import os as _os
+GEMM_CLUSTER = int(_os.environ.get('PRAM_GEMM_CLUSTER', '0'))  # 0 = auto; 1 / 2 force single CTAs / 2-CTA clusters (tests, A/B timing)
 _S1_TAPS = [(dy, dx, 0) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
 # stride 2 on a 2x2 phase-split input: tap r in {0,1,2} reads phase (1,0,1) at offset (-1,0,0)
 _PH = ((1, -1), (0, 0), (1, 0))
@@ -293,6 +295,7 @@ def gemm_tc(a: Split, a_ld: int, in_w: int, in_h: int, in_planes: int, cin: int,
                 setattr(A, name + '_hi', sp.hi.data_ptr())
                 setattr(A, name + '_lo', sp.lo.data_ptr() if sp.lo is not None else None)
         A.seg_split, A.seg_n0, A.seg_n1 = qkv['seg_split'], qkv['seg_n0'], qkv['seg_n1']
+    A.cluster = GEMM_CLUSTER
     import ctypes
     call('pram_gemm_tc', ctypes.byref(A), stream_ptr())
 

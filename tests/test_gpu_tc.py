@@ -173,3 +173,49 @@ def test_gconv3x3_tc(ops, dev, split, b, h, w):
     # and against the fp32 CUDA-core kernel on the same (quantised) input
     simt = ops.gconv3x3_f32(X.float(), wp, bias.to(dev), True)
     assert _relerr(out.float(), simt) < (TOL[split] if split == 3 else 3e-2)
+
+
+@pytest.mark.parametrize('case', ['conv', 'linear', 'linear_odd', 'qkv'])
+def test_gemm_cluster_multicast_bit_identical(ops, dev, case):
+    """2-CTA clusters with the weight tile TMA-multicast to both CTAs must give bit-identical results to the
+    single-CTA schedule (same MMA order per tile), including an odd number of M tiles (one CTA of the last pair idles
+    on an all-zero, out-of-bounds A tile) and the fused qkv epilogue."""
+    g = torch.Generator().manual_seed(7)
+    outs = {}
+    for cl in (1, 2):
+        ops.GEMM_CLUSTER = cl
+        try:
+            if case == 'conv':
+                x = torch.randn(2, 40, 48, 128, generator=g.manual_seed(1))
+                wt = torch.randn(9, 256, 128, generator=g) * 0.03
+                X, Wp = ops.split_bf16(x.to(dev), True), ops.split_bf16(wt.to(dev), True)
+                o = ops.conv_tc(X, Wp, torch.ones(256, device=dev), 3, 1, True, 3, want_f32=True, want_ps=True)
+                outs[cl] = [o['f32'], o['bf'].hi, o['bf'].lo, o['ps'].hi]
+            elif case in ('linear', 'linear_odd'):
+                rows = 4096 if case == 'linear' else 128 * 37 + 5  # 38 M tiles (even) / ragged last tile + odd handling
+                rows = rows if case == 'linear' else 128 * 36 + 5   # 37 M tiles: odd
+                a = torch.randn(rows, 512, generator=g.manual_seed(2))
+                w = torch.randn(384, 512, generator=g) * 0.05
+                res = torch.randn(rows, 384, generator=g)
+                A, Wt = ops.split_bf16(a.to(dev), True), ops.split_bf16(w.to(dev), True)
+                of = torch.zeros(rows, 384, device=dev)
+                ob = ops.empty_split((rows, 384), dev, True, zero=True)
+                ops.linear_tc(A, 512, rows, 512, Wt, 384, torch.ones(384, device=dev), res.to(dev), 384, False, of, 384, ob, 384, split=3)
+                outs[cl] = [of, ob.hi, ob.lo]
+            else:
+                b, n = 3, 700
+                T = b * n
+                a = torch.randn(T, 256, generator=g.manual_seed(3))
+                w = torch.randn(768, 256, generator=g) * 0.05
+                cos, sin = torch.rand(T, 32, generator=g), torch.rand(T, 32, generator=g)
+                A, Wt = ops.split_bf16(a.to(dev), True), ops.split_bf16(w.to(dev), True)
+                q, k, v = (ops.empty_split((T, 256), dev, True, zero=True) for _ in range(3))
+                qkv = {'mode': 1, 'scale': 1.0, 'cos': cos.to(dev), 'sin': sin.to(dev), 'q': q, 'k': k, 'v': v,
+                       'seg_split': T, 'seg_n0': n, 'seg_n1': n}
+                ops.linear_tc(A, 256, T, 256, Wt, 768, torch.ones(768, device=dev), split=3, bn=256, qkv=qkv)
+                outs[cl] = [q.hi, q.lo, k.hi, k.lo, v.hi, v.lo]
+            torch.cuda.synchronize()
+        finally:
+            ops.GEMM_CLUSTER = 0
+    for t1, t2 in zip(outs[1], outs[2]):
+        assert torch.equal(t1, t2)
