@@ -8,7 +8,7 @@
 //                            O += P V   (TS: P read from TMEM as the A operand, V^T from smem)
 //   warps 2-17: softmax      one thread per query row and a quarter of the keys: tcgen05.ld S, running max with lazy
 //                            rescale of O (only when the max moved by > 8 in log2 units), exp2,
-//                            P packed to bf16 and written back to TMEM with tcgen05.st; epilogue O / l
+//                            P packed to bf16 and written back to TMEM (over S, in place) with tcgen05.st; epilogue O / l
 // SPLIT=3 keeps ~fp32 accuracy with bf16 tensor-core operands: Q,K,V and P are hi/lo split and each
 // product is three MMAs (hi*hi + lo*hi + hi*lo) into the same fp32 accumulator.
 #include "common.cuh"
@@ -24,7 +24,11 @@ constexpr int OPT = HD / NPART;                // 16 O columns per thread (resca
 constexpr int NUM_SM_WARPS = 4 * NPART;        // 16 softmax warps: 4 per SMSP, so the exp / pack chains of one warp hide
                                                // the tcgen05.ld / barrier latencies of the others
 constexpr int NUM_THREADS = 64 + 32 * NUM_SM_WARPS;  // TMA warp, MMA warp, softmax warps
-constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_PHI = 256, COL_PLO = 320, COL_O = 384, TMEM_COLS = 512;
+// TMEM: two S buffers (128 fp32 columns each) and O.  P(g) is written IN PLACE over S(g) (bf16 hi plane in columns
+// [0,64) of the buffer, lo plane in [64,128)) once every warp of the lane quarter holds its scores in registers, so P
+// is double-buffered for free: softmax(g+1) never waits for PV(g), and the tensor pipe's in-order execution
+// (PV(g) is issued before S(g+2)) is the only "buffer free" signal an S buffer needs.
+constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_O = 256, TMEM_COLS = 512;
 
 struct Args {
     int BH, heads, Nq, Nk;
@@ -181,10 +185,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
     uint64_t* k_empty = bars + 5;   // [3]
     uint64_t* v_full = bars + 8;    // [2]
     uint64_t* v_empty = bars + 10;  // [2]
-    uint64_t* s_full = bars + 12;   // [2]
-    uint64_t* s_empty = bars + 14;  // [2]
-    uint64_t* p_full = bars + 16;
-    uint64_t* o_done = bars + 17;
+    uint64_t* s_full = bars + 12;   // [2]  S(g) accumulated
+    uint64_t* p_full = bars + 14;   // [2]  P(g) stored by all softmax warps
+    uint64_t* o_done = bars + 16;   // [2]  PV(g) retired
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -197,9 +200,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
         for (int s = 0; s < 3; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-            mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NUM_SM_WARPS);
+            mbar_init(&s_full[s], 1); mbar_init(&p_full[s], NUM_SM_WARPS); mbar_init(&o_done[s], 1);
         }
-        mbar_init(p_full, NUM_SM_WARPS); mbar_init(o_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -270,7 +272,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
         auto issue_S = [&](uint32_t gg) {
             const int st = gg & 1, kst = gg % C::K_STAGES;
             mbar_wait(&k_full[kst], (gg / C::K_STAGES) & 1);
-            mbar_wait(&s_empty[st], ((gg >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t k_hi = smem_u32(k_s + kst * C::K_STAGE), k_lo = k_hi + C::K_BYTES;
             const uint32_t d = tmem_base + (st ? COL_S1 : COL_S0);
@@ -289,21 +290,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++w) {
             mbar_wait(q_full, w & 1);
             tc_fence_after();
+            // S runs two tiles ahead of PV.  S(g) reuses the buffer of tile g-2, whose PV was issued earlier: in-order
+            // execution of the tensor pipe orders the overwrite after PV(g-2) has read P(g-2) from it.
             issue_S(g);
+            if (kv_tiles > 1) issue_S(g + 1);
+            if (kv_tiles <= 2) umma_commit(q_empty);  // every S MMA of this item has been issued: Q frees when they retire
             for (int j = 0; j < kv_tiles; ++j, ++g) {
-                if (j + 1 < kv_tiles) issue_S(g + 1);
-                else umma_commit(q_empty);  // every S MMA of this item has been issued: Q slot frees when they retire
-                mbar_wait(p_full, g & 1);
-                tc_fence_after();
                 const int st = g & 1;
+                mbar_wait(&p_full[st], (g >> 1) & 1);
                 mbar_wait(&v_full[st], (g >> 1) & 1);
                 tc_fence_after();
                 const uint32_t v_hi = smem_u32(v_s + st * C::V_STAGE), v_lo = v_hi + C::V_BYTES;
                 const uint32_t d = tmem_base + COL_O;
+                const uint32_t p_col = tmem_base + (st ? COL_S1 : COL_S0);
 #pragma unroll
                 for (int ks = 0; ks < BKV / 16; ++ks) {
                     const uint32_t vo = p.v_mn ? ks * 2048 : (ks >> 2) * (C::V_BYTES / 2) + (ks & 3) * 32;
-                    const uint32_t a_hi = tmem_base + COL_PHI + ks * 8, a_lo = tmem_base + COL_PLO + ks * 8;
+                    const uint32_t a_hi = p_col + ks * 8, a_lo = p_col + 64 + ks * 8;
                     const uint64_t bh_d = p.v_mn ? make_desc_mn(v_hi + vo) : make_desc(v_hi + vo);
                     umma_ts(d, a_hi, bh_d, idesc_o, (j | ks) != 0);
                     if (SPLIT == 3) {
@@ -312,7 +315,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                     }
                 }
                 umma_commit(&v_empty[st]);
-                umma_commit(o_done);
+                umma_commit(&o_done[st]);
+                if (j + 2 < kv_tiles) {
+                    issue_S(g + 2);
+                    if (j + 3 == kv_tiles) umma_commit(q_empty);
+                }
             }
         }
     } else if (warp >= 2) {
@@ -384,32 +391,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                     }
                 }
                 l += ls0 + ls1;
-                // P (and O) may be touched only after the previous PV retired
-                if (j > 0) {
-                    mbar_wait(o_done, (g - 1) & 1);
+                // O may be touched only after the previous PV retired (rare: the reference max moved by > 2^8)
+                if (j > 0 && warp_need) {
+                    mbar_wait(&o_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
                     tc_fence_after();
-                    if (warp_need) {
-                        const uint32_t o_addr = tmem_base + lane_off + COL_O + part * OPT;
-                        uint32_t o[16];
-                        tmem_ld16(o_addr, o);
+                    const uint32_t o_addr = tmem_base + lane_off + COL_O + part * OPT;
+                    uint32_t o[16];
+                    tmem_ld16(o_addr, o);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-                        tmem_st16(o_addr, o);
-                    }
+                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+                    tmem_st16(o_addr, o);
                 }
-                tmem_st16(tmem_base + lane_off + COL_PHI + part * (CPT / 2), ph);
-                if (SPLIT == 3) tmem_st16(tmem_base + lane_off + COL_PLO + part * (CPT / 2), pl);
+                // P over S, in place: all four warps of this lane quarter loaded their scores before the bar.sync above
+                const uint32_t p_addr = tmem_base + lane_off + (st ? COL_S1 : COL_S0) + part * (CPT / 2);
+                tmem_st16(p_addr, ph);
+                if (SPLIT == 3) tmem_st16(p_addr + 64, pl);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&s_empty[st]); mbar_arrive(p_full); }
+                if (lane == 0) mbar_arrive(&p_full[st]);
             }
             // epilogue: O / l (row sum over the four parts), each warp stores 16 of the 64 head dims
             float* x = xch + (g & 1) * (NPART * 128);
             x[part * 128 + r] = l;
             asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NPART) : "memory");
             const float inv = 1.f / ((x[r] + x[128 + r]) + (x[256 + r] + x[384 + r]));
-            mbar_wait(o_done, (g - 1) & 1);
+            mbar_wait(&o_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
             tc_fence_after();
             const int qn = q0 + r;
             const int b = bh / p.heads, hh = bh - b * p.heads;
