@@ -76,10 +76,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // bounded wait: a protocol bug must trap, never hang the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    // try_wait suspends the thread for a hardware-bounded time per call; the spin counter (2 instructions per poll
+    // instead of a 64-bit clock comparison) turns a protocol bug into a trap after seconds instead of a hang
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {
+        if (++spins > (1u << 28)) {
             printf("pram gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();
         }

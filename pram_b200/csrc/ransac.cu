@@ -218,6 +218,7 @@ __global__ void compact_matches_kernel(const float* __restrict__ kpts, const lon
 struct HypBest { int count; double res; rs::Pose pose; };
 
 constexpr int HYP_THREADS = 128;
+constexpr int HYP_CHUNK = 1024;  // correspondences staged per pass (20 KB of shared memory)
 
 __global__ void __launch_bounds__(HYP_THREADS) ransac_hyp_kernel(const double* __restrict__ corr, const int* __restrict__ count,
                                                                  int cap, double thr2, unsigned int seed,
@@ -231,6 +232,9 @@ __global__ void __launch_bounds__(HYP_THREADS) ransac_hyp_kernel(const double* _
     rs::Pose best_pose;
     for (int i = 0; i < 9; ++i) best_pose.R[i] = (i % 4 == 0);
     best_pose.t[0] = best_pose.t[1] = best_pose.t[2] = 0;
+    rs::Pose sol[4];
+    int ns = 0;
+    __shared__ float s_pts[HYP_CHUNK * 5];
     if (m >= 3) {
         // three distinct indices from a counter-based hash
         unsigned int h = rs::hash32(seed ^ rs::hash32((unsigned)b * 0x9e3779b9u + (unsigned)hyp));
@@ -248,18 +252,50 @@ __global__ void __launch_bounds__(HYP_THREADS) ransac_hyp_kernel(const double* _
             const double* c = C + (long long)idx[k] * 5;
             x[k][0] = c[0]; x[k][1] = c[1]; X[k][0] = c[2]; X[k][1] = c[3]; X[k][2] = c[4];
         }
-        rs::Pose sol[4];
-        const int ns = rs::p3p(x, X, sol);
-        for (int s = 0; s < ns; ++s) {
-            int cnt = 0;
-            double res = 0;
-            for (int i = 0; i < m; ++i) {
-                const double e = rs::reproj_err2(sol[s], C + (long long)i * 5);
-                if (e <= thr2) { ++cnt; res += e; }
+        ns = rs::p3p(x, X, sol);
+    }
+    // Scoring: every solution against all correspondences.  The correspondences are staged in shared memory as
+    // fp32 (one broadcast read feeds all 128 hypotheses of the block) and the inlier test is division-free:
+    //   |x_c/z_c - x|^2 <= thr^2   <=>   (x_c - x z_c)^2 + (y_c - y z_c)^2 <= thr^2 z_c^2,   z_c > 0
+    // fp32 only RANKS hypotheses; the winner is re-scored, locally optimised and refined in fp64 by the finalize
+    // kernel, which also produces the inlier mask.
+    float Rf[4][12];
+    int cnt[4] = {0, 0, 0, 0};
+    float res[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int sidx = 0; sidx < 4; ++sidx)
+#pragma unroll
+        for (int k = 0; k < 12; ++k) Rf[sidx][k] = (sidx < ns) ? (float)(k < 9 ? sol[sidx].R[k] : sol[sidx].t[k - 9]) : 0.f;
+    const float thr2f = (float)thr2;
+    for (int c0 = 0; c0 < m; c0 += HYP_CHUNK) {
+        const int nc = min(HYP_CHUNK, m - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nc * 5; i += HYP_THREADS) s_pts[i] = (float)C[(long long)c0 * 5 + i];
+        __syncthreads();
+#pragma unroll
+        for (int sidx = 0; sidx < 4; ++sidx) {
+            if (sidx >= ns) break;
+            const float* R = Rf[sidx];
+            int c = 0;
+            float rs_ = 0.f;
+            for (int i = 0; i < nc; ++i) {
+                const float x = s_pts[5 * i], y = s_pts[5 * i + 1], X = s_pts[5 * i + 2], Y = s_pts[5 * i + 3], Z = s_pts[5 * i + 4];
+                const float zc = fmaf(R[6], X, fmaf(R[7], Y, fmaf(R[8], Z, R[11])));
+                const float xc = fmaf(R[0], X, fmaf(R[1], Y, fmaf(R[2], Z, R[9])));
+                const float yc = fmaf(R[3], X, fmaf(R[4], Y, fmaf(R[5], Z, R[10])));
+                const float dx = fmaf(-x, zc, xc), dy = fmaf(-y, zc, yc);
+                const float num = fmaf(dx, dx, dy * dy), z2 = zc * zc;
+                if (zc > 1e-12f && num <= thr2f * z2) { ++c; rs_ += __fdividef(num, z2); }
             }
-            if (cnt > best_cnt || (cnt == best_cnt && res < best_res)) { best_cnt = cnt; best_res = res; best_pose = sol[s]; }
+            cnt[sidx] += c;
+            res[sidx] += rs_;
         }
     }
+#pragma unroll
+    for (int sidx = 0; sidx < 4; ++sidx)
+        if (sidx < ns && (cnt[sidx] > best_cnt || (cnt[sidx] == best_cnt && (double)res[sidx] < best_res))) {
+            best_cnt = cnt[sidx]; best_res = (double)res[sidx]; best_pose = sol[sidx];
+        }
     // block arg-max: (count desc, residual asc, thread index asc) -- deterministic
     __shared__ int s_cnt[HYP_THREADS];
     __shared__ double s_res[HYP_THREADS];
