@@ -26,7 +26,7 @@ METRIC = 'localization frames/sec (640x480, 1024 kpts)'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=32, help='frames per GPU per step')
@@ -373,7 +373,7 @@ def roofline_probe(pipe, frames_dev, dev):
     mma_mult = 3 if prec == 'bf16x3' else 1
     # DRAM traffic of the same launch from the committed `ncu --set full` capture (profiles/), B=32 bf16x3 only
     traffic = None
-    prof = ROOT / 'profiles' / 'r01_ncu_full_conv3b_attention_v1_summary.csv'
+    prof = ROOT / 'profiles' / 'r01_ncu_full_conv3b_attention_v6_summary.csv'
     if prof.exists() and B == 32 and prec == 'bf16x3':
         import csv
         rows = list(csv.reader(open(prof)))

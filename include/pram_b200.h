@@ -100,6 +100,11 @@ int pram_gconv3x3_tc(const void* in_hi, const void* in_lo, const float* w, const
 int pram_conv1a(const float* img_nchw, const float* w, const float* bias, int B, int H, int W, void* ps_hi,
                 void* ps_lo, float* out_f32, pram_stream_t stream);
 
+/* conv1a on tcgen05: the CTA builds the 128 x 32 im2col operand (bf16 hi/lo, SWIZZLE_128B K-major) in shared memory
+ * itself, 2 k-steps x 3 MMAs per 128 pixels, phase-split split-bf16 output as above.  nets/sfd2.py:141. */
+int pram_conv1a_tc(const float* img_nchw, const float* w, const float* bias, int B, int H, int W, void* ps_hi, void* ps_lo,
+                   int split, pram_stream_t stream);
+
 /* F.normalize over the channel axis of an NHWC map.  nets/sfd2.py:333. */
 int pram_l2norm_rows(const float* in, float* out, long long rows, int C, pram_stream_t stream);
 
@@ -156,6 +161,7 @@ typedef struct pram_tc_args {
     void* q_hi; void* q_lo; void* k_hi; void* k_lo; void* v_hi; void* v_lo;
     int seg_split, seg_n0, seg_n1, heads;
     int cluster;                          /* 0 = auto, 1 = single CTAs, 2 = 2-CTA clusters, weight tile TMA-multicast */
+    int l2_prefetch;                      /* 1 = L2-prefetch the next tile's activation boxes (single-tap layers); default off */
 } pram_tc_args;
 int pram_gemm_tc(const pram_tc_args* args, pram_stream_t stream);
 

@@ -64,7 +64,7 @@ class TcArgs(C.Structure):
         ('qkv_mode', _I), ('cosb', _P), ('sinb', _P), ('qk_scale', _F),
         ('q_hi', _P), ('q_lo', _P), ('k_hi', _P), ('k_lo', _P), ('v_hi', _P), ('v_lo', _P),
         ('seg_split', _I), ('seg_n0', _I), ('seg_n1', _I), ('heads', _I),
-        ('cluster', _I),
+        ('cluster', _I), ('l2_prefetch', _I),
     ]
 
 
@@ -82,6 +82,7 @@ SIGNATURES['pram_project_points'] = (_I, [_P, _I, _P, _D, _D, _D, _D, _D, _D, _P
 SIGNATURES['pram_projection_top2'] = (_I, [_P, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _P, _P])
 SIGNATURES['pram_gconv3x3_split'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P])
 SIGNATURES['pram_gconv3x3_tc'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P])
+SIGNATURES['pram_conv1a_tc'] = (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _P])
 SIGNATURES['pram_conv1a'] = (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P])
 SIGNATURES['pram_layernorm_gelu_split'] = (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _P])
 

@@ -51,6 +51,7 @@ struct Args {
     const float* cosb; const float* sinb; float qk_scale;
     __nv_bfloat16* q_hi; __nv_bfloat16* q_lo; __nv_bfloat16* k_hi; __nv_bfloat16* k_lo; __nv_bfloat16* v_hi; __nv_bfloat16* v_lo;
     int seg_split, seg_n0, seg_n1, heads;
+    int l2_prefetch;     // 1: pull the next tile's activation boxes into L2 one tile ahead (single-tap layers)
 };
 
 // ---------------------------------------------------------------------------------------- PTX
@@ -110,6 +111,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// L2 prefetch of a future operand box (no shared memory, no barrier): shortens the latency of the later TMA load
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -248,6 +254,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
             const int nt = tile % n_tiles, mt = (tile / n_tiles) * CL + crank;  // mt >= m_tiles: all-zero A (OOB fill)
             const int txi = mt % tiles_x, tyi = (mt / tiles_x) % tiles_y, b = mt / (tiles_x * tiles_y);
             const int x0 = txi * TW, y0 = tyi * TH, n0 = nt * BN;
+            // optional experiment (off by default, no gain measured): Linear / 1x1 layers stream their activations from
+            // HBM exactly once and only two 96 KB stages fit in shared memory; pull the next tile's boxes into L2 early
+            if (p.l2_prefetch && tile + ncl < total) {
+                const int nxt = tile + ncl;
+                const int nnt = nxt % n_tiles, nmt = (nxt / n_tiles) * CL + crank;
+                if (nnt == 0 || n_tiles == 1 || nmt != mt) {  // a new M tile: its boxes have not been requested yet
+                    const int ntx = nmt % tiles_x, nty = (nmt / tiles_x) % tiles_y, nb = nmt / (tiles_x * tiles_y);
+                    for (int kc = 0; kc < p.kblocks; ++kc) {
+                        tma_prefetch_4d(&map_a_hi, kc * BK, ntx * TW + p.tap_dx[0], nty * TH + p.tap_dy[0], nb * p.planes_per_image + p.tap_plane[0]);
+                        if (SPLIT == 3)
+                            tma_prefetch_4d(&map_a_lo, kc * BK, ntx * TW + p.tap_dx[0], nty * TH + p.tap_dy[0], nb * p.planes_per_image + p.tap_plane[0]);
+                    }
+                }
+            }
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int tap = kb / p.kblocks, kc = kb - tap * p.kblocks;
                 mbar_wait(&empty[stage], phase ^ 1);
@@ -642,6 +662,7 @@ struct pram_tc_args {
     void* q_hi; void* q_lo; void* k_hi; void* k_lo; void* v_hi; void* v_lo;
     int seg_split, seg_n0, seg_n1, heads;
     int cluster;                          // 0 = auto, 1 = single CTAs, 2 = 2-CTA clusters with a multicast weight tile
+    int l2_prefetch;                      // 1 = pull the next tile's activation boxes into L2 one tile ahead (single-tap layers); default off
 };
 
 PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
@@ -703,6 +724,7 @@ PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
     k.q_hi = (__nv_bfloat16*)a->q_hi; k.q_lo = (__nv_bfloat16*)a->q_lo; k.k_hi = (__nv_bfloat16*)a->k_hi;
     k.k_lo = (__nv_bfloat16*)a->k_lo; k.v_hi = (__nv_bfloat16*)a->v_hi; k.v_lo = (__nv_bfloat16*)a->v_lo;
     k.seg_split = a->seg_split; k.seg_n0 = a->seg_n0; k.seg_n1 = a->seg_n1; k.heads = a->heads;
+    k.l2_prefetch = (a->ntaps == 1) && (a->l2_prefetch == 1);  // measured on B200: no gain (the thin GEMMs are store-bound), off unless asked for
     if (a->qkv_mode) {
         if (bn != 256 || a->heads * 64 != 256 || !a->q_hi || !a->v_hi || a->ps_hi || a->l2norm) return PRAM_ERR_UNSUPPORTED;
         if ((a->qkv_mode == 1 && (a->N != 768 || !a->k_hi || !a->cosb || !a->sinb)) || (a->qkv_mode == 2 && a->N != 512)) return PRAM_ERR_ARG;

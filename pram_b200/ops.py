@@ -254,6 +254,7 @@ def empty_split(shape, device, with_lo: bool = True, zero: bool = False) -> Spli
 
 import os as _os
 GEMM_CLUSTER = int(_os.environ.get('PRAM_GEMM_CLUSTER', '0'))  # 0 = auto; 1 / 2 force single CTAs / 2-CTA clusters (tests, A/B timing)
+GEMM_L2_PREFETCH = int(_os.environ.get('PRAM_GEMM_L2_PREFETCH', '0'))  # 1 = on (experiment; default off)
 _S1_TAPS = [(dy, dx, 0) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
 # stride 2 on a 2x2 phase-split input: tap r in {0,1,2} reads phase (1,0,1) at offset (-1,0,0)
 _PH = ((1, -1), (0, 0), (1, 0))
@@ -296,6 +297,7 @@ def gemm_tc(a: Split, a_ld: int, in_w: int, in_h: int, in_planes: int, cin: int,
                 setattr(A, name + '_lo', sp.lo.data_ptr() if sp.lo is not None else None)
         A.seg_split, A.seg_n0, A.seg_n1 = qkv['seg_split'], qkv['seg_n0'], qkv['seg_n1']
     A.cluster = GEMM_CLUSTER
+    A.l2_prefetch = GEMM_L2_PREFETCH
     import ctypes
     call('pram_gemm_tc', ctypes.byref(A), stream_ptr())
 
@@ -348,6 +350,9 @@ def linear_tc(a: Split, lda: int, rows: int, k: int, w: Split, n: int, bias: Opt
             1 if w_batched else 0, bias, res, ldres, relu, out_f32, ld_f32, out_bf, ld_bf, None, 0, False, split, bn, qkv)
 
 
+CONV1A_TC = True  # tcgen05 kernel (conv1a_tc.cu); False = the CUDA-core kernel (also used when an fp32 copy is wanted)
+
+
 def conv1a(image_nchw: Tensor, w: Tensor, bias: Tensor, split: int, want_f32: bool = False):
     """conv1a + BN + ReLU from the NCHW fp32 image -> phase-split Split [B*4,ceil(H/2),ceil(W/2),64]
     (and optionally fp32 NHWC)."""
@@ -356,7 +361,10 @@ def conv1a(image_nchw: Tensor, w: Tensor, bias: Tensor, split: int, want_f32: bo
     dev = image_nchw.device
     ps = empty_split((b * 4, (h + 1) // 2, (wd + 1) // 2, 64), dev, with_lo=(split == 3), zero=bool(h % 2 or wd % 2))
     f32 = torch.empty((b, h, wd, 64), device=dev, dtype=torch.float32) if want_f32 else None
-    call('pram_conv1a', ptr(image_nchw), ptr(w), ptr(bias), b, h, wd, ptr(ps.hi), ptr(ps.lo), ptr(f32), stream_ptr())
+    if CONV1A_TC and not want_f32:
+        call('pram_conv1a_tc', ptr(image_nchw), ptr(w), ptr(bias), b, h, wd, ptr(ps.hi), ptr(ps.lo), split, stream_ptr())
+    else:
+        call('pram_conv1a', ptr(image_nchw), ptr(w), ptr(bias), b, h, wd, ptr(ps.hi), ptr(ps.lo), ptr(f32), stream_ptr())
     return ps, f32
 
 

@@ -45,6 +45,9 @@ class LocalizationPipeline:
         self.num_hypotheses = 1024
         self.pre_filtering_th = 0.95  # configs/config_train_7scenes_sfd2.yaml: pre_filtering_th
         self.seg_k = 20               # configs/config_train_7scenes_sfd2.yaml: seg_k
+        import os
+        self.two_streams = os.environ.get('PRAM_TWO_STREAMS', '1') != '0'
+        self._side = None
 
     # -- stages -------------------------------------------------------------------------------
     def features(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -67,21 +70,42 @@ class LocalizationPipeline:
                              'descriptors1': smap.descriptors, 'keypoints1': smap.keypoints,
                              'image_shape0': shp, 'image_shape1': shp})
 
-    def localize(self, images: torch.Tensor, smap: Optional[SyntheticMap] = None) -> Dict[str, torch.Tensor]:
-        shape = tuple(images.shape)
-        f = self.features(images)
-        out = {'keypoints': f['keypoints'], 'num_keypoints': f['num_keypoints'],
-               'prediction': self.recognize(f, shape)}
+    def _recognition(self, f: Dict[str, torch.Tensor], shape, out: Dict[str, torch.Tensor]):
+        out['prediction'] = self.recognize(f, shape)
         out['labels'] = out['prediction'].argmax(-1)
         # recognition -> matching glue (reference frame.py:96-121, multimap3d.py:348-379), kept on the device
         b, k, c = out['prediction'].shape
         bg, sid, non_bg = ops.segmentation(out['prediction'].reshape(b * k, c), self.pre_filtering_th)
         out['seg_ids'], out['non_bg'] = sid.view(b, k), non_bg.view(b, k)
         out['landmarks'] = ops.rank_landmarks(out['prediction'], out['non_bg'], self.seg_k, max_ranks=8)
-        if smap is not None:
-            m = self.match(f, smap, shape)
-            out.update(m)
-            out.update(self.pose(f, m, smap, shape))
+
+    def localize(self, images: torch.Tensor, smap: Optional[SyntheticMap] = None) -> Dict[str, torch.Tensor]:
+        shape = tuple(images.shape)
+        f = self.features(images)
+        out = {'keypoints': f['keypoints'], 'num_keypoints': f['num_keypoints']}
+        if smap is None or not self.two_streams:
+            self._recognition(f, shape, out)
+            if smap is not None:
+                m = self.match(f, smap, shape)
+                out.update(m)
+                out.update(self.pose(f, m, smap, shape))
+            return out
+        # recognition (SegNetViT + ranking) and matching + pose (GML, Sinkhorn, RANSAC) only share the features: they
+        # run on two streams (a fork/join inside the captured graph), so the prologue / tail of every persistent
+        # kernel of one branch is filled by the other branch
+        main = torch.cuda.current_stream(self.dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        side = self._side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._recognition(f, shape, out)
+        m = self.match(f, smap, shape)
+        out.update(m)
+        out.update(self.pose(f, m, smap, shape))
+        main.wait_stream(side)
+        for v in (out['prediction'], out['labels'], out['seg_ids'], out['non_bg'], *out['landmarks'].values()):
+            v.record_stream(main)
         return out
 
     def pose(self, f: Dict[str, torch.Tensor], m: Dict[str, torch.Tensor], smap: SyntheticMap, image_shape):

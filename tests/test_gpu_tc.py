@@ -219,3 +219,34 @@ def test_gemm_cluster_multicast_bit_identical(ops, dev, case):
             ops.GEMM_CLUSTER = 0
     for t1, t2 in zip(outs[1], outs[2]):
         assert torch.equal(t1, t2)
+
+
+@pytest.mark.parametrize('split', [3, 1])
+@pytest.mark.parametrize('b,h,w', [(2, 16, 128), (1, 31, 77), (3, 24, 300)])
+def test_conv1a_tc(ops, dev, split, b, h, w):
+    """conv1a on tcgen05 (CTA-built im2col operand) vs torch-CPU fp32 conv2d + ReLU, through the phase-split layout,
+    and vs the CUDA-core kernel; ragged widths / odd heights exercise the zero rows and the phase-split padding."""
+    g = torch.Generator().manual_seed(h * w)
+    x = torch.rand(b, 3, h, w, generator=g) * 2 - 1
+    wt = torch.randn(64, 3, 3, 3, generator=g) * 0.2
+    bias = torch.randn(64, generator=g) * 0.1
+    ref = torch.relu(torch.nn.functional.conv2d(x, wt, bias, padding=1)).permute(0, 2, 3, 1)  # NHWC
+    wp = wt.permute(2, 3, 1, 0).reshape(27, 64).contiguous().to(dev)  # k = (ry*3 + rx)*3 + c
+    outs = {}
+    for tc in (True, False):
+        ops.CONV1A_TC = tc
+        try:
+            ps, _ = ops.conv1a(x.to(dev), wp, bias.to(dev), split)
+            torch.cuda.synchronize()
+        finally:
+            ops.CONV1A_TC = True
+        hp, wq = (h + 1) // 2, (w + 1) // 2
+        full = torch.zeros(b, hp * 2, wq * 2, 64)
+        psf = ps.float().view(b, 2, 2, hp, wq, 64).cpu()
+        for py in range(2):
+            for px in range(2):
+                full[:, py::2, px::2] = psf[:, py, px]
+        outs[tc] = full[:, :h, :w]
+    tol = TOL[split] if split == 3 else 3e-2
+    assert _relerr(outs[False], ref) < tol
+    assert _relerr(outs[True], ref) < tol
