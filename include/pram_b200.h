@@ -206,6 +206,13 @@ int pram_projection_top2(const float* sim, int ld, int M, int N, const float* kp
                          const unsigned char* valid, float window, float ratio, long long* match, float* d0, float* d1,
                          pram_stream_t stream);
 
+/* NearestNeighbor matcher (localization/matchers/nearest_neighbor.py:5-56): top-2 per similarity row, ratio / distance
+ * tests (thresholds <= 0 disable them), optional mutual check.  sim [B][N][M], simT [B][M][N] (NULL when mutual == 0);
+ * matches0 int64 [B][N] (-1 = none), scores0 = (sim+1)/2 or 0; *_ws: [B][M] scratch for the reverse direction. */
+int pram_nn_match(const float* sim, const float* simT, int B, int N, int M, float ratio_threshold, float distance_threshold,
+                  int mutual, long long* matches0, float* scores0, long long* matches1_ws, float* scores1_ws,
+                  pram_stream_t stream);
+
 /* fp32 -> split bf16 planes: hi = bf16(x), lo = bf16(x - hi) (lo may be NULL). */
 int pram_split_bf16(const float* in, void* hi, void* lo, long long n, pram_stream_t stream);
 

@@ -781,3 +781,36 @@ def match_by_projection(q_kpts: np.ndarray, q_descs: np.ndarray, xyz: np.ndarray
     ok = ((d[:, 0] / d[:, 1]) <= 0.995) & (d[:, 0] < 100)
     ok = ok.numpy()
     return np.where(ok)[0], idx[ids.numpy()[ok, 0]], d.numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# NearestNeighbor matcher (reference localization/matchers/nearest_neighbor.py:5-56)
+# ------------------------------------------------------------------------------------------------
+
+def nn_find_nn(sim: Tensor, ratio_thresh, distance_thresh):
+    """reference nearest_neighbor.py:5-16."""
+    sim_nn, ind_nn = sim.topk(2 if ratio_thresh else 1, dim=-1, largest=True)
+    dist_nn = 2 * (1 - sim_nn)
+    mask = torch.ones(ind_nn.shape[:-1], dtype=torch.bool)
+    if ratio_thresh:
+        mask = mask & (dist_nn[..., 0] <= (ratio_thresh ** 2) * dist_nn[..., 1])
+    if distance_thresh:
+        mask = mask & (dist_nn[..., 0] <= distance_thresh ** 2)
+    matches = torch.where(mask, ind_nn[..., 0], ind_nn.new_tensor(-1))
+    scores = torch.where(mask, (sim_nn[..., 0] + 1) / 2, sim_nn.new_tensor(0))
+    return matches, scores
+
+
+def nearest_neighbor_forward(desc0: Tensor, desc1: Tensor, ratio_threshold=None, distance_threshold=None,
+                             do_mutual_check: bool = True):
+    """desc0 [B,D,N], desc1 [B,D,M] -> {'matches0', 'matching_scores0'}; reference nearest_neighbor.py:36-56 and
+    mutual_check :19-24."""
+    sim = torch.einsum('bdn,bdm->bnm', desc0, desc1)
+    m0, s0 = nn_find_nn(sim, ratio_threshold, distance_threshold)
+    if do_mutual_check:
+        m1, _ = nn_find_nn(sim.transpose(1, 2), ratio_threshold, distance_threshold)
+        inds0 = torch.arange(m0.shape[-1])
+        loop = torch.gather(m1, -1, torch.where(m0 > -1, m0, m0.new_tensor(0)))
+        ok = (m0 > -1) & (inds0 == loop)
+        m0 = torch.where(ok, m0, m0.new_tensor(-1))
+    return {'matches0': m0, 'matching_scores0': s0, 'sim': sim}

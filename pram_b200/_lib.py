@@ -80,6 +80,7 @@ SIGNATURES['pram_segmentation'] = (_I, [_P, _I, _I, _F, _P, _P, _P, _P, _P])
 SIGNATURES['pram_rank_landmarks'] = (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P])
 SIGNATURES['pram_project_points'] = (_I, [_P, _I, _P, _D, _D, _D, _D, _D, _D, _P, _P, _P])
 SIGNATURES['pram_projection_top2'] = (_I, [_P, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _P, _P])
+SIGNATURES['pram_nn_match'] = (_I, [_P, _P, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P])
 SIGNATURES['pram_gconv3x3_split'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P])
 SIGNATURES['pram_gconv3x3_tc'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P])
 SIGNATURES['pram_conv1a_tc'] = (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _P])

@@ -255,3 +255,70 @@ PRAM_API int pram_projection_top2(const float* sim, int ld, int M, int N, const 
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// NearestNeighbor matcher (reference localization/matchers/nearest_neighbor.py:5-56; section 8f row 4):
+//   find_nn: top-2 of each similarity row, dist = 2 (1 - sim), optional ratio test d0 <= ratio^2 d1 and distance
+//   test d0 <= dist_th^2; matches = arg-max or -1, scores = (sim0 + 1) / 2 or 0.  One warp per row; the M x N
+//   similarity comes from the tcgen05 GEMM.  mutual_check: keep i -> j only if j -> i.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nn_top2_kernel(const float* __restrict__ sim, long long batch_stride, int ld, int rows,
+                                                      int cols, int B, float ratio2 /*< 0: off*/, float dist2 /*< 0: off*/,
+                                                      long long* __restrict__ matches, float* __restrict__ scores) {
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= (long long)B * rows) return;
+    const int b = (int)(wid / rows), i = (int)(wid - (long long)b * rows);
+    const float* p = sim + (long long)b * batch_stride + (long long)i * ld;
+    float v0 = -INFINITY, v1 = -INFINITY;
+    int i0 = 0x7fffffff;
+    for (int j = lane; j < cols; j += 32) {
+        const float v = p[j];
+        if (v > v0) { v1 = v0; v0 = v; i0 = j; }   // ascending j: the first occurrence wins ties
+        else if (v > v1) v1 = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov0 = __shfl_xor_sync(0xffffffffu, v0, o), ov1 = __shfl_xor_sync(0xffffffffu, v1, o);
+        const int oi0 = __shfl_xor_sync(0xffffffffu, i0, o);
+        const bool other_wins = (ov0 > v0) || (ov0 == v0 && oi0 < i0);
+        const float loser = other_wins ? v0 : ov0;
+        v1 = fmaxf(fmaxf(v1, ov1), loser);
+        if (other_wins) { v0 = ov0; i0 = oi0; }
+    }
+    if (lane == 0) {
+        const float d0 = 2.f * (1.f - v0), d1 = 2.f * (1.f - v1);
+        bool ok = true;
+        if (ratio2 >= 0.f) ok = ok && (d0 <= ratio2 * d1);
+        if (dist2 >= 0.f) ok = ok && (d0 <= dist2);
+        matches[wid] = ok ? (long long)i0 : -1ll;
+        scores[wid] = ok ? (v0 + 1.f) * 0.5f : 0.f;
+    }
+}
+
+__global__ void nn_mutual_kernel(long long* __restrict__ m0, const long long* __restrict__ m1, int N, int M, int B) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * N) return;
+    const int b = (int)(t / N), i = (int)(t - (long long)b * N);
+    const long long j = m0[t];
+    if (j > -1 && m1[(long long)b * M + j] != i) m0[t] = -1;
+}
+
+// sim [B][N][M] (row stride ld = M), simT [B][M][N] (may be NULL when mutual == 0)
+PRAM_API int pram_nn_match(const float* sim, const float* simT, int B, int N, int M, float ratio_threshold, float distance_threshold,
+                           int mutual, long long* matches0, float* scores0, long long* matches1_ws, float* scores1_ws,
+                           cudaStream_t stream) {
+    if (!sim || !matches0 || !scores0 || B <= 0 || N <= 0 || M <= 0) return PRAM_ERR_ARG;
+    if (mutual && (!simT || !matches1_ws || !scores1_ws)) return PRAM_ERR_ARG;
+    const float r2 = ratio_threshold > 0.f ? ratio_threshold * ratio_threshold : -1.f;
+    const float d2 = distance_threshold > 0.f ? distance_threshold * distance_threshold : -1.f;
+    nn_top2_kernel<<<cdiv((long long)B * N * 32, 256), 256, 0, stream>>>(sim, (long long)N * M, M, N, M, B, r2, d2, matches0, scores0);
+    PRAM_CHECK_LAUNCH();
+    if (mutual) {
+        nn_top2_kernel<<<cdiv((long long)B * M * 32, 256), 256, 0, stream>>>(simT, (long long)N * M, N, M, N, B, r2, d2, matches1_ws, scores1_ws);
+        PRAM_CHECK_LAUNCH();
+        nn_mutual_kernel<<<cdiv((long long)B * N, 256), 256, 0, stream>>>(matches0, matches1_ws, N, M, B);
+        PRAM_CHECK_LAUNCH();
+    }
+    return PRAM_OK;
+}

@@ -64,7 +64,7 @@ def absolute_pose_estimation(points2D, points3D, camera, estimation_options: Opt
 def feature_matching(query_data: dict, db_data: dict, matcher) -> np.ndarray:
     """Reference pose_estimator.py:45-86: match query features against one database image, optionally
     restricted to keypoints with a 3-D point, and remap the matches to database keypoint ids."""
-    dev = next(matcher.parameters()).device
+    dev = next((p.device for p in matcher.parameters()), torch.device('cuda'))  # parameter-free matchers (NN) run on cuda
     db_3D_ids = db_data.get('db_3D_ids')
     if db_3D_ids is None:
         valid_ids = None
@@ -92,3 +92,37 @@ def feature_matching(query_data: dict, db_data: dict, matcher) -> np.ndarray:
         ok = matches >= 0
         matches[ok] = valid_ids[matches[ok]]
     return matches
+
+
+def find_2D_3D_matches(query_data: dict, db_id, points3D, feature_file, db_images, matcher, obs_th: int = 0):
+    """Same contract as reference ``localization/pose_estimator.py:88-134``: match the query against database image
+    ``db_id`` (features read from the h5-like mapping ``feature_file[name][key][()]``, descriptors stored [D, N]),
+    keep matches whose database keypoint has a 3-D point observed in at least ``obs_th`` images, and return
+    ``(mp3d [n,3] float, mkpq [n,2] float (+0.5 pixel-centre shift), mp3d_ids list, q_ids list)``.
+    The matcher call is the device part (``feature_matching``); the filtering is vectorised numpy instead of the
+    reference's per-match Python loop (same order: ascending query index)."""
+    kpq = query_data['keypoints']
+    db_name = db_images[db_id].name
+    grp = feature_file[db_name]
+    rd = lambda k: np.asarray(grp[k][()])  # h5py datasets and plain numpy arrays both support [()]
+    kpdb = rd('keypoints')
+    desc_db = rd('descriptors').transpose()
+    points3D_ids = np.asarray(db_images[db_id].point3D_ids)
+    matches = feature_matching(query_data=query_data,
+                               db_data={'keypoints': kpdb, 'scores': rd('scores'), 'descriptors': desc_db,
+                                        'db_3D_ids': points3D_ids, 'image_size': rd('image_size')},
+                               matcher=matcher)
+    matches = np.asarray(matches)
+    q_ids = np.nonzero(matches != -1)[0]
+    if q_ids.size:
+        ids3d = points3D_ids[matches[q_ids]]
+        keep = ids3d != -1
+        q_ids, ids3d = q_ids[keep], ids3d[keep]
+        if obs_th > 0 and q_ids.size:
+            keep = np.array([len(points3D[i].image_ids) >= obs_th for i in ids3d], bool)
+            q_ids, ids3d = q_ids[keep], ids3d[keep]
+    else:
+        ids3d = np.zeros((0,), np.int64)
+    mp3d = np.array([points3D[i].xyz for i in ids3d], float).reshape(-1, 3)
+    mkpq = np.asarray(kpq, float)[q_ids].reshape(-1, 2) + 0.5
+    return mp3d, mkpq, [int(i) for i in ids3d], [int(i) for i in q_ids]

@@ -500,3 +500,35 @@ def match_by_projection(q_kpts: Tensor, q_descs: Tensor, xyz: Tensor, descs: Ten
     call('pram_projection_top2', ptr(sim), n, m, n, ptr(_f32c(q_kpts)), ptr(uv), ptr(valid), float(2 * threshold),
          float(ratio), ptr(match), ptr(d0), ptr(d1), stream_ptr())
     return match, d0, d1
+
+
+def nearest_neighbor_match(desc0: Tensor, desc1: Tensor, ratio_threshold: Optional[float], distance_threshold: Optional[float],
+                           do_mutual_check: bool = True, split: int = 3):
+    """desc0 [B,D,N], desc1 [B,D,M] (the reference matcher's 'bdn' layout) -> (matches0 [B,N] i64, scores0 [B,N]);
+    reference localization/matchers/nearest_neighbor.py:5-56.  sim = desc0^T desc1 runs on the tcgen05 GEMM."""
+    _lib.require_cuda(desc0, 'descriptors0')
+    b, d, n = desc0.shape
+    m = desc1.shape[2]
+    dev = desc0.device
+    a0 = split_bf16(_f32c(desc0.transpose(1, 2)), split == 3)  # [B,N,D] K-major rows (layout plumbing only)
+    a1 = split_bf16(_f32c(desc1.transpose(1, 2)), split == 3)
+    dpad = d  # Cin % 8 == 0 is required by the TMA strides
+    if d % 8:
+        raise _lib.PramError('descriptor dimension must be a multiple of 8')
+    sim = torch.empty((b, n, m), device=dev, dtype=torch.float32)
+    linear_tc(Split(a0.hi.view(b * n, d), a0.lo.view(b * n, d) if a0.lo is not None else None), d, n, d,
+              Split(a1.hi.view(b * m, d), a1.lo.view(b * m, d) if a1.lo is not None else None), m, out_f32=sim, ld_f32=m,
+              split=split, batch=b, w_batched=True)
+    simt = m1 = s1 = None
+    if do_mutual_check:
+        simt = torch.empty((b, m, n), device=dev, dtype=torch.float32)
+        linear_tc(Split(a1.hi.view(b * m, d), a1.lo.view(b * m, d) if a1.lo is not None else None), d, m, d,
+                  Split(a0.hi.view(b * n, d), a0.lo.view(b * n, d) if a0.lo is not None else None), n, out_f32=simt, ld_f32=n,
+                  split=split, batch=b, w_batched=True)
+        m1 = torch.empty((b, m), device=dev, dtype=torch.int64)
+        s1 = torch.empty((b, m), device=dev, dtype=torch.float32)
+    m0 = torch.empty((b, n), device=dev, dtype=torch.int64)
+    s0 = torch.empty((b, n), device=dev, dtype=torch.float32)
+    call('pram_nn_match', ptr(sim), ptr(simt), b, n, m, float(ratio_threshold or 0.0), float(distance_threshold or 0.0),
+         int(bool(do_mutual_check)), ptr(m0), ptr(s0), ptr(m1), ptr(s1), stream_ptr())
+    return m0, s0

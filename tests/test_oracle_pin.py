@@ -171,3 +171,20 @@ def test_next_row_oracles_vs_reference_methods():
     assert len(ref) == len(ours)
     for (s0, i0, v0), (s1, i1, v1) in zip(ref, ours):
         assert s0 == s1 and np.array_equal(i0, i1) and v0 == v1
+
+
+@needs_ref
+def test_nearest_neighbor_oracle_vs_reference_module():
+    """The NN-matcher restatement against the reference's own plugin (importable as-is)."""
+    RL.import_reference()
+    from localization.matchers.nearest_neighbor import NearestNeighbor
+    g = torch.Generator().manual_seed(5)
+    d0 = torch.nn.functional.normalize(torch.randn(2, 128, 300, generator=g), dim=1)
+    d1 = torch.nn.functional.normalize(torch.randn(2, 128, 257, generator=g), dim=1)
+    d1[:, :, :100] = torch.nn.functional.normalize(d0[:, :, 50:150] + 0.1 * torch.randn(2, 128, 100, generator=g), dim=1)
+    for conf in ({}, {'ratio_threshold': 0.9}, {'distance_threshold': 0.7, 'do_mutual_check': False},
+                 {'ratio_threshold': 0.95, 'distance_threshold': 0.9}):
+        ref = NearestNeighbor(conf)({'descriptors0': d0, 'descriptors1': d1})
+        ours = O.nearest_neighbor_forward(d0, d1, **{**NearestNeighbor.default_conf, **conf})
+        assert torch.equal(ref['matches0'], ours['matches0'])
+        assert torch.equal(ref['matching_scores0'], ours['matching_scores0'])
