@@ -74,8 +74,9 @@ NMS_HD void nms_slide8(const float* v, float* out) {
 }
 
 // ---- phase 0: stage the tile; item = row * (NG + 2) + (c + 1), c in [-1, NG] (pad groups included) ----
+// split into value / store so that the kernel can keep several global loads in flight per thread
 template <class G>
-NMS_HD void nms_load(const NmsTile& t, int item) {
+NMS_HD float4 nms_load_value(const NmsTile& t, int item) {
     const int row = item / (G::NG + 2), c = item - row * (G::NG + 2) - 1;
     const float NEG = -INFINITY;
     float4 v = make_float4(NEG, NEG, NEG, NEG);
@@ -91,8 +92,15 @@ NMS_HD void nms_load(const NmsTile& t, int item) {
             if (gx + 3 >= 0 && gx + 3 < t.W) v.w = p[3];
         }
     }
-    *reinterpret_cast<float4*>(t.S + row * G::SWP + 4 * (c + 1)) = v;
+    return v;
 }
+template <class G>
+NMS_HD void nms_store_value(const NmsTile& t, int item, float4 v) {
+    const int row = item / (G::NG + 2), c1 = item - row * (G::NG + 2);
+    *reinterpret_cast<float4*>(t.S + row * G::SWP + 4 * c1) = v;
+}
+template <class G>
+NMS_HD void nms_load(const NmsTile& t, int item) { nms_store_value<G>(t, item, nms_load_value<G>(t, item)); }
 
 // pad rows of T and the mask arrays; item over max(8 * SW / 4, 3 * MASK_BYTES / 4) words
 template <class G>

@@ -357,7 +357,21 @@ PRAM_API int pram_l2norm_rows(const float* in, float* out, long long rows, int C
 // ------------------------------------------------------------------------------------------
 // single-pass variant for C % 128 == 0 (256 / 512 / 1024): the row lives in registers (NV float4 per
 // lane), one 16-byte load and one 16-byte (fp32) / 8-byte (bf16 plane) store per element group
-template <int NV>
+// erf by Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7 + fp32 rounding): one rcp, one ex2, five FMAs instead of the
+// ~25-instruction erff.  Used only by the split-bf16 (tensor-core path) variant, whose outputs are rounded to 2 x bf16
+// (2^-17 relative) anyway; the fp32 exact-arithmetic path keeps erff.
+__device__ __forceinline__ float erf_as(float x) {
+    const float z = fabsf(x);
+    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float y = 1.f - p * t * __expf(-z * z);
+    return copysignf(y, x);
+}
+
+template <int NV, bool FAST_ERF>
 __global__ void __launch_bounds__(256) layernorm_gelu_vec_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, float* __restrict__ out,
                                                                 __nv_bfloat16* __restrict__ out_hi,
@@ -390,7 +404,8 @@ __global__ void __launch_bounds__(256) layernorm_gelu_vec_kernel(const float* __
                       (v[k].z - mean) * rstd * g.z + bt.z, (v[k].w - mean) * rstd * g.w + bt.w};
         if (gelu) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = 0.5f * o[j] * (1.f + erff(o[j] * 0.70710678118654752440f));
+            for (int j = 0; j < 4; ++j)
+                o[j] = 0.5f * o[j] * (1.f + (FAST_ERF ? erf_as(o[j] * 0.70710678118654752440f) : erff(o[j] * 0.70710678118654752440f)));
         }
         if (out) reinterpret_cast<float4*>(out + row * C)[c4] = make_float4(o[0], o[1], o[2], o[3]);
         if (out_hi) {
@@ -411,10 +426,18 @@ static bool layernorm_vec_launch(const float* in, const float* gamma, const floa
     const int grid = cdiv(rows * 32, 256);
     __nv_bfloat16* h = (__nv_bfloat16*)hi;
     __nv_bfloat16* l = (__nv_bfloat16*)lo;
+    // the fp32 output path is the exact-arithmetic mode (erff); split-bf16-only output may use the cheaper erf
+    const bool fast = (out == nullptr);
     switch (C) {
-        case 256: layernorm_gelu_vec_kernel<2><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu); return true;
-        case 512: layernorm_gelu_vec_kernel<4><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu); return true;
-        case 1024: layernorm_gelu_vec_kernel<8><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu); return true;
+        case 256: if (fast) layernorm_gelu_vec_kernel<2, true><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu);
+                  else layernorm_gelu_vec_kernel<2, false><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu);
+                  return true;
+        case 512: if (fast) layernorm_gelu_vec_kernel<4, true><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu);
+                  else layernorm_gelu_vec_kernel<4, false><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu);
+                  return true;
+        case 1024: if (fast) layernorm_gelu_vec_kernel<8, true><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu);
+                   else layernorm_gelu_vec_kernel<8, false><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu);
+                   return true;
         default: return false;
     }
 }

@@ -106,14 +106,17 @@ PRAM_API int pram_resize_bilinear(const float* in, int B, int Hi, int Wi, float*
 // Implementation: nms_tile.cuh (phase functions shared with the host emulation in tests/nms_host.cu).
 // ------------------------------------------------------------------------------------------
 constexpr int NMS_MAXR = 4;
-constexpr int NMS_THREADS = 384;
+// threads per CTA: 24 warps on the tall tile (1 CTA / SM; the passes are latency-bound chains of shared-memory loads),
+// 12 on the short one (2 CTAs / SM)
+template <int TH> struct NmsThreads { static constexpr int value = (TH >= 96) ? 768 : 384; };
 
 template <int R, int TH>
-__global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
+__global__ void __launch_bounds__(NmsThreads<TH>::value) nms_kernel(
     const float* __restrict__ score, int H, int W, float th_lo, float th_hi,
     float* __restrict__ nms_out, unsigned long long* __restrict__ cand, int cap,
     int* __restrict__ cand_count, int* __restrict__ count_hi) {
     using G = NmsGeom<R, TH>;
+    constexpr int NMS_THREADS = NmsThreads<TH>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int block_count, block_base, block_hi;
     NmsTile t;
@@ -131,7 +134,18 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
     if (tid == 0) { block_count = 0; block_hi = 0; }
     constexpr int N_INIT = (8 * G::SW / 4 > G::MASK_BYTES / 4) ? 8 * G::SW / 4 : G::MASK_BYTES / 4;
     for (int i = tid; i < N_INIT; i += NMS_THREADS) nms_init<G>(t, i);
-    for (int i = tid; i < G::SH * (G::NG + 2); i += NMS_THREADS) nms_load<G>(t, i);
+    {   // tile load, 4 independent 16-byte global loads in flight per thread
+        constexpr int NLOAD = G::SH * (G::NG + 2);
+        for (int i0 = tid; i0 < NLOAD; i0 += 4 * NMS_THREADS) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * NMS_THREADS < NLOAD) v[u] = nms_load_value<G>(t, i0 + u * NMS_THREADS);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * NMS_THREADS < NLOAD) nms_store_value<G>(t, i0 + u * NMS_THREADS, v[u]);
+        }
+    }
     __syncthreads();
     for (int i = tid; i < G::SH * (G::SW / 8); i += NMS_THREADS) nms_rowmax<G, R, false>(t, i);
     __syncthreads();
@@ -210,7 +224,7 @@ static int nms_launch(const float* score, int B, int H, int W, float th_lo, floa
         attr_set = true;
     }
     dim3 grid(cdiv(W, G::TW), cdiv(H, G::TH), B);
-    kern<<<grid, NMS_THREADS, G::SMEM, stream>>>(score, H, W, th_lo, th_hi, nms_out, cand, cap, cand_count, count_hi);
+    kern<<<grid, NmsThreads<TH>::value, G::SMEM, stream>>>(score, H, W, th_lo, th_hi, nms_out, cand, cap, cand_count, count_hi);
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
 }
