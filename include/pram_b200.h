@@ -173,7 +173,7 @@ int pram_gemm_tc(const pram_tc_args* args, pram_stream_t stream);
  * nets/gml.py:175-181. */
 int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
                       const void* vt_lo, int B, int heads, int Nq, int Nk, int nk_pad, float scale, float* out_f32,
-                      void* out_hi, void* out_lo, int out_ld, int split, int p_swap, int v_mn, pram_stream_t stream);
+                      void* out_hi, void* out_lo, int out_ld, int split, int kv_tile /* 0 = auto, 64 (two CTAs per SM) or 128 */, int v_mn, pram_stream_t stream);
 
 /* qkv fp32 rows -> the attention kernel's operands (rotary + scale on q,k; V transposed per head).
  * nets/segnetvit.py:98-103, nets/gml.py:169-174. */

@@ -17,18 +17,26 @@
 
 namespace fa {
 
-constexpr int BQ = 128, BKV = 128, HD = 64;
-constexpr int NPART = 4;                       // softmax warps per TMEM lane quarter: each takes BKV / NPART key columns
-constexpr int CPT = BKV / NPART;               // 32 key columns per thread
-constexpr int OPT = HD / NPART;                // 16 O columns per thread (rescale + epilogue)
-constexpr int NUM_SM_WARPS = 4 * NPART;        // 16 softmax warps: 4 per SMSP, so the exp / pack chains of one warp hide
-                                               // the tcgen05.ld / barrier latencies of the others
-constexpr int NUM_THREADS = 64 + 32 * NUM_SM_WARPS;  // TMA warp, MMA warp, softmax warps
-// TMEM: two S buffers (128 fp32 columns each) and O.  P(g) is written IN PLACE over S(g) (bf16 hi plane in columns
-// [0,64) of the buffer, lo plane in [64,128)) once every warp of the lane quarter holds its scores in registers, so P
-// is double-buffered for free: softmax(g+1) never waits for PV(g), and the tensor pipe's in-order execution
-// (PV(g) is issued before S(g+2)) is the only "buffer free" signal an S buffer needs.
-constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_O = 256, TMEM_COLS = 512;
+constexpr int BQ = 128, HD = 64;
+
+// Geometry by key-tile size.  BKV = 128: one CTA per SM, 16 softmax warps.  BKV = 64: half the shared memory and TMEM
+// per CTA, 8 softmax warps, TWO CTAs per SM -- the two CTAs run out of phase, so the per-tile handshake chain of one
+// (TMEM load -> row max -> exchange -> exp -> TMEM store -> mbarrier round trip) overlaps the MMAs of the other.
+template <int BKV>
+struct Geo {
+    static constexpr int NPART = BKV / 32;             // softmax warps per TMEM lane quarter: each takes 32 key columns
+    static constexpr int CPT = 32;                     // key columns per thread
+    static constexpr int OPT = HD / NPART;             // O columns per thread (rescale + epilogue): 16 or 32
+    static constexpr int NUM_SM_WARPS = 4 * NPART;
+    static constexpr int NUM_THREADS = 64 + 32 * NUM_SM_WARPS;  // TMA warp, MMA warp, softmax warps
+    // TMEM: two S buffers (BKV fp32 columns each) and O.  P(g) is written IN PLACE over S(g) (bf16 hi plane in columns
+    // [0, BKV/2) of the buffer, lo plane in [BKV/2, BKV)) once every warp of the lane quarter holds its scores in
+    // registers, so P is double-buffered for free: softmax(g+1) never waits for PV(g), and the tensor pipe's in-order
+    // execution (PV(g) is issued before S(g+2)) is the only "buffer free" signal an S buffer needs.
+    static constexpr uint32_t COL_S0 = 0, COL_S1 = BKV, COL_O = 2 * BKV;
+    static constexpr uint32_t TMEM_COLS = (BKV == 128) ? 512 : 256;
+    static constexpr int CTAS_PER_SM = (BKV == 128) ? 1 : 2;
+};
 
 struct Args {
     int BH, heads, Nq, Nk;
@@ -150,30 +158,39 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+__device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+__device__ __forceinline__ void tmem_stN(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st16(taddr, r); }
+__device__ __forceinline__ void tmem_stN(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st32(taddr, r); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-template <int SPLIT>
+template <int SPLIT, int BKV>
 struct Cfg {
     static constexpr int NPL = (SPLIT == 3) ? 2 : 1;
     static constexpr int Q_BYTES = BQ * HD * 2;           // 16 KB per plane
-    static constexpr int K_BYTES = BKV * HD * 2;          // 16 KB per plane
-    static constexpr int V_BYTES = BKV * HD * 2;          // two boxes of 64 d x 64 keys
-    // K and V live in separate rings: K_{g+1} is needed (for S_{g+1}) while V_{g-1} / V_g are still being consumed
-    // by the PV MMAs, so K gets 3 stages and is prefetched one tile ahead of V (2 stages)
-    static constexpr int K_STAGES = 3, V_STAGES = 2;
+    static constexpr int K_BYTES = BKV * HD * 2;          // per plane
+    static constexpr int V_BYTES = BKV * HD * 2;          // per plane (V^T form: BKV / 64 boxes of 64 d x 64 keys)
+    static constexpr int VBOX_BYTES = 64 * HD * 2;
+    // K and V live in separate rings: S runs two tiles ahead of PV, so K(g+2) is needed while V(g) / V(g+1) are still
+    // being consumed
+    static constexpr int K_STAGES = (BKV == 128) ? 3 : 2, V_STAGES = 2;
     static constexpr int K_STAGE = NPL * K_BYTES, V_STAGE = NPL * V_BYTES;
-    static constexpr int SMEM_BYTES = NPL * Q_BYTES + K_STAGES * K_STAGE + V_STAGES * V_STAGE + 1024 + 256 + 2 * NPART * 128 * 4 /*row max/sum exchange*/;
-    static_assert(SMEM_BYTES <= 227 * 1024, "dynamic shared memory budget of sm_100a exceeded");
+    static constexpr int SMEM_BYTES = NPL * Q_BYTES + K_STAGES * K_STAGE + V_STAGES * V_STAGE + 1024 + 256 +
+                                      2 * Geo<BKV>::NPART * 128 * 4 /*row max/sum exchange*/;
+    static_assert(SMEM_BYTES <= (BKV == 128 ? 227 : 113) * 1024, "dynamic shared memory budget of sm_100a exceeded");
 };
 
-template <int SPLIT>
-__global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
+template <int SPLIT, int BKV>
+__global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) attention_tc_kernel(
     const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
     const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo,
     const __grid_constant__ CUtensorMap map_v_hi, const __grid_constant__ CUtensorMap map_v_lo, const Args p) {
-    using C = Cfg<SPLIT>;
+    using C = Cfg<SPLIT, BKV>;
+    using Gm = Geo<BKV>;
+    constexpr int NPART = Gm::NPART, CPT = Gm::CPT, OPT = Gm::OPT, NUM_SM_WARPS = Gm::NUM_SM_WARPS;
+    constexpr uint32_t COL_S0 = Gm::COL_S0, COL_S1 = Gm::COL_S1, COL_O = Gm::COL_O, TMEM_COLS = Gm::TMEM_COLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* q_s = smem;                                  // [NPL][16 KB]
@@ -247,11 +264,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                 tma_load_3d(vs, &map_v_hi, &v_full[st], 0, k0, bh);  // one {64 d x 128 keys} box
                 if (SPLIT == 3) tma_load_3d(vs + C::V_BYTES, &map_v_lo, &v_full[st], 0, k0, bh);
             } else {
-                tma_load_3d(vs, &map_v_hi, &v_full[st], k0, 0, bh);
-                tma_load_3d(vs + C::V_BYTES / 2, &map_v_hi, &v_full[st], k0 + 64, 0, bh);
-                if (SPLIT == 3) {
-                    tma_load_3d(vs + C::V_BYTES, &map_v_lo, &v_full[st], k0, 0, bh);
-                    tma_load_3d(vs + C::V_BYTES + C::V_BYTES / 2, &map_v_lo, &v_full[st], k0 + 64, 0, bh);
+#pragma unroll
+                for (int hb = 0; hb < BKV / 64; ++hb) {
+                    tma_load_3d(vs + hb * C::VBOX_BYTES, &map_v_hi, &v_full[st], k0 + 64 * hb, 0, bh);
+                    if (SPLIT == 3) tma_load_3d(vs + C::V_BYTES + hb * C::VBOX_BYTES, &map_v_lo, &v_full[st], k0 + 64 * hb, 0, bh);
                 }
             }
         };
@@ -306,8 +322,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                 const uint32_t p_col = tmem_base + (st ? COL_S1 : COL_S0);
 #pragma unroll
                 for (int ks = 0; ks < BKV / 16; ++ks) {
-                    const uint32_t vo = p.v_mn ? ks * 2048 : (ks >> 2) * (C::V_BYTES / 2) + (ks & 3) * 32;
-                    const uint32_t a_hi = p_col + ks * 8, a_lo = p_col + 64 + ks * 8;
+                    const uint32_t vo = p.v_mn ? ks * 2048 : (ks >> 2) * C::VBOX_BYTES + (ks & 3) * 32;
+                    const uint32_t a_hi = p_col + ks * 8, a_lo = p_col + BKV / 2 + ks * 8;
                     const uint64_t bh_d = p.v_mn ? make_desc_mn(v_hi + vo) : make_desc(v_hi + vo);
                     umma_ts(d, a_hi, bh_d, idesc_o, (j | ks) != 0);
                     if (SPLIT == 3) {
@@ -363,7 +379,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                 float* x = xch + (g & 1) * (NPART * 128);
                 x[part * 128 + r] = mx;
                 asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NPART) : "memory");
-                mx = fmaxf(fmaxf(x[r], x[128 + r]), fmaxf(x[256 + r], x[384 + r]));
+                mx = x[r];
+#pragma unroll
+                for (int q2 = 1; q2 < NPART; ++q2) mx = fmaxf(mx, x[q2 * 128 + r]);
                 // lazy rescale: keep the stale reference max unless it moved by more than 8 (log2 units)
                 const bool need = (mx > m_used + 8.f);
                 const bool warp_need = __any_sync(0xffffffffu, need) || (j == 0);
@@ -397,16 +415,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                     mbar_wait(&o_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
                     tc_fence_after();
                     const uint32_t o_addr = tmem_base + lane_off + COL_O + part * OPT;
-                    uint32_t o[16];
-                    tmem_ld16(o_addr, o);
+                    uint32_t o[OPT];
+                    tmem_ldN(o_addr, o);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-                    tmem_st16(o_addr, o);
+                    for (int i = 0; i < OPT; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+                    tmem_stN(o_addr, o);
                 }
                 // P over S, in place: all four warps of this lane quarter loaded their scores before the bar.sync above
                 const uint32_t p_addr = tmem_base + lane_off + (st ? COL_S1 : COL_S0) + part * (CPT / 2);
                 tmem_st16(p_addr, ph);
-                if (SPLIT == 3) tmem_st16(p_addr + 64, pl);
+                if (SPLIT == 3) tmem_st16(p_addr + BKV / 2, pl);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -416,28 +434,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
             float* x = xch + (g & 1) * (NPART * 128);
             x[part * 128 + r] = l;
             asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NPART) : "memory");
-            const float inv = 1.f / ((x[r] + x[128 + r]) + (x[256 + r] + x[384 + r]));
+            float lsum_all = x[r];
+#pragma unroll
+            for (int q2 = 1; q2 < NPART; ++q2) lsum_all += x[q2 * 128 + r];
+            const float inv = 1.f / lsum_all;
             mbar_wait(&o_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
             tc_fence_after();
             const int qn = q0 + r;
             const int b = bh / p.heads, hh = bh - b * p.heads;
             const long long orow = ((long long)b * p.Nq + qn) * p.out_ld + hh * HD + part * OPT;
             {
-                uint32_t v[16];
-                tmem_ld16(tmem_base + lane_off + COL_O + part * OPT, v);
+                uint32_t v[OPT];
+                tmem_ldN(tmem_base + lane_off + COL_O + part * OPT, v);
                 if (qn < p.Nq) {
-                    float f[16];
+                    float f[OPT];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * inv;
+                    for (int i = 0; i < OPT; ++i) f[i] = __uint_as_float(v[i]) * inv;
                     if (p.out_f32) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4)
+                        for (int i = 0; i < OPT; i += 4)
                             *reinterpret_cast<float4*>(p.out_f32 + orow + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
                     }
                     if (p.out_hi) {
-                        uint32_t hi[8], lo[8];
+                        uint32_t hi[OPT / 2], lo[OPT / 2];
 #pragma unroll
-                        for (int i = 0; i < 16; i += 2) {
+                        for (int i = 0; i < OPT; i += 2) {
                             __nv_bfloat162 h2 = __floats2bfloat162_rn(f[i], f[i + 1]);
                             const uint32_t u = *reinterpret_cast<uint32_t*>(&h2);
                             hi[i >> 1] = u;
@@ -446,11 +467,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_tc_kernel(
                         }
                         uint4* oh = reinterpret_cast<uint4*>(p.out_hi + orow);
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                        for (int i = 0; i < OPT / 8; ++i) oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
                         if (p.out_lo) {
                             uint4* ol = reinterpret_cast<uint4*>(p.out_lo + orow);
 #pragma unroll
-                            for (int i = 0; i < 2; ++i) ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                            for (int i = 0; i < OPT / 8; ++i) ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
                         }
                     }
                 }
@@ -509,7 +530,7 @@ PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k
     using namespace fa;
     if (!q_hi || !k_hi || !vt_hi || B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return PRAM_ERR_ARG;
     if (split != 1 && split != 3) return PRAM_ERR_ARG;
-    if (p_swap) return PRAM_ERR_UNSUPPORTED;  // former debug knob of the P packing order; kept in the ABI, must be 0
+    if (p_swap != 0 && p_swap != 64 && p_swap != 128) return PRAM_ERR_ARG;  // key-tile variant: 0 = auto, 64, 128
     if (split == 3 && (!q_lo || !k_lo || !vt_lo)) return PRAM_ERR_ARG;
     if ((!v_mn && ((nk_pad % 8) || nk_pad < Nk)) || (out_ld % 8)) return PRAM_ERR_UNSUPPORTED;
     static int num_sms = 0;
@@ -523,12 +544,14 @@ PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k
     const void* qs[2] = {q_hi, q_lo ? q_lo : q_hi};
     const void* ks[2] = {k_hi, k_lo ? k_lo : k_hi};
     const void* vs[2] = {vt_hi, vt_lo ? vt_lo : vt_hi};
+    // key-tile variant: 64 (two CTAs per SM, out of phase) unless asked otherwise
+    const int bkv = (p_swap == 128) ? 128 : 64;
     for (int i = 0; i < 2; ++i) {
         int rc = encode3(&mq[i], qs[i], HD, Nq, BH, HD * 2, (cuuint64_t)Nq * HD * 2, HD, BQ);
         if (rc) return rc;
-        rc = encode3(&mk[i], ks[i], HD, Nk, BH, HD * 2, (cuuint64_t)Nk * HD * 2, HD, BKV);
+        rc = encode3(&mk[i], ks[i], HD, Nk, BH, HD * 2, (cuuint64_t)Nk * HD * 2, HD, bkv);
         if (rc) return rc;
-        if (v_mn) rc = encode3(&mv[i], vs[i], HD, Nk, BH, HD * 2, (cuuint64_t)Nk * HD * 2, HD, BKV);
+        if (v_mn) rc = encode3(&mv[i], vs[i], HD, Nk, BH, HD * 2, (cuuint64_t)Nk * HD * 2, HD, bkv);
         else rc = encode3(&mv[i], vs[i], nk_pad, HD, BH, (cuuint64_t)nk_pad * 2, (cuuint64_t)nk_pad * HD * 2, 64, HD);
         if (rc) return rc;
     }
@@ -538,18 +561,18 @@ PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k
     a.out_f32 = out_f32; a.out_hi = (__nv_bfloat16*)out_hi; a.out_lo = (__nv_bfloat16*)out_lo; a.out_ld = out_ld;
     a.v_mn = v_mn;
     const int total = BH * ((Nq + BQ - 1) / BQ);
-    const int grid = total < num_sms ? total : num_sms;
-    if (split == 3) {
-        auto kern = attention_tc_kernel<3>;
-        static bool attr = false;
-        if (!attr) { PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::SMEM_BYTES)); attr = true; }
-        kern<<<grid, NUM_THREADS, Cfg<3>::SMEM_BYTES, stream>>>(mq[0], mq[1], mk[0], mk[1], mv[0], mv[1], a);
-    } else {
-        auto kern = attention_tc_kernel<1>;
-        static bool attr = false;
-        if (!attr) { PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES)); attr = true; }
-        kern<<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, stream>>>(mq[0], mq[1], mk[0], mk[1], mv[0], mv[1], a);
-    }
+#define PRAM_ATT_LAUNCH(SPLIT_, BKV_)                                                                                   \
+    do {                                                                                                                \
+        auto kern = attention_tc_kernel<SPLIT_, BKV_>;                                                                  \
+        static bool attr = false;                                                                                       \
+        if (!attr) { PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<SPLIT_, BKV_>::SMEM_BYTES)); attr = true; } \
+        const int cap = Geo<BKV_>::CTAS_PER_SM * num_sms;                                                               \
+        const int grid = total < cap ? total : cap;                                                                     \
+        kern<<<grid, Geo<BKV_>::NUM_THREADS, Cfg<SPLIT_, BKV_>::SMEM_BYTES, stream>>>(mq[0], mq[1], mk[0], mk[1], mv[0], mv[1], a); \
+    } while (0)
+    if (split == 3) { if (bkv == 128) PRAM_ATT_LAUNCH(3, 128); else PRAM_ATT_LAUNCH(3, 64); }
+    else { if (bkv == 128) PRAM_ATT_LAUNCH(1, 128); else PRAM_ATT_LAUNCH(1, 64); }
+#undef PRAM_ATT_LAUNCH
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
 }

@@ -394,7 +394,7 @@ def layernorm_gelu_split(x: Tensor, gamma: Tensor, beta: Tensor, c: int, out: Sp
 
 # ---- tensor-core flash attention ---------------------------------------------------------------------
 
-P_SWAP = 0  # reserved ABI argument of pram_attention_tc (former debug knob); must stay 0
+ATT_KV_TILE = int(_os.environ.get('PRAM_ATT_KV_TILE', '0'))  # key-tile variant of pram_attention_tc: 0 = auto, 64, 128
 
 
 def attention_prep(qkv: Tensor, nparts: int, b: int, n: int, heads: int, cos: Optional[Tensor], sin: Optional[Tensor],
@@ -418,7 +418,7 @@ def attention_tc(q: Split, k: Split, vt: Split, b: int, heads: int, nq: int, nk:
     """``vt`` is V^T [b*heads, 64, nk_pad] (v_mn=False) or V itself [b*heads, nk, 64] (v_mn=True)."""
     call('pram_attention_tc', ptr(q.hi), ptr(q.lo), ptr(k.hi), ptr(k.lo), ptr(vt.hi), ptr(vt.lo), b, heads, nq, nk, nk_pad,
          float(scale), ptr(out_f32), ptr(out_bf.hi) if out_bf is not None else None,
-         ptr(out_bf.lo) if (out_bf is not None and out_bf.lo is not None) else None, out_ld, split, P_SWAP, int(v_mn),
+         ptr(out_bf.lo) if (out_bf is not None and out_bf.lo is not None) else None, out_ld, split, ATT_KV_TILE, int(v_mn),
          stream_ptr())
 
 

@@ -250,3 +250,34 @@ def test_conv1a_tc(ops, dev, split, b, h, w):
     tol = TOL[split] if split == 3 else 3e-2
     assert _relerr(outs[False], ref) < tol
     assert _relerr(outs[True], ref) < tol
+
+
+@pytest.mark.parametrize('kv_tile', [64, 128])
+@pytest.mark.parametrize('b,nq,nk', [(1, 128, 128), (2, 75, 130), (1, 1024, 1024), (2, 300, 1000), (1, 4096, 1024)])
+def test_attention_tc_kv_tile_variants(ops, dev, kv_tile, b, nq, nk):
+    """Both key-tile variants of the flash-attention kernel (64: two CTAs per SM, 128: one) vs torch fp32."""
+    g = torch.Generator().manual_seed(nq + nk + kv_tile)
+    h = 4
+    q, k, v = (torch.randn(b, h, n, 64, generator=g) for n in (nq, nk, nk))
+    attn = torch.softmax(torch.einsum('bhid,bhjd->bhij', q, k) * 0.125, -1)
+    ref = torch.einsum('bhij,bhjd->bhid', attn, v).transpose(1, 2).flatten(-2)
+    Q = ops.split_bf16(q.reshape(b * h, nq, 64).to(dev), True)
+    K = ops.split_bf16(k.reshape(b * h, nk, 64).to(dev), True)
+    V = ops.split_bf16(v.reshape(b * h, nk, 64).to(dev), True)
+    nk_pad = (nk + 7) // 8 * 8
+    vt = torch.zeros(b, h, 64, nk_pad)
+    vt[..., :nk] = v.transpose(-1, -2)
+    VT = ops.split_bf16(vt.reshape(b * h, 64, nk_pad).to(dev), True)
+    ops.ATT_KV_TILE = kv_tile
+    try:
+        out = torch.zeros(b, nq, 256, device=dev)
+        obf = ops.empty_split((b, nq, 256), dev, True)
+        ops.attention_tc(Q, K, V, b, h, nq, nk, nk, 0.125, out, obf, 256, 3, v_mn=True)
+        out2 = torch.zeros(b, nq, 256, device=dev)
+        ops.attention_tc(Q, K, VT, b, h, nq, nk, nk_pad, 0.125, out2, None, 256, 3)
+        torch.cuda.synchronize()
+    finally:
+        ops.ATT_KV_TILE = 0
+    assert _relerr(out.cpu(), ref) < 2e-4
+    assert _relerr(obf.float().cpu(), ref) < 2e-4
+    assert _relerr(out2.cpu(), ref) < 2e-4, 'V^T (K-major) operand path'
