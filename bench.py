@@ -20,7 +20,22 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 H, W, KPTS, NCLASS = 480, 640, 1024, 113
+FOCAL, MAX_ERROR = 525.0, 8.0
 METRIC = 'localization frames/sec (640x480, 1024 kpts)'
+# BASELINE.json configs: the metric is quoted on the 7Scenes shape; the other two are extra workloads (--workload)
+WORKLOADS = {
+    '7scenes': dict(h=480, w=640, kpts=1024, nclass=113, focal=525.0, max_error=8.0, batch=32),      # configs[1] / [2]
+    'cambridge': dict(h=768, w=1024, kpts=2048, nclass=161, focal=800.0, max_error=12.0, batch=16),  # configs[3]
+    'aachen': dict(h=1200, w=1600, kpts=4096, nclass=513, focal=1200.0, max_error=12.0, batch=8),    # configs[4]
+}
+
+
+def set_workload(name, batch):
+    global H, W, KPTS, NCLASS, FOCAL, MAX_ERROR, METRIC
+    wl = WORKLOADS[name]
+    H, W, KPTS, NCLASS, FOCAL, MAX_ERROR = wl['h'], wl['w'], wl['kpts'], wl['nclass'], wl['focal'], wl['max_error']
+    METRIC = f'localization frames/sec ({W}x{H}, {KPTS} kpts)'
+    return batch if batch > 0 else wl['batch']
 
 
 def parse():
@@ -29,7 +44,8 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=32, help='frames per GPU per step')
+    ap.add_argument('--batch', type=int, default=0, help='frames per GPU per step (default: 32 for the 7Scenes workload)')
+    ap.add_argument('--workload', default='7scenes', choices=list(WORKLOADS), help='7scenes = the BASELINE.json metric config')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying a CUDA graph')
@@ -37,8 +53,8 @@ def parse():
 
 
 def workload_name(batch):
-    return (f'full pipeline, 7Scenes-shaped synthetic stream: SFD2 + SegNetViT(113 classes, 15 layers) + GML(9 layers, '
-            f'Sinkhorn 20, one matcher call per frame) + PnP/RANSAC(1024 hypotheses, max_error 8 px), '
+    return (f'full pipeline, synthetic {W}x{H} stream: SFD2 + SegNetViT({NCLASS} classes, 15 layers) + GML(9 layers, '
+            f'Sinkhorn 20, one matcher call per frame, {KPTS} keypoints) + PnP/RANSAC(1024 hypotheses, max_error {MAX_ERROR:g} px), '
             f'{batch} frames/GPU/step')
 
 
@@ -122,9 +138,9 @@ def cpu_chain(frames_cpu, sd_sfd2, sd_vit, sd_gml, perm):
             if ok.sum() >= 4:
                 kq = k.numpy()[ok].astype(np.float64) + 0.5
                 z = 1.0 + 4.0 * np.random.RandomState(0).rand(int(ok.sum()))
-                X = np.stack([(kq[:, 0] - W / 2) / 525.0 * z, (kq[:, 1] - H / 2) / 525.0 * z, z], 1)
-                Kc = np.array([[525.0, 0, W / 2], [0, 525.0, H / 2], [0, 0, 1.0]])
-                cv2.solvePnPRansac(X, kq, Kc, None, reprojectionError=8.0, iterationsCount=1000, flags=cv2.SOLVEPNP_P3P)
+                X = np.stack([(kq[:, 0] - W / 2) / FOCAL * z, (kq[:, 1] - H / 2) / FOCAL * z, z], 1)
+                Kc = np.array([[FOCAL, 0, W / 2], [0, FOCAL, H / 2], [0, 0, 1.0]])
+                cv2.solvePnPRansac(X, kq, Kc, None, reprojectionError=MAX_ERROR, iterationsCount=1000, flags=cv2.SOLVEPNP_P3P)
 
 
 def time_cpu(n_frames, reps):
@@ -201,7 +217,7 @@ def run_ours(args):
     gml = GML({}); gml.load_state_dict(sd_gml, strict=True)
     for m_ in (sfd2, vit, gml):
         m_.set_precision(args.precision)
-    pipe = LocalizationPipeline(sfd2, vit, gml, max_keypoints=KPTS, device=dev)
+    pipe = LocalizationPipeline(sfd2, vit, gml, max_keypoints=KPTS, focal=FOCAL, ransac_max_error=MAX_ERROR, device=dev)
 
     B = args.batch
     frames_host = make_frames(B, seed0=rank * B).pin_memory()
@@ -374,7 +390,7 @@ def roofline_probe(pipe, frames_dev, dev):
     # DRAM traffic of the same launch from the committed `ncu --set full` capture (profiles/), B=32 bf16x3 only
     traffic = None
     prof = ROOT / 'profiles' / 'r01_ncu_full_conv3b_attention_v6_summary.csv'
-    if prof.exists() and B == 32 and prec == 'bf16x3':
+    if prof.exists() and B == 32 and (H, W) == (480, 640) and prec == 'bf16x3':
         import csv
         rows = list(csv.reader(open(prof)))
         hdr = rows[0]
@@ -391,6 +407,7 @@ def roofline_probe(pipe, frames_dev, dev):
 
 if __name__ == '__main__':
     a = parse()
+    a.batch = set_workload(a.workload, a.batch)
     if a.impl == 'reference':
         run_reference(a)
     else:
