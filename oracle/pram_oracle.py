@@ -814,3 +814,37 @@ def nearest_neighbor_forward(desc0: Tensor, desc1: Tensor, ratio_threshold=None,
         ok = (m0 > -1) & (inds0 == loop)
         m0 = torch.where(ok, m0, m0.new_tensor(-1))
     return {'matches0': m0, 'matching_scores0': s0, 'sim': sim}
+
+
+def select_with_mask_loops(keypoints, scores, descriptors, mask, topK=-1):
+    """Literal restatement of the mask branch of extract_sfd2_return (reference nets/sfd2.py:502-571, with its
+    ``np.float`` spelled ``float``): per-keypoint Python loops, kept as the checker of the vectorised product code."""
+    labels, others = [], []
+    kw, sw, dw, ko, so, do = [], [], [], [], [], []
+    id_img = np.int32(mask[:, :, 2]) * 256 * 256 + np.int32(mask[:, :, 1]) * 256 + np.int32(mask[:, :, 0])
+    for i in range(keypoints.shape[0]):
+        x, y = keypoints[i, 0], keypoints[i, 1]
+        gid = id_img[int(y), int(x)]
+        if gid == 0:
+            ko.append(keypoints[i]); so.append(scores[i]); do.append(descriptors[i]); others.append(0)
+        else:
+            kw.append(keypoints[i]); sw.append(scores[i]); dw.append(descriptors[i]); labels.append(gid)
+    if topK > 0:
+        if topK <= len(kw):
+            idxes = np.array(sw, float).argsort()[::-1][:topK]
+            keypoints = np.array(kw, float)[idxes]
+            scores = np.array(sw, float)[idxes]
+            labels = np.array(labels, np.int32)[idxes]
+            descriptors = np.array(dw, float)[idxes]
+        elif topK >= len(kw) + len(ko):
+            keypoints, scores, descriptors = kw, sw, dw
+            for i in range(len(others)):
+                keypoints.append(ko[i]); scores.append(so[i]); descriptors.append(do[i]); labels.append(others[i])
+        else:
+            n = topK - len(kw)
+            idxes = np.array(so, float).argsort()[::-1][:n]
+            keypoints, scores, descriptors = kw, sw, dw
+            for i in idxes:
+                keypoints.append(ko[i]); scores.append(so[i]); descriptors.append(do[i]); labels.append(others[i])
+    return {'keypoints': np.array(keypoints, float), 'descriptors': np.array(descriptors, float),
+            'scores': np.array(scores, float), 'labels': np.array(labels, np.int32)}

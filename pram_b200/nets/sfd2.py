@@ -305,9 +305,8 @@ def extract_sfd2_return(model: ResNet4x, img: torch.Tensor, conf_th: float = 0.0
                         min_keypoints: int = 0, **kwargs):
     """Offline-export variant (reference nets/sfd2.py:386-589): NMS radius 3, strict ``>`` threshold,
     score-descending order, border 4, sampling with x/(w/2)-1, float64 numpy outputs.
-    ``img``: [1,3,H,W] (or [3,H,W]) RGB in [0,1], not normalised.  ``mask`` is not supported."""
-    if mask is not None:
-        raise NotImplementedError('mask-guided selection (reference nets/sfd2.py:502-571) is out of scope')
+    ``img``: [1,3,H,W] (or [3,H,W]) RGB in [0,1], not normalised.  ``mask`` ([H,W,3] uint8 label image, BGR-packed
+    ids) selects labelled keypoints first (reference nets/sfd2.py:502-571; host-side numpy like the reference)."""
     dev = next(model.parameters()).device
     x = img.reshape(1, 3, img.shape[-2], img.shape[-1]).to(dev).float()
     mean = torch.tensor(RGB_mean, device=dev).view(1, 3, 1, 1)
@@ -345,11 +344,38 @@ def extract_sfd2_return(model: ResNet4x, img: torch.Tensor, conf_th: float = 0.0
     pts = np.vstack(all_pts)
     desc = np.vstack(all_desc)
     keypoints, scores = pts[:, :2], pts[:, 2]
+    if mask is not None:
+        return select_with_mask(keypoints, scores, desc, mask, topK)
     if topK > 0:
         idx = np.array(scores, dtype=float).argsort()[::-1][:topK]
         keypoints, scores, desc = keypoints[idx], scores[idx], desc[idx]
     return {'keypoints': np.array(keypoints, dtype=float), 'descriptors': np.array(desc, dtype=float),
             'scores': np.array(scores, dtype=float)}
+
+
+def select_with_mask(keypoints: np.ndarray, scores: np.ndarray, descriptors: np.ndarray, mask: np.ndarray, topK: int = -1):
+    """Mask-guided selection of the export path (reference nets/sfd2.py:502-571), vectorised: keypoints on a labelled
+    pixel (id = B + 256 G + 65536 R of ``mask[int(y), int(x)]`` != 0) come first; ``topK`` keeps the best labelled
+    ones, or all labelled ones plus the best unlabelled ones.  Same outputs and orders as the reference's loops
+    (including its ``topK <= 0`` quirk: every keypoint is returned, ``labels`` only covers the labelled ones)."""
+    id_img = np.int32(mask[:, :, 2]) * 256 * 256 + np.int32(mask[:, :, 1]) * 256 + np.int32(mask[:, :, 0])
+    gid = id_img[keypoints[:, 1].astype(int), keypoints[:, 0].astype(int)]
+    w_idx, o_idx = np.nonzero(gid != 0)[0], np.nonzero(gid == 0)[0]
+    labels = gid[w_idx]
+    if topK > 0:
+        if topK <= w_idx.size:
+            sel = w_idx[np.array(scores[w_idx], float).argsort()[::-1][:topK]]
+            labels = gid[sel]
+        elif topK >= w_idx.size + o_idx.size:
+            sel = np.concatenate([w_idx, o_idx])
+            labels = np.concatenate([labels, np.zeros(o_idx.size, labels.dtype)])
+        else:
+            extra = o_idx[np.array(scores[o_idx], float).argsort()[::-1][:topK - w_idx.size]]
+            sel = np.concatenate([w_idx, extra])
+            labels = np.concatenate([labels, np.zeros(extra.size, labels.dtype)])
+        keypoints, scores, descriptors = keypoints[sel], scores[sel], descriptors[sel]
+    return {'keypoints': np.array(keypoints, float), 'descriptors': np.array(descriptors, float),
+            'scores': np.array(scores, float), 'labels': np.array(labels, np.int32)}
 
 
 def _sample_at_map_coords(desc_nhwc: torch.Tensor, pix: torch.Tensor) -> torch.Tensor:
