@@ -162,6 +162,10 @@ __device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&r)[16]) { tm
 __device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
 __device__ __forceinline__ void tmem_stN(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st16(taddr, r); }
 __device__ __forceinline__ void tmem_stN(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st32(taddr, r); }
+// explicit shared-space accessors for the row max / row sum exchange (the pointer is derived from the manually aligned
+// dynamic shared-memory base, so the compiler would otherwise emit generic LD / ST)
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -347,7 +351,7 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
         const int qd = warp & 3, part = (warp - 2) >> 2;
         const int r = qd * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        float* xch = reinterpret_cast<float*>(tmem_base_s + 4);  // [2 parity][NPART][128 rows]
+        const uint32_t xch = smem_u32(tmem_base_s + 4);  // float [2 parity][NPART][128 rows]
         const uint32_t bar_id = 1 + qd;
         uint32_t g = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x) {
@@ -376,12 +380,12 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
                 }
                 float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
                 mx *= p.scale_log2;  // scale > 0
-                float* x = xch + (g & 1) * (NPART * 128);
-                x[part * 128 + r] = mx;
+                const uint32_t x = xch + (uint32_t)((g & 1) * (NPART * 128) + r) * 4u;
+                sts_f32(x + part * 512, mx);
                 asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NPART) : "memory");
-                mx = x[r];
+                mx = lds_f32(x);
 #pragma unroll
-                for (int q2 = 1; q2 < NPART; ++q2) mx = fmaxf(mx, x[q2 * 128 + r]);
+                for (int q2 = 1; q2 < NPART; ++q2) mx = fmaxf(mx, lds_f32(x + q2 * 512));
                 // lazy rescale: keep the stale reference max unless it moved by more than 8 (log2 units)
                 const bool need = (mx > m_used + 8.f);
                 const bool warp_need = __any_sync(0xffffffffu, need) || (j == 0);
@@ -431,12 +435,12 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
                 if (lane == 0) mbar_arrive(&p_full[st]);
             }
             // epilogue: O / l (row sum over the four parts), each warp stores 16 of the 64 head dims
-            float* x = xch + (g & 1) * (NPART * 128);
-            x[part * 128 + r] = l;
+            const uint32_t x = xch + (uint32_t)((g & 1) * (NPART * 128) + r) * 4u;
+            sts_f32(x + part * 512, l);
             asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NPART) : "memory");
-            float lsum_all = x[r];
+            float lsum_all = lds_f32(x);
 #pragma unroll
-            for (int q2 = 1; q2 < NPART; ++q2) lsum_all += x[q2 * 128 + r];
+            for (int q2 = 1; q2 < NPART; ++q2) lsum_all += lds_f32(x + q2 * 512);
             const float inv = 1.f / lsum_all;
             mbar_wait(&o_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
             tc_fence_after();

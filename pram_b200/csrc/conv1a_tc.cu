@@ -79,6 +79,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// explicit shared-space 16-byte accessors (the tile pointers come from the manually aligned dynamic shared-memory base)
+__device__ __forceinline__ void sts_u4(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
@@ -124,8 +134,8 @@ __global__ void __launch_bounds__(TM, 4) conv1a_tc_kernel(const float* __restric
             split2(w0, w1, hi[i >> 1], lo[i >> 1]);
         }
         const int off = n * ROW_BYTES + ((j ^ (n & 7)) << 4);
-        *reinterpret_cast<uint4*>(b_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(b_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        sts_u4(smem_u32(b_hi) + off, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+        sts_u4(smem_u32(b_lo) + off, make_uint4(lo[0], lo[1], lo[2], lo[3]));
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
@@ -133,6 +143,7 @@ __global__ void __launch_bounds__(TM, 4) conv1a_tc_kernel(const float* __restric
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
     constexpr uint32_t idesc = make_idesc(TM, NOUT);
+    const uint32_t sa_hi_g = smem_u32(a_hi), sa_lo_g = smem_u32(a_lo), bias_a = smem_u32(bias_s);
 
     const int tiles_x = (W + TM - 1) / TM;
     const long long total = (long long)B * H * tiles_x;
@@ -164,8 +175,8 @@ __global__ void __launch_bounds__(TM, 4) conv1a_tc_kernel(const float* __restric
 #pragma unroll
                 for (int i = 0; i < 4; ++i) split2(v[8 * j + 2 * i], v[8 * j + 2 * i + 1], hi[i], lo[i]);
                 const int off = t * ROW_BYTES + ((j ^ (t & 7)) << 4);
-                *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                if (SPLIT == 3) *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                sts_u4(sa_hi_g + off, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+                if (SPLIT == 3) sts_u4(sa_lo_g + off, make_uint4(lo[0], lo[1], lo[2], lo[3]));
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
@@ -198,14 +209,14 @@ __global__ void __launch_bounds__(TM, 4) conv1a_tc_kernel(const float* __restric
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int co = hc * 32 + 8 * j + 2 * i;
-                    const float f0 = fmaxf(__uint_as_float(acc[8 * j + 2 * i]) + bias_s[co], 0.f);
-                    const float f1 = fmaxf(__uint_as_float(acc[8 * j + 2 * i + 1]) + bias_s[co + 1], 0.f);
+                    const float f0 = fmaxf(__uint_as_float(acc[8 * j + 2 * i]) + lds_f32(bias_a + 4 * co), 0.f);
+                    const float f1 = fmaxf(__uint_as_float(acc[8 * j + 2 * i + 1]) + lds_f32(bias_a + 4 * co + 4), 0.f);
                     split2(f0, f1, hi[i], lo[i]);
                 }
                 const int ch = hc * 4 + j;  // 16-byte chunk (8 channels) of this pixel's 128-byte line
                 const int off = t * ROW_BYTES + ((ch ^ (t & 7)) << 4);
-                *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                if (SPLIT == 3) *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                sts_u4(sa_hi_g + off, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+                if (SPLIT == 3) sts_u4(sa_lo_g + off, make_uint4(lo[0], lo[1], lo[2], lo[3]));
             }
         }
         tc_fence_before();  // accumulator reads ordered before the next tile's MMA
@@ -218,8 +229,8 @@ __global__ void __launch_bounds__(TM, 4) conv1a_tc_kernel(const float* __restric
             if (xx < W) {
                 const long long off = ((((long long)(b * 4 + (y & 1) * 2 + (xx & 1))) * Hp + (y >> 1)) * Wp + (xx >> 1)) * 64 + ch * 8;
                 const int so = px * ROW_BYTES + ((ch ^ (px & 7)) << 4);
-                *reinterpret_cast<uint4*>(ps_hi + off) = *reinterpret_cast<const uint4*>(a_hi + so);
-                if (SPLIT == 3) *reinterpret_cast<uint4*>(ps_lo + off) = *reinterpret_cast<const uint4*>(a_lo + so);
+                *reinterpret_cast<uint4*>(ps_hi + off) = lds_u4(sa_hi_g + so);
+                if (SPLIT == 3) *reinterpret_cast<uint4*>(ps_lo + off) = lds_u4(sa_lo_g + so);
             }
         }
         __syncthreads();  // staging reads done before the next tile's im2col rows overwrite the region

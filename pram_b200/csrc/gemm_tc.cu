@@ -170,6 +170,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// Explicit shared-space accessors for the epilogue staging tile and row tables.  The staging pointers are derived
+// from the manually 1024-byte-aligned dynamic shared-memory base (integer arithmetic), so the compiler no longer
+// knows their address space and emits GENERIC LD / ST (ncu: long-scoreboard stalls on every staged value, lg-throttle
+// on the stores); these force LDS / STS.
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ int lds32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
     hi = __float2bfloat16_rn(v);
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
@@ -333,8 +352,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
         const int q = warp & 3, half = (warp - 2) >> 2;
         const int r = q * 32 + lane;  // row of the tile == TMEM lane
         uint8_t* epi_base = smem + C::STAGES * C::STAGE_BYTES + 256;
-        float* tile_s = reinterpret_cast<float*>(epi_base) + (warp - 2) * 1024;             // [32][32] swizzled
-        EpiQuarter& eq = reinterpret_cast<EpiQuarter*>(epi_base + 8 * 4096)[q];
+        const uint32_t tile_a = smem_u32(epi_base) + (uint32_t)(warp - 2) * 4096u;          // [32][32] fp32, swizzled
+        // per-quarter row tables (struct EpiQuarter): pix / pix_ps / inv, 32 entries each
+        const uint32_t eq_pix = smem_u32(epi_base + 8 * 4096) + (uint32_t)q * (uint32_t)sizeof(EpiQuarter), eq_ps = eq_pix + 128u, eq_inv = eq_pix + 256u;
         const float* __restrict__ resp = p.res;
         const float* __restrict__ biasp = p.bias;
         const bool res_vec = ((p.res_ld & 3) == 0);
@@ -349,15 +369,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                 const int y = tyi * TH + (r >> p.tw_log2), x = txi * TW + (r & (TW - 1));
                 const bool valid = (y < p.Ho) && (x < p.Wo) && (mt < m_tiles);
                 const int Hp = (p.Ho + 1) >> 1, Wp = (p.Wo + 1) >> 1;
-                eq.pix[lane] = valid ? (int)(((long long)b * p.Ho + y) * p.Wo + x) : -1;
-                eq.pix_ps[lane] = (int)((((long long)(b * 4 + (y & 1) * 2 + (x & 1))) * Hp + (y >> 1)) * Wp + (x >> 1));
+                sts32(eq_pix + 4 * lane, valid ? (int)(((long long)b * p.Ho + y) * p.Wo + x) : -1);
+                sts32(eq_ps + 4 * lane, (int)((((long long)(b * 4 + (y & 1) * 2 + (x & 1))) * Hp + (y >> 1)) * Wp + (x >> 1)));
                 if (MODE == 2) {  // rows are tokens (Linear): token -> (segment, batch element, position)
                     const int t = x;
                     const bool s1 = t >= p.seg_split;
                     const int ns = s1 ? p.seg_n1 : p.seg_n0, tt = s1 ? t - p.seg_split : t;
                     const int bb = tt / ns, nn = tt - bb * ns;
-                    eq.pix_ps[lane] = (s1 ? p.seg_split * p.heads * 64 : 0) + (bb * p.heads * ns + nn) * 64;
-                    eq.inv[lane] = __int_as_float(ns * 64);
+                    sts32(eq_ps + 4 * lane, (s1 ? p.seg_split * p.heads * 64 : 0) + (bb * p.heads * ns + nn) * 64);
+                    sts32(eq_inv + 4 * lane, ns * 64);
                 }
             }
             // the two warps of a quarter exchange the row table through a named barrier (id 1 + q, 64 threads)
@@ -366,7 +386,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                 if constexpr (MODE != 1) return;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int pixr = eq.pix[i * 4 + g1];
+                    const int pixr = lds32(eq_pix + 4 * (i * 4 + g1));
                     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (resp && pixr >= 0 && nb < p.N) {
                         const float* rp = resp + (long long)pixr * p.res_ld + nb + col1;
@@ -392,7 +412,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                 const int pr0 = (half * 32 + col1) >> 1;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int pixr = eq.pix[i * 4 + g1];
+                    const int pixr = lds32(eq_pix + 4 * (i * 4 + g1));
                     rot_c[i] = make_float2(1.f, 1.f);
                     rot_s[i] = make_float2(0.f, 0.f);
                     if (rot && pixr >= 0) {
@@ -419,7 +439,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                         }
                     }
                 }
-                if (half == 0) eq.inv[lane] = fmaxf(sqrtf(ss), 1e-12f);
+                if (half == 0) sts32(eq_inv + 4 * lane, __float_as_int(fmaxf(sqrtf(ss), 1e-12f)));
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
             }
             for (int c = half * 32; c < BN; c += 64) {
@@ -429,11 +449,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                 {
                     uint32_t v[32];
                     tmem_ld32(taddr + c, v);
-                    float4* trow = reinterpret_cast<float4*>(tile_s + lane * 32);
+                    const uint32_t trow = tile_a + (uint32_t)lane * 128u;
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4)  // 16-byte chunk j4 of row `lane` lives at chunk position j4 ^ (lane & 7)
-                        trow[j4 ^ (lane & 7)] = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
-                                                            __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
+                        sts128(trow + (uint32_t)((j4 ^ (lane & 7)) << 4), make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
+                                                                              __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])));
                 }
                 float4 rcur[MODE == 1 ? 8 : 1];
                 if constexpr (MODE == 1) {
@@ -450,9 +470,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int row = i * 4 + g1;
-                        const int pixr = eq.pix[row];
-                        float4* tp = reinterpret_cast<float4*>(tile_s + row * 32) + ((col1 >> 2) ^ (row & 7));
-                        const float4 tv = *tp;
+                        const int pixr = lds32(eq_pix + 4 * row);
+                        const uint32_t tp = tile_a + (uint32_t)row * 128u + (uint32_t)((((col1 >> 2) ^ (row & 7))) << 4);
+                        const float4 tv = lds128(tp);
                         float f[4] = {tv.x + bz[0], tv.y + bz[1], tv.z + bz[2], tv.w + bz[3]};
                         if constexpr (MODE == 1) { f[0] += rcur[i].x; f[1] += rcur[i].y; f[2] += rcur[i].z; f[3] += rcur[i].w; }
                         if (MODE == 2 && pixr >= 0) {
@@ -473,7 +493,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                             for (int k = 0; k < 4; ++k) f[k] = fmaxf(f[k], 0.f);
                         }
                         if (p.l2norm) {
-                            const float d = eq.inv[row];
+                            const float d = __int_as_float(lds32(eq_inv + 4 * row));
 #pragma unroll
                             for (int k = 0; k < 4; ++k) f[k] = f[k] / d;
                         }
@@ -486,7 +506,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                                 for (int k = 0; k < 4; ++k) if (nb + col1 + k < p.N) op[k] = f[k];
                             }
                         }
-                        if (MODE == 2 || p.out_hi || p.ps_hi) *tp = make_float4(f[0], f[1], f[2], f[3]);
+                        if (MODE == 2 || p.out_hi || p.ps_hi) sts128(tp, make_float4(f[0], f[1], f[2], f[3]));
                     }
                 }
                 // ---- pass 2 (bf16 mapping: 4 lanes per row): split into hi / lo planes, 16-byte stores ----
@@ -501,11 +521,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int row = i * 8 + g2;
-                        const int pixr = eq.pix[row];
+                        const int pixr = lds32(eq_pix + 4 * row);
                         uint32_t hi[4], lo[4];
                         {
-                            const float4* tr = reinterpret_cast<const float4*>(tile_s + row * 32);
-                            const float4 a = tr[(col2 >> 2) ^ (row & 7)], bq = tr[((col2 >> 2) + 1) ^ (row & 7)];
+                            const uint32_t tr = tile_a + (uint32_t)row * 128u;
+                            const float4 a = lds128(tr + (uint32_t)((((col2 >> 2)) ^ (row & 7)) << 4)), bq = lds128(tr + (uint32_t)((((col2 >> 2) + 1) ^ (row & 7)) << 4));
                             const float fv[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
                             for (int k = 0; k < 8; k += 2) {
@@ -518,7 +538,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                             }
                         }
                         if (MODE == 2 && pixr >= 0 && qh) {
-                            const long long qo = (long long)eq.pix_ps[row] + (long long)(c >> 6) * __float_as_int(eq.inv[row]) + (c & 63) + col2;
+                            const long long qo = (long long)lds32(eq_ps + 4 * row) + (long long)(c >> 6) * lds32(eq_inv + 4 * row) + (c & 63) + col2;
                             *reinterpret_cast<uint4*>(qh + qo) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                             if (ql) *reinterpret_cast<uint4*>(ql + qo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
@@ -529,7 +549,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                                     *reinterpret_cast<uint4*>(p.out_lo + (long long)pixr * p.ld_bf + nb + col2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                             }
                             if (p.ps_hi) {
-                                const long long pp = eq.pix_ps[row];
+                                const long long pp = lds32(eq_ps + 4 * row);
                                 *reinterpret_cast<uint4*>(p.ps_hi + pp * p.ld_ps + nb + col2) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                                 if (p.ps_lo)
                                     *reinterpret_cast<uint4*>(p.ps_lo + pp * p.ld_ps + nb + col2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
