@@ -62,17 +62,25 @@ __global__ void __launch_bounds__(THREADS, 2) gconv_mma_kernel(
 
     // ---- stage the input tile: (pixel, 16-byte chunk, plane) -> swizzled shared memory, zero fill outside ----
     {
+        // thread = (16-byte chunk c of the 64-channel slab, pixel p0 + 32 k): one constant division per copy and
+        // 32-bit offsets inside the frame (the index arithmetic was 26 % of the kernel's instructions)
         const uint32_t sbase = smem_u32(smem);
-        for (int idx = threadIdx.x; idx < PY * PX * 8 * NPL; idx += THREADS) {
-            const int c = idx & 7;
-            const int pp = (idx >> 3) % (PY * PX);
-            const int pl = idx / (8 * PY * PX);
-            const int py = pp / PX, px = pp - py * PX;
-            const int gy = ty0 + py - 1, gx = tx0 + px - 1;
-            const bool inb = (gy >= 0 && gy < H && gx >= 0 && gx < W);
-            const __nv_bfloat16* base = pl ? in_lo : in_hi;
-            const __nv_bfloat16* src = inb ? base + (((long long)b * H + gy) * W + gx) * C + slab * SLAB + c * 8 : base;
-            cp_async16(sbase + pl * PLANE_BYTES + pp * PIX_BYTES + ((c ^ (px & 7)) << 4), src, inb ? 16 : 0);
+        const int c = threadIdx.x & 7, p0 = threadIdx.x >> 3;
+        const long long frame = (long long)b * H * W * C + slab * SLAB + c * 8;
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) {
+            const __nv_bfloat16* base = (pl ? in_lo : in_hi) + frame;
+#pragma unroll
+            for (int it = 0; it < (PY * PX + 31) / 32; ++it) {
+                const int pp = p0 + it * 32;
+                if (pp < PY * PX) {
+                    const int py = pp / PX, px = pp - py * PX;
+                    const int gy = ty0 + py - 1, gx = tx0 + px - 1;
+                    const bool inb = ((unsigned)gy < (unsigned)H) && ((unsigned)gx < (unsigned)W);
+                    const __nv_bfloat16* src = inb ? base + (gy * W + gx) * C : base;
+                    cp_async16(sbase + pl * PLANE_BYTES + pp * PIX_BYTES + ((c ^ (px & 7)) << 4), src, inb ? 16 : 0);
+                }
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -146,15 +154,20 @@ __global__ void __launch_bounds__(THREADS, 2) gconv_mma_kernel(
             }
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < TY * TX * 8 * NPL; idx += THREADS) {
-        const int c = idx & 7;
-        const int op = (idx >> 3) % (TY * TX);
-        const int pl = idx / (8 * TY * TX);
-        const int gy = ty0 + op / TX, gx = tx0 + (op % TX);
-        if (gy < H && gx < W) {
-            const uint4 v = *reinterpret_cast<const uint4*>(smem + pl * (TY * TX * PIX_BYTES) + op * PIX_BYTES + ((c ^ (op & 7)) << 4));
-            __nv_bfloat16* dst = (pl ? out_lo : out_hi) + (((long long)b * H + gy) * W + gx) * C + slab * SLAB + c * 8;
-            *reinterpret_cast<uint4*>(dst) = v;
+    {
+        const int c = threadIdx.x & 7, o0 = threadIdx.x >> 3;
+        const long long frame = (long long)b * H * W * C + slab * SLAB + c * 8;
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) {
+            __nv_bfloat16* base = (pl ? out_lo : out_hi) + frame;
+#pragma unroll
+            for (int it = 0; it < TY * TX / 32; ++it) {
+                const int op = o0 + it * 32;
+                const int gy = ty0 + (op >> 5), gx = tx0 + (op & 31);  // TX == 32
+                if (gy < H && gx < W)
+                    *reinterpret_cast<uint4*>(base + (gy * W + gx) * C) =
+                        *reinterpret_cast<const uint4*>(smem + pl * (TY * TX * PIX_BYTES) + op * PIX_BYTES + ((c ^ (op & 7)) << 4));
+            }
         }
     }
 }
@@ -169,7 +182,8 @@ PRAM_API int pram_gconv3x3_tc(const void* in_hi, const void* in_lo, const float*
     if (!in_hi || !w || !out_hi || B <= 0 || H <= 0 || W <= 0) return PRAM_ERR_ARG;
     if (split != 1 && split != 3) return PRAM_ERR_ARG;
     if (split == 3 && (!in_lo || !out_lo)) return PRAM_ERR_ARG;
-    if (C % SLAB) return PRAM_ERR_UNSUPPORTED;
+    if (C % SLAB || (long long)H * W * C >= (1LL << 31)) return PRAM_ERR_UNSUPPORTED;  // 32-bit offsets inside a frame
+    static_assert(TX == 32, "the store loop decodes pixels with shifts");
     const int tiles = cdiv(W, TX) * cdiv(H, TY);
     dim3 grid(B * tiles, C / SLAB);
     if (split == 3) {
