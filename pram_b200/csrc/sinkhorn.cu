@@ -80,20 +80,37 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
         float4 cp[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) cp[k] = make_float4(0, 0, 0, 0);
+        // rows are streamed from L2; the next row of this warp is fetched while the current one is reduced (the
+        // warp_sum in the middle of the body would otherwise leave a single row of loads in flight per warp)
+        constexpr bool kCacheRow = (NV <= 17);  // wider rows are re-read (L1-resident) instead of cached in registers
+        float4 nx[kCacheRow ? NV : 1];
+        auto load_row = [&](int i, float4 (&dst)[kCacheRow ? NV : 1]) {
+            if (!kCacheRow) return;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                const int j = k * 128 + lane * 4;
+                dst[kCacheRow ? k : 0] = (j < ldp && i < r1) ? *reinterpret_cast<const float4*>(P + (long long)i * ldp + j)
+                                                              : make_float4(0, 0, 0, 0);
+            }
+        };
+        load_row(r0 + warp, nx);
         for (int i = r0 + warp; i < r1; i += WARPS) {
-            constexpr bool kCacheRow = (NV <= 17);  // wider rows are re-read (L1-resident) instead
             float4 pr[kCacheRow ? NV : 1];
             float s = 0.f;
+            if (kCacheRow) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) pr[kCacheRow ? k : 0] = nx[kCacheRow ? k : 0];
+                load_row(i + WARPS, nx);  // prefetch (zeros past the last row)
+            }
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
                 int j = k * 128 + lane * 4;
                 float4 pv = make_float4(0, 0, 0, 0);
                 if (j < ldp) {
-                    pv = *reinterpret_cast<const float4*>(P + (long long)i * ldp + j);
+                    pv = kCacheRow ? pr[kCacheRow ? k : 0] : *reinterpret_cast<const float4*>(P + (long long)i * ldp + j);
                     float4 vv = *reinterpret_cast<const float4*>(v_s + j);
                     s += pv.x * vv.x + pv.y * vv.y + pv.z * vv.z + pv.w * vv.w;
                 }
-                if (kCacheRow) pr[kCacheRow ? k : 0] = pv;
             }
             s = warp_sum(s);
             const float ri = (i == M) ? (float)MR : 1.f;
