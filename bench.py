@@ -64,12 +64,12 @@ def workload_name(batch):
 
 def make_frames(batch, seed0=0):
     import torch
-    from oracle import pram_oracle as O  # input generator only (polys frames)
-    return torch.cat([O.frame_tensor(H, W, seed=seed0 + i) for i in range(batch)], 0)
+    import benchdata  # seeded polygon frames; not part of the oracle
+    return torch.cat([benchdata.frame_tensor(H, W, seed=seed0 + i) for i in range(batch)], 0)
 
 
 def states():
-    from oracle import ref_loader as RL
+    import benchdata as RL  # checkpoints / seeded random weights; not part of the oracle
     sfd2 = RL.load_sfd2_state()
     gml = RL.load_gml_state()
     tag = 'shipped SFD2+GML checkpoints' if (sfd2 is not None and gml is not None) else 'seeded random weights'
@@ -328,7 +328,7 @@ def run_ours(args):
                    'sample': f'2 frames x 3 reps (median), oracle torch-CPU fp32, {cores} threads'}
         matched = float((out['matches0'] > -1).float().mean().item())
         # pose check against the synthetic map's known poses (reported, not timed)
-        from oracle import pram_oracle as O
+        import benchdata as O
         errs = [O.pose_error(out['qvec'][i].cpu().numpy(), out['tvec'][i].cpu().numpy(),
                              O.rotmat_to_quat(smap.R[i].double().cpu().numpy()), smap.t[i].double().cpu().numpy())
                 for i in range(B)]

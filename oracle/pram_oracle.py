@@ -470,34 +470,7 @@ def adagml_forward(sd, data: dict, n_layers: int = 9, n_min_tokens: int = 256,
 # (localization/singlemap3d.py:168-175, :324, :454; tracker.py:211; pose_estimator.py:213,338,452).
 # --------------------------------------------------------------------------------------------
 
-def quat_to_rotmat(q: np.ndarray) -> np.ndarray:
-    """wxyz quaternion -> R; same convention as reference colmap_utils/read_write_model.py:556."""
-    w, x, y, z = q
-    return np.array([
-        [1 - 2 * y * y - 2 * z * z, 2 * x * y - 2 * w * z, 2 * z * x + 2 * w * y],
-        [2 * x * y + 2 * w * z, 1 - 2 * x * x - 2 * z * z, 2 * y * z - 2 * w * x],
-        [2 * z * x - 2 * w * y, 2 * y * z + 2 * w * x, 1 - 2 * x * x - 2 * y * y]])
-
-
-def rotmat_to_quat(R: np.ndarray) -> np.ndarray:
-    """R -> wxyz quaternion with w >= 0."""
-    K = np.array([
-        [R[0, 0] - R[1, 1] - R[2, 2], 0, 0, 0],
-        [R[0, 1] + R[1, 0], R[1, 1] - R[0, 0] - R[2, 2], 0, 0],
-        [R[0, 2] + R[2, 0], R[1, 2] + R[2, 1], R[2, 2] - R[0, 0] - R[1, 1], 0],
-        [R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1], R[0, 0] + R[1, 1] + R[2, 2]]]) / 3.0
-    vals, vecs = np.linalg.eigh(K)
-    q = vecs[[3, 0, 1, 2], np.argmax(vals)]
-    return -q if q[0] < 0 else q
-
-
-def pose_error(q_pred, t_pred, q_gt, t_gt) -> Tuple[float, float]:
-    """(rotation error in degrees, camera-centre error); reference localization/utils.py:30-53."""
-    Rp, Rg = quat_to_rotmat(np.asarray(q_pred, float)), quat_to_rotmat(np.asarray(q_gt, float))
-    cp = -Rp.T @ np.asarray(t_pred, float).reshape(3)
-    cg = -Rg.T @ np.asarray(t_gt, float).reshape(3)
-    d = min(1.0, max(-1.0, abs(float(np.dot(q_pred, q_gt)))))
-    return 2 * math.acos(d) * 180 / math.pi, float(np.linalg.norm(cp - cg))
+from benchdata import quat_to_rotmat, rotmat_to_quat, pose_error  # noqa: E402,F401  (shared metric helpers)
 
 
 def p3p_solve(x: np.ndarray, X: np.ndarray) -> List[Tuple[np.ndarray, np.ndarray]]:
@@ -700,28 +673,7 @@ def camera_intrinsics(camera) -> Tuple[float, float, float, float]:
 # Synthetic inputs -- seeded, dataset-free
 # --------------------------------------------------------------------------------------------
 
-def polys_frame(h: int = 480, w: int = 640, seed: int = 0, n_poly: int = 600) -> np.ndarray:
-    """Grey canvas + random filled polygons + sigma=0.8 blur -> float32 RGB [h,w,3] in [0,1]."""
-    import cv2
-    rs = np.random.RandomState(seed)
-    img = np.full((h, w, 3), 127, np.uint8)
-    for _ in range(n_poly):
-        k = rs.randint(3, 7)
-        off = np.array([rs.randint(0, w), rs.randint(0, h)])
-        pts = (rs.randint(0, 60, size=(k, 2)) + off - 30).astype(np.int32)
-        col = tuple(int(c) for c in rs.randint(0, 256, size=3))
-        cv2.fillPoly(img, [pts], col)
-    img = cv2.GaussianBlur(img, (0, 0), 0.8)
-    return img.astype(np.float32) / 255.0
-
-
-def frame_tensor(h: int = 480, w: int = 640, seed: int = 0) -> Tensor:
-    """ImageNet-normalised [1,3,h,w] tensor of ``polys_frame`` (the online loop's preprocessing,
-    reference localization/loc_by_rec_online.py:86-106)."""
-    img = torch.from_numpy(polys_frame(h, w, seed)).permute(2, 0, 1)[None]
-    mean = torch.tensor(RGB_MEAN).view(1, 3, 1, 1)
-    std = torch.tensor(RGB_STD).view(1, 3, 1, 1)
-    return ((img - mean) / std).contiguous()
+from benchdata import polys_frame, frame_tensor  # noqa: E402,F401  (input generator shared with bench.py)
 
 
 # --------------------------------------------------------------------------------------------
