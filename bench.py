@@ -207,6 +207,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout by default; stdout must carry exactly one JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     _lib.load()  # fails loudly if the CUDA library is missing
 
