@@ -207,9 +207,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # NCCL writes its version / debug lines to stdout by default; stdout must carry exactly one JSON line
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner on stdout while the communicator is created; stdout must carry exactly one
+        # JSON line, so fd 1 points at stderr for the duration of the (eager) initialisation
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        try:
+            os.dup2(2, 1)
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     _lib.load()  # fails loudly if the CUDA library is missing
 
     sd_sfd2, sd_vit, sd_gml, tag = states()
