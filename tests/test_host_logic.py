@@ -24,3 +24,87 @@ def test_select_with_mask_matches_reference_loops(topK):
     for k in ref:
         assert out[k].dtype == ref[k].dtype and np.array_equal(out[k], ref[k]), k
     assert 0 < (out['labels'] != 0).sum() < n
+
+
+def test_match_features_batch_host_logic_cpu():
+    """match_pairs groups pairs of equal shape into one batched matcher call, keeps AdaGML at batch 1, packs
+    descriptors the way each matcher expects ([B,N,D] for the attentional ones, [B,D,N] for NN) and returns the
+    reference's record dtypes -- checked on CPU with a recording stand-in for the matcher."""
+    import torch
+    from pram_b200.localization import match_features_batch as MFB
+
+    class Recorder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.calls = []
+
+        def forward(self, data):
+            self.calls.append({k: tuple(v.shape) for k, v in data.items() if torch.is_tensor(v)})
+            b, n = data['keypoints0'].shape[:2]
+            m0 = torch.arange(n)[None].repeat(b, 1) % data['keypoints1'].shape[1]
+            return {'matches0': m0, 'matching_scores0': torch.full((b, n), 0.5)}
+
+    def feat(n, seed, size=(640, 480)):
+        r = np.random.RandomState(seed)
+        return {'keypoints': r.rand(n, 2).astype(np.float32), 'descriptors': r.randn(128, n).astype(np.float32),
+                'scores': r.rand(n).astype(np.float32), 'image_size': np.array(size)}
+    store = {'q0': feat(50, 0), 'q1': feat(50, 1), 'q2': feat(70, 2), 'd0': feat(60, 3), 'd1': feat(60, 4)}
+    pairs = [('q0', 'd0'), ('q1', 'd1'), ('q2', 'd0'), ('q0', 'd1')]
+    rec = Recorder()
+    out = MFB.match_pairs(MFB.confs['gml'], pairs, store, model=rec, device='cpu')
+    assert len(rec.calls) == 2                      # three 50x60 pairs in one call, the 70x60 pair alone
+    big = max(rec.calls, key=lambda c: c['keypoints0'][0])
+    assert big['keypoints0'] == (3, 50, 2) and big['descriptors0'] == (3, 50, 128) and big['descriptors1'] == (3, 60, 128)
+    assert big['image0'] == (1, 1, 480, 640)        # (h, w) from image_size = (w, h), like FeaturePairsDataset
+    assert set(out) == {MFB.names_to_pair(*p) for p in pairs}
+    r0 = out[MFB.names_to_pair('q2', 'd0')]
+    assert r0['matches0'].dtype == np.int16 and r0['matches0'].shape == (70,) and r0['matching_scores0'].dtype == np.float16
+    # NN layout and AdaGML batching rule
+    rec = Recorder()
+    MFB.match_pairs(MFB.confs['NNM'], pairs[:2], store, model=rec, device='cpu')
+    assert rec.calls[0]['descriptors0'] == (2, 128, 50)
+    rec = Recorder()
+    MFB.match_pairs(MFB.confs['adagml'], pairs[:2], store, model=rec, device='cpu')
+    assert len(rec.calls) == 2 and rec.calls[0]['keypoints0'][0] == 1
+    assert MFB.names_to_pair('a/b.png', 'c/d.png') == 'a-b.png/c-d.png'
+
+
+def test_find_2d_3d_matches_cpu():
+    """find_2D_3D_matches (reference localization/pose_estimator.py:88-134) with a stand-in matcher on CPU: id remap
+    through the valid-3D mask, observation threshold, +0.5 pixel-centre shift, ascending query order."""
+    import torch
+    from types import SimpleNamespace
+    from pram_b200.localization.pose_estimator import find_2D_3D_matches
+    rs = np.random.RandomState(3)
+    n_q, n_db = 40, 30
+    q = {'keypoints': rs.rand(n_q, 2).astype(np.float32) * 100, 'scores': rs.rand(n_q).astype(np.float32),
+         'descriptors': rs.randn(n_q, 16).astype(np.float32), 'image_size': np.array([640, 480])}
+    store = {'db.png': {'keypoints': rs.rand(n_db, 2).astype(np.float32), 'scores': rs.rand(n_db).astype(np.float32),
+                        'descriptors': rs.randn(16, n_db).astype(np.float32), 'image_size': np.array([640, 480])}}
+    ids3d = np.where(np.arange(n_db) % 3 == 0, -1, np.arange(n_db) + 500)
+    valid = np.nonzero(ids3d != -1)[0]
+    db_images = {0: SimpleNamespace(name='db.png', point3D_ids=ids3d)}
+    points3D = {int(i): SimpleNamespace(xyz=rs.randn(3), image_ids=[0] * (int(i) % 3 + 1)) for i in ids3d if i != -1}
+
+    class Stub(torch.nn.Module):  # query i -> (i mod n_valid)-th VALID database keypoint unless i % 5 == 0 (unmatched)
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, data):
+            assert data['keypoints1'].shape[1] == valid.size and data['descriptors1'].shape == (1, valid.size, 16)
+            m = torch.full((1, n_q), -1, dtype=torch.long)
+            idx = torch.tensor([i for i in range(n_q) if i % 5])
+            m[0, idx] = idx % valid.size
+            return {'matches0': m}
+    mp3d, mkpq, mp3d_ids, q_ids = find_2D_3D_matches(q, 0, points3D, store, db_images, Stub(), obs_th=2)
+    exp_q, exp_ids = [], []
+    for i in range(n_q):
+        if i % 5 == 0:
+            continue
+        pid = int(ids3d[valid[i % valid.size]])
+        if len(points3D[pid].image_ids) >= 2:
+            exp_q.append(i); exp_ids.append(pid)
+    assert q_ids == exp_q and mp3d_ids == exp_ids and len(exp_q) > 3
+    assert np.allclose(mkpq, q['keypoints'][exp_q].astype(float) + 0.5)
+    assert np.allclose(mp3d, np.array([points3D[i].xyz for i in exp_ids]))
