@@ -108,3 +108,71 @@ def test_find_2d_3d_matches_cpu():
     assert q_ids == exp_q and mp3d_ids == exp_ids and len(exp_q) > 3
     assert np.allclose(mkpq, q['keypoints'][exp_q].astype(float) + 0.5)
     assert np.allclose(mp3d, np.array([points3D[i].xyz for i in exp_ids]))
+
+
+def test_singlemap3d_localize_with_ref_frame_cpu():
+    """SingleMap3D.localize_with_ref_frame / .match (reference localization/singlemap3d.py:127-226) with stand-ins
+    for the matcher and the pose operator on CPU: result keys and values, semantic (per-landmark) reference subsets,
+    the (1, 3, W, H) image_shape quirk, the +0.5 shift handed to the pose operator, the failure convention, and that a
+    reference frame is uploaded once."""
+    import torch
+    from types import SimpleNamespace
+    from pram_b200.localization.singlemap3d import RefFrame, SingleMap3D
+    rs = np.random.RandomState(0)
+    cam = SimpleNamespace(width=640, height=480, model='PINHOLE', params=[525, 525, 320, 240])
+    n_ref = 50
+    segs = rs.randint(1, 4, n_ref)
+    ref = RefFrame(cam, 7, np.hstack([rs.rand(n_ref, 2) * 400, rs.rand(n_ref, 1)]).astype(np.float32),
+                   rs.randn(n_ref, 16).astype(np.float32), rs.randn(n_ref, 3), np.arange(n_ref) + 1000, segs, device='cpu')
+    seen = []
+
+    class Stub(torch.nn.Module):  # query i -> reference (i mod n1) for odd i
+        def forward(self, data):
+            seen.append((data['image_shape0'], data['image_shape1'], data['keypoints1'].shape[1]))
+            n0, n1 = data['keypoints0'].shape[1], data['keypoints1'].shape[1]
+            m = torch.full((1, n0), -1, dtype=torch.long)
+            idx = torch.arange(1, n0, 2)
+            m[0, idx] = idx % n1
+            return {'matches0': m}
+    calls = {}
+
+    def pose_fn(p2d, p3d, camera, estimation_options=None, refinement_options=None):
+        calls['args'] = (p2d.copy(), p3d.copy(), estimation_options)
+        if calls.get('fail'):
+            return None
+        return {'cam_from_world': SimpleNamespace(rotation=SimpleNamespace(quat=np.array([0.1, 0.2, 0.3, 0.9])),
+                                                  translation=np.array([1.0, 2.0, 3.0])),
+                'num_inliers': 5, 'inliers': np.ones(p2d.shape[0], bool)}
+    smap = SingleMap3D({'localization': {'threshold': 8}}, Stub(), {7: ref}, {2: [7, 9], 0: [7]},
+                       {int(i): int(s) for i, s in zip(ref.point3D_ids, segs)}, device='cpu', pose_fn=pose_fn)
+    nq = 30
+    q = SimpleNamespace(camera=cam, descriptors=rs.randn(nq, 16).astype(np.float32),
+                        keypoints=np.hstack([rs.rand(nq, 2) * 400, rs.rand(nq, 1)]).astype(np.float32))
+    ids = np.arange(4, 24)
+    ret = smap.localize_with_ref_frame(q, ids, sid=2, semantic_matching=True)
+    sub = np.nonzero(segs == 2)[0]
+    local = np.arange(ids.size)
+    matched = local[1::2]
+    ref_idx = sub[matched % sub.size]
+    assert seen[-1] == ((1, 3, 640, 480), (1, 3, 640, 480), sub.size)
+    assert ret['success'] and np.allclose(ret['qvec'], [0.9, 0.1, 0.2, 0.3]) and np.allclose(ret['tvec'], [1, 2, 3])
+    assert np.array_equal(ret['matched_keypoint_ids'], ids[matched])
+    assert np.allclose(ret['matched_keypoints'], q.keypoints[ids[matched], :2])
+    assert np.allclose(ret['matched_xyzs'], ref.xyzs[ref_idx]) and np.array_equal(ret['matched_point3D_ids'], ref.point3D_ids[ref_idx])
+    assert (ret['matched_sids'] == 2).all() and ret['reference_frame_id'] == 7
+    assert np.allclose(ret['matched_ref_keypoints'], ref.keypoints[ref_idx, :2])
+    assert np.allclose(calls['args'][0], q.keypoints[ids[matched], :2] + 0.5) and calls['args'][2] == {'ransac': {'max_error': 8}}
+    # non-semantic path uses every reference keypoint; second call re-uses the resident copy
+    smap.localize_with_ref_frame(q, ids, sid=2, semantic_matching=False)
+    smap.localize_with_ref_frame(q, ids, sid=0, semantic_matching=True)   # sid 0 -> all keypoints too
+    assert seen[-1][2] == n_ref and set(ref._dev) == {2, 'all'}
+    # failure convention
+    calls['fail'] = True
+    bad = smap.localize_with_ref_frame(q, ids, sid=2)
+    assert bad['success'] is False and bad['num_inliers'] == 0 and bad['inliers'].shape == (matched.size,) and not bad['inliers'].any()
+    # match()
+    m = smap.match({'keypoints': q.keypoints[:, :2], 'descriptors': q.descriptors, 'scores': q.keypoints[:, 2], 'camera': cam},
+                   ref.get_keypoints())
+    exp = np.arange(1, nq, 2)
+    assert np.array_equal(m['matched_keypoint_ids'], exp) and np.allclose(m['matched_xyzs'], ref.xyzs[exp % n_ref])
+    assert np.array_equal(m['matched_point3D_ids'], ref.point3D_ids[exp % n_ref])
