@@ -176,3 +176,41 @@ def test_singlemap3d_localize_with_ref_frame_cpu():
     exp = np.arange(1, nq, 2)
     assert np.array_equal(m['matched_keypoint_ids'], exp) and np.allclose(m['matched_xyzs'], ref.xyzs[exp % n_ref])
     assert np.array_equal(m['matched_point3D_ids'], ref.point3D_ids[exp % n_ref])
+
+
+def test_tracker_track_last_frame_cpu():
+    """Tracker.track_last_frame (reference localization/tracker.py:162-233) with stand-in operators: matches without a
+    3-D point (id -1) are dropped, ids / xyz / sids gathered in query order, +0.5 shift, result keys."""
+    import torch
+    from types import SimpleNamespace
+    from pram_b200.localization.tracker import Tracker
+    rs = np.random.RandomState(4)
+    cam = SimpleNamespace(width=640, height=480)
+    n0, n1 = 30, 25
+    curr = SimpleNamespace(camera=cam, keypoints=rs.rand(n0, 3).astype(np.float32) * 100, descriptors=rs.randn(n0, 8).astype(np.float32))
+    pids = np.where(np.arange(n1) % 4 == 0, -1, np.arange(n1) + 300)
+    last = SimpleNamespace(camera=cam, keypoints=rs.rand(n1, 3).astype(np.float32) * 100, descriptors=rs.randn(n1, 8).astype(np.float32),
+                           xyzs=rs.randn(n1, 3), point3D_ids=pids, seg_ids=rs.randint(0, 5, n1), reference_frame_id=11,
+                           matched_scene_name='scene')
+
+    class Stub(torch.nn.Module):
+        def forward(self, data):
+            m = torch.full((1, n0), -1, dtype=torch.long)
+            idx = torch.arange(0, n0, 3)
+            m[0, idx] = (idx * 7) % n1
+            return {'matches0': m}
+    got = {}
+
+    def pose_fn(p2d, p3d, camera, estimation_options=None, refinement_options=None):
+        got['p2d'], got['opt'] = p2d.copy(), estimation_options
+        return {'cam_from_world': SimpleNamespace(rotation=SimpleNamespace(quat=np.array([0., 0., 0., 1.])), translation=np.zeros(3)),
+                'num_inliers': p2d.shape[0], 'inliers': np.ones(p2d.shape[0], bool)}
+    ret = Tracker({'localization': {'threshold': 12}}, Stub(), device='cpu', pose_fn=pose_fn).track_last_frame(curr, last)
+    q = np.arange(0, n0, 3); r = (q * 7) % n1
+    ok = pids[r] >= 0
+    q, r = q[ok], r[ok]
+    assert np.array_equal(ret['matched_keypoint_ids'], q) and np.array_equal(ret['matched_point3D_ids'], pids[r])
+    assert np.allclose(ret['matched_xyzs'], last.xyzs[r]) and np.array_equal(ret['matched_sids'], last.seg_ids[r])
+    assert np.allclose(ret['matched_keypoints'], curr.keypoints[q, :2]) and np.allclose(ret['matched_ref_keypoints'], last.keypoints[r, :2])
+    assert np.allclose(got['p2d'], curr.keypoints[q, :2] + 0.5) and got['opt'] == {'ransac': {'max_error': 12}}
+    assert ret['success'] and np.allclose(ret['qvec'], [1, 0, 0, 0]) and ret['reference_frame_id'] == 11 and ret['matched_scene_name'] == 'scene'
