@@ -512,8 +512,7 @@ def nearest_neighbor_match(desc0: Tensor, desc1: Tensor, ratio_threshold: Option
     dev = desc0.device
     a0 = split_bf16(_f32c(desc0.transpose(1, 2)), split == 3)  # [B,N,D] K-major rows (layout plumbing only)
     a1 = split_bf16(_f32c(desc1.transpose(1, 2)), split == 3)
-    dpad = d  # Cin % 8 == 0 is required by the TMA strides
-    if d % 8:
+    if d % 8:  # 16-byte TMA strides
         raise _lib.PramError('descriptor dimension must be a multiple of 8')
     sim = torch.empty((b, n, m), device=dev, dtype=torch.float32)
     linear_tc(Split(a0.hi.view(b * n, d), a0.lo.view(b * n, d) if a0.lo is not None else None), d, n, d,
