@@ -356,9 +356,35 @@ def run_ours(args):
             'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': frames_host.numel() * 4,
                     'd2h_bytes_per_step': res_host.numel() * 8 * 2},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+            'whole_step_bound': whole_step_bound(value, world, 3 if args.precision == 'bf16x3' else 1),
         }))
     if world > 1:
         dist.destroy_process_group()
+
+
+def algorithmic_gflop_per_frame(h, w, k, c):
+    """SURVEY.md section 8d closed forms: SFD2 conv stack (scaled from 132.95 GFLOP @640x480), SegNetViT, one GML pair
+    with M = N = k."""
+    sfd2 = 132.95 * (h * w) / (480.0 * 640.0)
+    vit = (15 * (1310720.0 * k + 1024.0 * k * k) + 131072.0 * k + 2.0 * k * (262144.0 + 1024.0 * c)) / 1e9
+    per_layer = 1310720.0 * 2 * k + 1024.0 * 2 * k * k + 1179648.0 * 2 * k + 1536.0 * k * k
+    gml = (9 * per_layer + 2 * 128 * 256 * 2 * k + 2 * 256 * 256 * 2 * k + 512.0 * k * k) / 1e9
+    return sfd2 + vit + gml
+
+
+def whole_step_bound(value_fps, n_gpus, mma_mult):
+    """Frames/s ceiling if every algorithmic FLOP ran at the measured sustained cuBLAS bf16 rate (x mma_mult issued
+    FLOPs for bf16x3), and the achieved fraction of it.  Reported beside the per-kernel roofline; never raises."""
+    try:
+        peaks = json.loads((ROOT / 'MEASURED_PEAKS.json').read_text()) if (ROOT / 'MEASURED_PEAKS.json').exists() else {}
+        sustained = float(peaks.get('bf16_tflops_sustained', 1400.0))
+        gf = algorithmic_gflop_per_frame(H, W, KPTS, NCLASS)
+        bound = n_gpus * sustained * 1e3 / (gf * mma_mult)
+        return {'algorithmic_gflop_per_frame': gf, 'tensor_flops_issued_per_algorithmic_flop': mma_mult,
+                'tensor_bound_frames_per_s': bound, 'frac_of_tensor_bound': value_fps / bound,
+                'peak': sustained, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PFLOP/s'}
+    except Exception as e:  # noqa: BLE001 -- metadata only
+        return {'error': repr(e)}
 
 
 def roofline_probe(pipe, frames_dev, dev):
