@@ -214,3 +214,24 @@ def test_tracker_track_last_frame_cpu():
     assert np.allclose(ret['matched_keypoints'], curr.keypoints[q, :2]) and np.allclose(ret['matched_ref_keypoints'], last.keypoints[r, :2])
     assert np.allclose(got['p2d'], curr.keypoints[q, :2] + 0.5) and got['opt'] == {'ransac': {'max_error': 12}}
     assert ret['success'] and np.allclose(ret['qvec'], [1, 0, 0, 0]) and ret['reference_frame_id'] == 11 and ret['matched_scene_name'] == 'scene'
+
+
+def test_bench_workloads_and_step_bound():
+    """bench.py metadata helpers: the SURVEY.md 8d closed forms (250.8 / 677 / 1911 GFLOP per frame) and the
+    step-level tensor ceiling; the workload table matches the BASELINE.json shapes."""
+    import json
+    import bench
+    assert abs(bench.algorithmic_gflop_per_frame(480, 640, 1024, 113) - 250.8) < 0.1
+    assert abs(bench.algorithmic_gflop_per_frame(768, 1024, 2048, 161) - 677.1) < 0.5
+    assert abs(bench.algorithmic_gflop_per_frame(1200, 1600, 4096, 513) - 1911.0) < 2.0
+    b = bench.whole_step_bound(1000.0, 2, 3)
+    json.dumps(b)
+    assert b['tensor_bound_frames_per_s'] > 2000 and 0 < b['frac_of_tensor_bound'] < 1
+    assert bench.WORKLOADS['7scenes']['kpts'] == 1024 and bench.WORKLOADS['cambridge']['h'] == 768 and bench.WORKLOADS['aachen']['kpts'] == 4096
+    saved = (bench.H, bench.W, bench.KPTS, bench.NCLASS, bench.FOCAL, bench.MAX_ERROR, bench.METRIC)
+    try:
+        assert bench.set_workload('cambridge', 0) == 16 and (bench.H, bench.W, bench.KPTS, bench.NCLASS) == (768, 1024, 2048, 161)
+        assert '1024x768' in bench.METRIC and bench.set_workload('7scenes', 4) == 4
+        assert bench.METRIC == 'localization frames/sec (640x480, 1024 kpts)'
+    finally:
+        bench.H, bench.W, bench.KPTS, bench.NCLASS, bench.FOCAL, bench.MAX_ERROR, bench.METRIC = saved
