@@ -110,21 +110,21 @@ __global__ void __launch_bounds__(RK_THREADS) rank_entries_kernel(
     int* __restrict__ entry_rank, int* __restrict__ entry_count, float* __restrict__ entry_score, int* __restrict__ n_entries,
     const int* __restrict__ label_at_rank) {
     __shared__ int cnt[RK_MAXC];
-    __shared__ float sum[RK_MAXC];
     __shared__ unsigned char used[RK_MAXC];
-    __shared__ int s_n, s_best, s_done;
+    __shared__ float wsum[RK_THREADS / 32];
+    __shared__ int s_n, s_best, s_done, s_e;
     const int b = blockIdx.x;
     const float* L = logits + (long long)b * N * C;
     for (int c = threadIdx.x; c < C; c += RK_THREADS) used[c] = 0;
     if (threadIdx.x == 0) { s_n = 0; s_done = 0; }
     __syncthreads();
     for (int k = 0; k < max_ranks && k < C; ++k) {
-        for (int c = threadIdx.x; c < C; c += RK_THREADS) { cnt[c] = 0; sum[c] = 0.f; }
+        for (int c = threadIdx.x; c < C; c += RK_THREADS) cnt[c] = 0;
         __syncthreads();
         const int* lab = label_at_rank + ((long long)b * max_ranks + k) * N;
         for (int i = threadIdx.x; i < N; i += RK_THREADS) {
             const int c = lab[i];
-            if (c >= 0) { atomicAdd(&cnt[c], 1); atomicAdd(&sum[c], L[(long long)i * C + c]); }
+            if (c >= 0) atomicAdd(&cnt[c], 1);  // integer counts: order independent
         }
         __syncthreads();
         // append unused, non-background classes of this rank by (count desc, class asc); warp 0 does the arg-max
@@ -145,14 +145,31 @@ __global__ void __launch_bounds__(RK_THREADS) rank_entries_kernel(
                         entry_sid[(long long)b * topk + e] = best;
                         entry_rank[(long long)b * topk + e] = k;
                         entry_count[(long long)b * topk + e] = bcnt;
-                        entry_score[(long long)b * topk + e] = sum[best] / (float)bcnt;
                         used[best] = 1;
+                        s_e = e;
                         s_n = e + 1;
                         if (s_n >= topk) s_done = 1;
                     }
                 }
             }
             __syncthreads();
+            if (s_best >= 0) {
+                // mean logit of the appended class over its keypoints, summed in a FIXED order (strided partials, shuffle
+                // tree, warp partials in index order): float atomics made the score depend on the scheduling, so a graph
+                // replay or a second stream could differ from the eager run in the last bit
+                const int best = s_best;
+                float part = 0.f;
+                for (int i = threadIdx.x; i < N; i += RK_THREADS)
+                    if (lab[i] == best) part += L[(long long)i * C + best];
+                part = warp_sum(part);
+                if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = part;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    float tot = 0.f;
+                    for (int w = 0; w < RK_THREADS / 32; ++w) tot += wsum[w];
+                    entry_score[(long long)b * topk + s_e] = tot / (float)cnt[best];
+                }
+            }
             const bool stop = (s_best < 0 || s_done);
             __syncthreads();  // everyone has read s_best before warp 0 overwrites it
             if (stop) break;

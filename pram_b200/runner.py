@@ -66,9 +66,16 @@ class LocalizationPipeline:
         including its (1,3,W,H) image_shape convention)."""
         b, _, h, w = image_shape
         shp = (1, 3, w, h)
-        return self.matcher({'descriptors0': f['descriptors'], 'keypoints0': f['keypoints'],
-                             'descriptors1': smap.descriptors, 'keypoints1': smap.keypoints,
-                             'image_shape0': shp, 'image_shape1': shp})
+        m = self.matcher({'descriptors0': f['descriptors'], 'keypoints0': f['keypoints'],
+                          'descriptors1': smap.descriptors, 'keypoints1': smap.keypoints,
+                          'image_shape0': shp, 'image_shape1': shp})
+        # slots j >= num_keypoints[b] of the fixed [B, K] layout are padding (keypoint (0,0), zero descriptor): they must
+        # never reach PnP as correspondences.  (They still take part in attention / Sinkhorn as tokens -- see DESIGN.md
+        # "padded slots"; the benched frames always fill the budget, which bench.py asserts.)
+        pad = torch.arange(f['keypoints'].shape[1], device=self.dev)[None] >= f['num_keypoints'][:, None]
+        m['matches0'] = m['matches0'].masked_fill(pad, -1)
+        m['matching_scores0'] = m['matching_scores0'].masked_fill(pad, 0.0)
+        return m
 
     def _recognition(self, f: Dict[str, torch.Tensor], shape, out: Dict[str, torch.Tensor]):
         out['prediction'] = self.recognize(f, shape)
@@ -82,7 +89,8 @@ class LocalizationPipeline:
     def localize(self, images: torch.Tensor, smap: Optional[SyntheticMap] = None) -> Dict[str, torch.Tensor]:
         shape = tuple(images.shape)
         f = self.features(images)
-        out = {'keypoints': f['keypoints'], 'num_keypoints': f['num_keypoints']}
+        out = {'keypoints': f['keypoints'], 'num_keypoints': f['num_keypoints'], 'scores': f['scores'],
+               'descriptors': f['descriptors']}
         if smap is None or not self.two_streams:
             self._recognition(f, shape, out)
             if smap is not None:
