@@ -165,6 +165,28 @@ typedef struct pram_tc_args {
 } pram_tc_args;
 int pram_gemm_tc(const pram_tc_args* args, pram_stream_t stream);
 
+/* K11/K13 block tail (tensor-core path), ONE persistent kernel per transformer block:
+ *   message = proj(ctx);  x_new = x + mlp.3(GELU(LayerNorm(mlp.0([x | message]))))
+ * (SelfMultiHeadAttention / CrossMultiHeadAttention tails: nets/segnetvit.py:104-106, nets/gml.py:135-137, 182-186).
+ * proj is folded into mlp.0 by the caller (w1 = [W0x | W0m.Wp], b1 = b0 + W0m.bp); the 128-token tile stays in
+ * TMEM / shared memory from the first MMA to the residual add (h = all 512 TMEM columns, LayerNorm + GELU in the
+ * epilogue warps, hidden activations fed to the second GEMM through a shared-memory operand ring). */
+typedef struct pram_mlp_block_args {
+    const void* a_hi; const void* a_lo;   /* bf16 [T][lda]: columns 0..255 = x, 256..511 = attention context */
+    long long lda;
+    int T;
+    const void* w1_hi; const void* w1_lo; /* bf16 [512][512] */
+    const float* b1;                      /* [512] */
+    const float* ln_g; const float* ln_b; /* [512] */
+    const void* w3_hi; const void* w3_lo; /* bf16 [256][512] */
+    const float* b3;                      /* [256] */
+    const float* res; long long res_ld;   /* fp32 residual rows, may be NULL */
+    float* out_f32; long long ld_f32;     /* may be NULL */
+    void* out_hi; void* out_lo; long long ld_bf;  /* may be NULL */
+    int split;                            /* 1: bf16, 3: bf16x3 */
+} pram_mlp_block_args;
+int pram_mlp_block_tc(const pram_mlp_block_args* args, pram_stream_t stream);
+
 /* K10/K12/K13 (tensor-core path): flash attention on tcgen05, head dim 64.  S = QK^T and O += PV on the
  * tensor cores (P is fed back from TMEM as the A operand), softmax on one thread per query row.
  * q/k: bf16 [B*heads][N][64]; vt: bf16 [B*heads][64][nk_pad] (keys contiguous) when v_mn == 0, or V itself

@@ -69,6 +69,22 @@ class TcArgs(C.Structure):
 
 
 SIGNATURES['pram_gemm_tc'] = (_I, [C.POINTER(TcArgs), _P])
+
+
+class MlpBlockArgs(C.Structure):
+    """Mirror of ``struct pram_mlp_block_args`` (include/pram_b200.h)."""
+    _fields_ = [
+        ('a_hi', _P), ('a_lo', _P), ('lda', _L), ('T', _I),
+        ('w1_hi', _P), ('w1_lo', _P), ('b1', _P), ('ln_g', _P), ('ln_b', _P),
+        ('w3_hi', _P), ('w3_lo', _P), ('b3', _P),
+        ('res', _P), ('res_ld', _L),
+        ('out_f32', _P), ('ld_f32', _L),
+        ('out_hi', _P), ('out_lo', _P), ('ld_bf', _L),
+        ('split', _I),
+    ]
+
+
+SIGNATURES['pram_mlp_block_tc'] = (_I, [C.POINTER(MlpBlockArgs), _P])
 SIGNATURES['pram_split_bf16'] = (_I, [_P, _P, _P, _L, _P])
 SIGNATURES['pram_attention_tc'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I, _I, _I, _I, _P])
 SIGNATURES['pram_attention_prep'] = (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P, _I, _P])

@@ -14,9 +14,14 @@ import torch.nn as nn
 
 from .. import ops
 
+import os
+
 HEADS = 4
 HDIM = 64
 D = 256
+# one fused tcgen05 kernel for proj -> mlp.0 -> LayerNorm + GELU -> mlp.3 (+ residual) (csrc/mlp_block_tc.cu);
+# PRAM_FUSED_BLOCK=0 keeps the four separate launches (A/B timing, bisecting)
+FUSED_BLOCK = os.environ.get('PRAM_FUSED_BLOCK', '1') != '0'
 
 
 def mlp_holder(d_in: int, d_hid: int, d_out: int) -> nn.Sequential:
@@ -70,7 +75,8 @@ def pack_self(blk: SelfBlockParams) -> Dict[str, torch.Tensor]:
     w, b = blk.qkv.weight.detach(), blk.qkv.bias.detach()
     idx = torch.arange(3 * HEADS * HDIM, device=w.device).view(HEADS, HDIM, 3).permute(2, 0, 1).reshape(-1)
     return {'qkv.w': _c(w[idx]), 'qkv.b': _c(b[idx]), 'proj.w': _c(blk.proj.weight), 'proj.b': _c(blk.proj.bias),
-            'qkv.tc': _tc(w[idx]), 'proj.tc': _tc(blk.proj.weight), **pack_mlp(blk.mlp, 'mlp')}
+            'qkv.tc': _tc(w[idx]), 'proj.tc': _tc(blk.proj.weight), **pack_mlp(blk.mlp, 'mlp'),
+            **pack_block_tail(blk.proj, blk.mlp)}
 
 
 def pack_cross(blk: CrossBlockParams) -> Dict[str, torch.Tensor]:
@@ -79,7 +85,20 @@ def pack_cross(blk: CrossBlockParams) -> Dict[str, torch.Tensor]:
     return {'qkv.w': _c(wqkv), 'qkv.tc': _tc(wqkv),
             'qkv.b': _c(torch.cat([blk.to_qk.bias.detach(), blk.to_v.bias.detach()], 0)),
             'proj.w': _c(blk.proj.weight), 'proj.b': _c(blk.proj.bias), 'proj.tc': _tc(blk.proj.weight),
-            **pack_mlp(blk.mlp, 'mlp')}
+            **pack_mlp(blk.mlp, 'mlp'), **pack_block_tail(blk.proj, blk.mlp)}
+
+
+def pack_block_tail(proj: nn.Linear, mlp: nn.Sequential) -> Dict[str, torch.Tensor]:
+    """Operands of the fused block tail: mlp.0([x | proj(ctx)]) = [x | ctx] . W1^T + b1 with
+    W1 = [W0[:, :256] | W0[:, 256:] . Wp] and b1 = b0 + W0[:, 256:] . bp, folded once in float64 (like the BatchNorm
+    folding of the conv stack); reference nets/segnetvit.py:104-106, nets/gml.py:135-137."""
+    if mlp[0].weight.shape != (2 * D, 2 * D) or mlp[3].weight.shape != (D, 2 * D) or proj.weight.shape != (D, D):
+        return {}
+    w0, b0 = mlp[0].weight.detach().double(), mlp[0].bias.detach().double()
+    wp, bp = proj.weight.detach().double(), proj.bias.detach().double()
+    w1 = torch.cat([w0[:, :D], w0[:, D:] @ wp], 1)
+    b1 = b0 + w0[:, D:] @ bp
+    return {'blk.w1.tc': ops.split_bf16(w1.float().contiguous()), 'blk.b1': b1.float().contiguous()}
 
 
 def pack_mlp(mlp: nn.Sequential, pre: str) -> Dict[str, torch.Tensor]:
@@ -99,6 +118,7 @@ class Workspace:
         self.T = tokens
         self.split = split  # 0: fp32 CUDA-core path; 1 / 3: tcgen05 path with bf16 / bf16x3 operands
         self.ctx_in_bf = False
+        self.fused = bool(split) and FUSED_BLOCK
         if split:
             lo = split == 3
             self.cat_bf = [ops.empty_split((tokens, 2 * D), device, lo), ops.empty_split((tokens, 2 * D), device, lo)]
@@ -114,6 +134,13 @@ class Workspace:
         self.q, self.k, self.v = e(tokens, D), e(tokens, D), e(tokens, D)
         self.ctx = e(tokens, D)
         self.hid = e(tokens, 2 * D)
+
+    def ctx_out(self):
+        """Where the tensor-core attention writes its context: the right half of the current concat rows when the block
+        tail is fused (the projection is folded into mlp.0 there), else the separate [T, 256] buffer."""
+        if self.fused:
+            return ops.split_cols(self.cat_bf[self.cur], D), 2 * D
+        return self.ctx_bf, D
 
     @property
     def x(self) -> torch.Tensor:  # current activations: left half of the current concat buffer
@@ -155,6 +182,15 @@ def _finish_block(ws: Workspace, pk: Dict[str, torch.Tensor]):
         cbf, nbf = ws.cat_bf[ws.cur], ws.cat_bf[ws.cur ^ 1]
         if not ws.ctx_in_bf:  # CUDA-core attention produced fp32 ctx (AdaGML's mean-attention variant)
             ops.split_bf16_into(ws.ctx, ws.ctx_bf)
+        if ws.fused:
+            if not ws.ctx_in_bf:  # layout plumbing: the fused kernel reads ctx from the right half of the concat rows
+                cbf.hi[:, D:].copy_(ws.ctx_bf.hi)
+                if cbf.lo is not None:
+                    cbf.lo[:, D:].copy_(ws.ctx_bf.lo)
+            ops.mlp_block_tc(cbf, 2 * D, T, pk['blk.w1.tc'], pk['blk.b1'], pk['mlp.ln.g'], pk['mlp.ln.b'], pk['mlp.3.tc'],
+                             pk['mlp.3.b'], cat, 2 * D, nxt, 2 * D, nbf, 2 * D, split=ws.split)
+            ws.cur ^= 1
+            return
         linear(ws, None, ws.ctx_bf, D, T, D, D, pk, 'proj', out_bf=ops.split_cols(cbf, D), ld_bf=2 * D)
         linear(ws, None, cbf, 2 * D, T, 2 * D, 2 * D, pk, 'mlp.0', out_f32=ws.hid, ld_f32=2 * D)
         ops.layernorm_gelu_split(ws.hid, pk['mlp.ln.g'], pk['mlp.ln.b'], 2 * D, ws.hid_bf)
@@ -177,9 +213,10 @@ def self_block(ws: Workspace, pk: Dict[str, torch.Tensor], segments: Sequence[Tu
         qkv = {'mode': 1, 'scale': 1.0, 'cos': cos, 'sin': sin, 'q': ws.q_bf, 'k': ws.k_bf, 'v': ws.v_bf,
                'seg_split': seg_split, 'seg_n0': segments[0][2], 'seg_n1': segments[-1][2]}
         ops.linear_tc(ws.x_bf, 2 * D, T, D, pk['qkv.tc'], 3 * D, pk['qkv.b'], split=ws.split, bn=256, qkv=qkv)
+        ctx, ctx_ld = ws.ctx_out()
         for off, b, n in segments:
             ops.attention_tc(ops.split_rows(ws.q_bf, off), ops.split_rows(ws.k_bf, off), ops.split_rows(ws.v_bf, off), b, HEADS,
-                             n, n, n, HDIM ** -0.5, None, ops.split_rows(ws.ctx_bf, off), D, ws.split, v_mn=True)
+                             n, n, n, HDIM ** -0.5, None, ops.split_rows(ctx, off), ctx_ld, ws.split, v_mn=True)
         _finish_block(ws, pk)
         return
     linear(ws, ws.x, ws.x_bf if ws.split else None, 2 * D, T, D, 3 * D, pk, 'qkv', out_f32=ws.qkv, ld_f32=3 * D)
@@ -208,8 +245,9 @@ def cross_block(ws: Workspace, pk: Dict[str, torch.Tensor], seg0: Tuple[int, int
         ops.linear_tc(ws.x_bf, 2 * D, T, D, pk['qkv.tc'], 2 * D, pk['qkv.b'], split=ws.split, bn=256, qkv=fused)
         q0, q1 = ops.split_rows(ws.q_bf, o0), ops.split_rows(ws.q_bf, o1)
         v0, v1 = ops.split_rows(ws.v_bf, o0), ops.split_rows(ws.v_bf, o1)
-        ops.attention_tc(q0, q1, v1, b, HEADS, m, n, n, 1.0, None, ops.split_rows(ws.ctx_bf, o0), D, ws.split, v_mn=True)
-        ops.attention_tc(q1, q0, v0, b, HEADS, n, m, m, 1.0, None, ops.split_rows(ws.ctx_bf, o1), D, ws.split, v_mn=True)
+        ctx, ctx_ld = ws.ctx_out()
+        ops.attention_tc(q0, q1, v1, b, HEADS, m, n, n, 1.0, None, ops.split_rows(ctx, o0), ctx_ld, ws.split, v_mn=True)
+        ops.attention_tc(q1, q0, v0, b, HEADS, n, m, m, 1.0, None, ops.split_rows(ctx, o1), ctx_ld, ws.split, v_mn=True)
         _finish_block(ws, pk)
         return
     qkv = ws.qkv.view(-1)[:T * 2 * D].view(T, 2 * D)  # (qk | v) rows, 512 wide

@@ -281,3 +281,48 @@ def test_attention_tc_kv_tile_variants(ops, dev, kv_tile, b, nq, nk):
     assert _relerr(out.cpu(), ref) < 2e-4
     assert _relerr(obf.float().cpu(), ref) < 2e-4
     assert _relerr(out2.cpu(), ref) < 2e-4, 'V^T (K-major) operand path'
+
+
+@pytest.mark.parametrize('split', [1, 3])
+@pytest.mark.parametrize('rows', [128, 77, 1000, 148 * 128 * 2 + 300])
+def test_mlp_block_tc(ops, dev, split, rows):
+    """Fused block tail (csrc/mlp_block_tc.cu) vs the unfused torch-CPU arithmetic of the reference block
+    (nets/segnetvit.py:104-106): proj -> cat -> Linear -> LayerNorm -> GELU -> Linear -> + x.  Ragged row counts
+    exercise the zero-filled tail tile; the largest case gives every CTA several tiles (barrier phases across tiles,
+    accumulator hand-over between tiles)."""
+    import torch.nn.functional as F
+    from pram_b200.nets import _blocks as B
+    g = torch.Generator().manual_seed(rows)
+    proj = torch.nn.Linear(256, 256)
+    mlp = B.mlp_holder(512, 512, 256)
+    with torch.no_grad():
+        for prm in list(proj.parameters()) + list(mlp.parameters()):
+            prm.copy_(torch.randn(prm.shape, generator=g) * (0.05 if prm.dim() == 2 else 0.5))
+        mlp[1].weight.add_(1.0)
+    x = torch.randn(rows, 256, generator=g)
+    ctx = torch.randn(rows, 256, generator=g)
+    with torch.no_grad():
+        ref = x + mlp(torch.cat([x, proj(ctx)], -1))
+    pk = B.pack_block_tail(proj.to(dev), mlp.to(dev))
+    lo = split == 3
+    if not lo:
+        pk['blk.w1.tc'] = ops.Split(pk['blk.w1.tc'].hi, None)
+    cat = torch.cat([x, ctx], 1).to(dev)
+    cat_bf = ops.split_bf16(cat, lo)
+    w3 = ops.split_bf16(mlp[3].weight.detach().float().contiguous(), lo)
+    out = torch.full((rows, 512), 7.0, device=dev)
+    obf = ops.empty_split((rows, 512), dev, lo, zero=True)
+    ops.mlp_block_tc(cat_bf, 512, rows, pk['blk.w1.tc'], pk['blk.b1'], mlp[1].weight.detach(), mlp[1].bias.detach(), w3,
+                     mlp[3].bias.detach(), cat, 512, out, 512, obf, 512, split=split)
+    torch.cuda.synchronize()
+    tol = {1: 3e-2, 3: 2e-4}[split]
+    assert _relerr(out[:, :256].cpu(), ref) < tol
+    assert _relerr(obf.float()[:, :256].cpu(), ref) < (tol if lo else 4e-2)
+    # the right halves of the output rows (the next block's context slots) are not touched
+    assert (out[:, 256:] == 7.0).all() and (obf.hi[:, 256:] == 0).all()
+    # same result again on the same buffers (no state left behind in TMEM / barriers between launches)
+    out2 = torch.empty_like(out)
+    ops.mlp_block_tc(cat_bf, 512, rows, pk['blk.w1.tc'], pk['blk.b1'], mlp[1].weight.detach(), mlp[1].bias.detach(), w3,
+                     mlp[3].bias.detach(), cat, 512, out2, 512, None, 0, split=split)
+    torch.cuda.synchronize()
+    assert torch.equal(out2[:, :256], out[:, :256])
