@@ -175,15 +175,14 @@ typedef struct pram_mlp_block_args {
     const void* a_hi; const void* a_lo;   /* bf16 [T][lda]: columns 0..255 = x, 256..511 = attention context */
     long long lda;
     int T;
-    const void* w1_hi; const void* w1_lo; /* bf16 [512][512] */
-    const float* b1;                      /* [512] */
-    const float* ln_g; const float* ln_b; /* [512] */
-    const void* w3_hi; const void* w3_lo; /* bf16 [256][512] */
-    const float* b3;                      /* [256] */
-    const float* res; long long res_ld;   /* fp32 residual rows, may be NULL */
+    const void* w1_hi; const void* w1_lo; /* bf16 [8][512][64]: tile kb = W1[:, 64 kb : 64 kb + 64] (every TMA box contiguous) */
+    const void* w3_hi; const void* w3_lo; /* bf16 [16][256][32]: tile s = W3[:, 32 s : 32 s + 32] */
+    const float* tables_host;             /* HOST fp32 [b1 512 | ln gamma 512 | ln beta 512 | b3 256] -> kernel parameter block */
+    const float* res; long long res_ld;   /* fp32 residual rows, or NULL: residual = hi + lo of columns 0..255 of a */
     float* out_f32; long long ld_f32;     /* may be NULL */
     void* out_hi; void* out_lo; long long ld_bf;  /* may be NULL */
     int split;                            /* 1: bf16, 3: bf16x3 */
+    long long* dbg;                       /* optional device buffer [grid][8][32] of SM clock stamps (profiling aid), NULL = off */
 } pram_mlp_block_args;
 int pram_mlp_block_tc(const pram_mlp_block_args* args, pram_stream_t stream);
 

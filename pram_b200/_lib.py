@@ -75,12 +75,11 @@ class MlpBlockArgs(C.Structure):
     """Mirror of ``struct pram_mlp_block_args`` (include/pram_b200.h)."""
     _fields_ = [
         ('a_hi', _P), ('a_lo', _P), ('lda', _L), ('T', _I),
-        ('w1_hi', _P), ('w1_lo', _P), ('b1', _P), ('ln_g', _P), ('ln_b', _P),
-        ('w3_hi', _P), ('w3_lo', _P), ('b3', _P),
+        ('w1_hi', _P), ('w1_lo', _P), ('w3_hi', _P), ('w3_lo', _P), ('tables_host', _P),
         ('res', _P), ('res_ld', _L),
         ('out_f32', _P), ('ld_f32', _L),
         ('out_hi', _P), ('out_lo', _P), ('ld_bf', _L),
-        ('split', _I),
+        ('split', _I), ('dbg', _P),
     ]
 
 

@@ -10,7 +10,7 @@
 //   phase B   LayerNorm statistics (two exact passes over TMEM), then per 64-column k-block:
 //             y = GELU(LN(h + b1)) -> split bf16 (hi, lo) written as a SWIZZLE_128B K-major UMMA operand into a 4-slot
 //             shared-memory ring; the MMA warp consumes the ring against TMA-streamed W3 tiles:
-//             out[128 x 256] += y_kblock . W3_kblock^T   (accumulator re-uses TMEM columns 0..255 once k-blocks 0..3,
+//             out[128 x 256] += y_kblock . W3_kblock^T   (N = 256 per MMA; accumulator re-uses TMEM columns 0..255 once k-blocks 0..3,
 //             which live there, have been converted)
 //   phase C   out + b3 + residual -> fp32 and split-bf16 rows of the next activation buffer
 //
@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace mb {
 
@@ -34,7 +35,8 @@ constexpr int EPI_WARPS = 16;
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;             // 576
 constexpr int A_BYTES = BM * BK * 2;                         // 16 KB: 128 rows x 128 B
 constexpr int W1_BYTES = 256 * BK * 2;                       // 32 KB: one N half of W1, one k-block
-constexpr int W3_BYTES = 128 * BK * 2;                       // 16 KB: one N half of W3, one k-block
+constexpr int BK3 = 32;                                      // W3 is streamed in half k-blocks: N = 256 rows x 32 K columns
+constexpr int W3_BYTES = 256 * BK3 * 2;                      // 16 KB per plane (SWIZZLE_64B rows of 64 B)
 constexpr int STAGE_A = 2 * A_BYTES + 2 * W1_BYTES;          // 96 KB (both planes; SPLIT = 1 uses the hi halves only)
 constexpr int NSTAGE_A = 2;
 constexpr int SLOT = 2 * A_BYTES;                            // 32 KB ring slot: hi | lo
@@ -44,18 +46,26 @@ constexpr int NSTAGE_3 = 3;
 constexpr int RING_OFF = 0, W3_OFF = NSLOT * SLOT;           // 0, 128 KB
 constexpr int REGION = W3_OFF + NSTAGE_3 * STAGE_3;          // 224 KB  (>= NSTAGE_A * STAGE_A = 192 KB)
 constexpr int RED_OFF = RING_OFF + 3 * SLOT;                 // LN partial sums live in ring slot 3 (written last)
-constexpr int BAR_OFF = REGION;                              // barriers (256 B) then the b3 table (1 KB)
-constexpr int SMEM_BYTES = 1024 + REGION + 256 + D_OUT * 4;
+constexpr int BAR_OFF = REGION;                              // barriers (256 B)
+constexpr int SMEM_BYTES = 1024 + REGION + 256;
 static_assert(NSTAGE_A * STAGE_A <= REGION, "phase A stages must fit the multiplexed region");
 static_assert(SMEM_BYTES <= 227 * 1024, "dynamic shared memory budget of sm_100a exceeded");
 
 struct Args {
     int T;
-    const float* b1; const float* ln_g; const float* ln_b; const float* b3;
-    const float* res; long long res_ld;
+    const float* res; long long res_ld;                          // fp32 residual rows, or NULL:
+    const __nv_bfloat16* xa_hi; const __nv_bfloat16* xa_lo; long long lda;  // ... residual = hi + lo of the A rows (x)
     float* out_f32; long long ld_f32;
     __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; long long ld_bf;
+    long long* dbg;   // optional timeline: [CTA][tile iteration (<= 8)][32] SM clock stamps (tools/bench_block.py --timeline)
 };
+__device__ __forceinline__ void stamp(const Args& p, uint32_t it, int slot) {
+    if (p.dbg && it < 8) p.dbg[((long long)blockIdx.x * 8 + it) * 32 + slot] = clock64();
+}
+// Per-column tables travel as a KERNEL PARAMETER (constant bank): every epilogue access is warp-uniform, so it becomes
+// one LDC broadcast instead of a global load (ncu on the first version: the 12 LDG per 16 elements in front of each
+// k-block were the longest stall of the LayerNorm pass).
+struct alignas(16) Tables { float b1[D_HID]; float g[D_HID]; float be[D_HID]; float b3[D_OUT]; };
 
 // ---------------------------------------------------------------------------------------- PTX (see gemm_tc.cu)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,6 +102,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -101,6 +114,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {  // K-major SWIZ
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
+    return d;
+}
+// K-major SWIZZLE_64B operand (rows of 64 B = 32 bf16): 8-row atoms of 512 B -> SBO = 512 B, layout type 4
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
     return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
@@ -150,6 +172,21 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
     __nv_bfloat162 l = __floats2bfloat162_rn(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
     lo = *reinterpret_cast<uint32_t*>(&l);
 }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// exact (erf) GELU in 13 instructions: with erf(|x|) = 1 - P(t) exp(-x^2), t = 1 / (1 + p |x|) (Abramowitz-Stegun 7.1.26,
+// abs error <= 1.5e-7) and x = y / sqrt(2):   GELU(y) = 0.5 y (1 + erf(x)) = max(y, 0) - |y| * [0.5 P(t)] * exp(-y^2 / 2)
+// (both signs).  1/sqrt(2), 0.5 and log2(e) are folded into the constants; rcp / ex2 are single MUFU instructions.
+__device__ __forceinline__ float gelu_fast(float y) {
+    const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(y), 1.f));
+    float pl = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    pl = fmaf(pl, t, 0.5f * 1.421413741f);
+    pl = fmaf(pl, t, 0.5f * -0.284496736f);
+    pl = fmaf(pl, t, 0.5f * 0.254829592f);
+    pl *= t;
+    const float ex = ex2_approx((y * -0.72134752044448170368f) * y);   // exp(-y^2 / 2)
+    return fmaf(-fabsf(y), pl * ex, fmaxf(y, 0.f));
+}
 // erf by Abramowitz-Stegun 7.1.26 (abs error <= 1.5e-7), same routine as the split-bf16 LayerNorm kernel (nn_simt.cu)
 __device__ __forceinline__ float erf_as(float x) {
     const float z = fabsf(x);
@@ -164,19 +201,19 @@ __device__ __forceinline__ float erf_as(float x) {
 
 // barrier block layout (uint64 each)
 enum : int { B_FULLA = 0, B_EMPTYA = 2, B_HFULL = 4, B_SLOTF = 5, B_SLOTE = 9, B_W3F = 13, B_W3E = 16, B_ACCF = 19, B_ACCE = 20,
-             B_COUNT = 21 };
+             B_H1FULL = 21, B_COUNT = 22 };
 
 template <int SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
     const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
     const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
-    const __grid_constant__ CUtensorMap map_w3_hi, const __grid_constant__ CUtensorMap map_w3_lo, const Args p) {
+    const __grid_constant__ CUtensorMap map_w3_hi, const __grid_constant__ CUtensorMap map_w3_lo, const Args p,
+    const __grid_constant__ Tables tb) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + B_COUNT);
-    float* b3_s = reinterpret_cast<float*>(smem + BAR_OFF + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = (p.T + BM - 1) / BM;
@@ -188,6 +225,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
         if (SPLIT == 3) { prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w1_lo); prefetch_tmap(&map_w3_lo); }
         for (int s = 0; s < NSTAGE_A; ++s) { mbar_init(&bars[B_FULLA + s], 1); mbar_init(&bars[B_EMPTYA + s], 1); }
         mbar_init(&bars[B_HFULL], 1);
+        mbar_init(&bars[B_H1FULL], 1);
         for (int s = 0; s < NSLOT; ++s) { mbar_init(&bars[B_SLOTF + s], EPI_WARPS); mbar_init(&bars[B_SLOTE + s], 1); }
         for (int s = 0; s < NSTAGE_3; ++s) { mbar_init(&bars[B_W3F + s], 1); mbar_init(&bars[B_W3E + s], 1); }
         mbar_init(&bars[B_ACCF], 1);
@@ -199,7 +237,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + D_OUT) b3_s[threadIdx.x - 64] = p.b3 ? p.b3[threadIdx.x - 64] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -221,29 +258,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
                     const uint32_t st = sbase + sa * STAGE_A;
                     mbar_expect_tx(&bars[B_FULLA + sa], A_TX);
                     tma_load_2d(st, &map_a_hi, &bars[B_FULLA + sa], kb * BK, row0);
-                    tma_load_2d(st + 2 * A_BYTES, &map_w1_hi, &bars[B_FULLA + sa], kb * BK, half * 256);
+                    tma_load_2d(st + 2 * A_BYTES, &map_w1_hi, &bars[B_FULLA + sa], 0, kb * D_HID + half * 256);
                     if (SPLIT == 3) {
                         tma_load_2d(st + A_BYTES, &map_a_lo, &bars[B_FULLA + sa], kb * BK, row0);
-                        tma_load_2d(st + 2 * A_BYTES + W1_BYTES, &map_w1_lo, &bars[B_FULLA + sa], kb * BK, half * 256);
+                        tma_load_2d(st + 2 * A_BYTES + W1_BYTES, &map_w1_lo, &bars[B_FULLA + sa], 0, kb * D_HID + half * 256);
                     }
                     if (++sa == NSTAGE_A) { sa = 0; pha ^= 1; }
                 }
                 // the first GEMM has retired: its stages may be overwritten by the W3 tiles
                 mbar_wait(&bars[B_HFULL], it & 1, 2);
-                for (int s = 0; s < 2 * KB2; ++s) {
-                    const int j = s >> 1, nh = s & 1;
+                // pull the NEXT tile's activation rows into L2 while this tile's epilogue / second GEMM run: its first operand
+                // stages then land in ~1.5k cycles instead of a DRAM round trip on the critical path between two tiles
+                if (tile + (int)gridDim.x < ntiles) {
+                    const int nrow0 = (tile + (int)gridDim.x) * BM;
+                    for (int kb = 0; kb < KB1; ++kb) {
+                        tma_prefetch_2d(&map_a_hi, kb * BK, nrow0);
+                        if (SPLIT == 3) tma_prefetch_2d(&map_a_lo, kb * BK, nrow0);
+                    }
+                }
+                for (int s = 0; s < 2 * KB2; ++s) {   // 16 half k-blocks of W3, all 256 output rows each
                     mbar_wait(&bars[B_W3E + s3], ph3 ^ 1, 3);
                     const uint32_t st = sbase + W3_OFF + s3 * STAGE_3;
                     mbar_expect_tx(&bars[B_W3F + s3], W3_TX);
-                    tma_load_2d(st, &map_w3_hi, &bars[B_W3F + s3], j * BK, nh * 128);
-                    if (SPLIT == 3) tma_load_2d(st + W3_BYTES, &map_w3_lo, &bars[B_W3F + s3], j * BK, nh * 128);
+                    tma_load_2d(st, &map_w3_hi, &bars[B_W3F + s3], 0, s * D_OUT);
+                    if (SPLIT == 3) tma_load_2d(st + W3_BYTES, &map_w3_lo, &bars[B_W3F + s3], 0, s * D_OUT);
                     if (++s3 == NSTAGE_3) { s3 = 0; ph3 ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp, one elected lane per instruction) =====================
-        constexpr uint32_t idesc1 = make_idesc(BM, 256), idesc2 = make_idesc(BM, 128);
+        constexpr uint32_t idesc1 = make_idesc(BM, 256);
         int sa = 0; uint32_t pha = 0;
         int s3 = 0; uint32_t ph3 = 0;
         uint32_t it = 0;
@@ -251,6 +296,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
             // ---- phase A: h = [x | ctx] . W1^T, N half 1 -> columns 256..511, then N half 0 -> columns 0..255 ----
             for (int s = 0; s < 2 * KB1; ++s) {
                 const int half = (s < KB1) ? 1 : 0, kb = s & (KB1 - 1);
+                if (s == 1 && lane == 0) stamp(p, it, 8);   // first operand stage of this tile has landed
                 if (s == KB1) {  // columns 0..255 still hold the previous tile's output accumulator until its epilogue read it
                     mbar_wait(&bars[B_ACCE], (it & 1) ^ 1, 4);
                     tc_fence_after();
@@ -270,9 +316,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
                     }
                 }
                 umma_commit(&bars[B_EMPTYA + sa]);
+                if (s == KB1 - 1) umma_commit(&bars[B_H1FULL]);  // columns 256..511 complete: their LN partial sums can start
                 if (++sa == NSTAGE_A) { sa = 0; pha ^= 1; }
             }
             umma_commit(&bars[B_HFULL]);
+            if (lane == 0) stamp(p, it, 9);                 // all first-GEMM MMAs issued
             // ---- phase B: out = GELU(LN(h)) . W3^T from the ring; accumulator in columns 0..255 (two N halves of 128) ----
             for (int j = 0; j < KB2; ++j) {
                 const int slot = j & (NSLOT - 1);
@@ -283,26 +331,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
                 }
                 tc_fence_after();
                 const uint32_t ring = sbase + RING_OFF + slot * SLOT;
-                for (int nh = 0; nh < 2; ++nh) {
+                // N = 256 per instruction: with two N = 128 halves the A operand was read from shared memory twice and the
+                // tensor pipe became shared-memory-bandwidth bound (8 KB per 64-cycle MMA = 128 B/clk); the W3 tiles are
+                // therefore streamed as half k-blocks {256 rows x 32 K columns} (SWIZZLE_64B), two UMMA_K steps each
+                for (int kh = 0; kh < 2; ++kh) {
                     mbar_wait(&bars[B_W3F + s3], ph3, 8);
                     tc_fence_after();
                     const uint32_t w = sbase + W3_OFF + s3 * STAGE_3;
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(nh * 128);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint32_t koff = k * UMMA_K * 2;
-                        umma(d_tmem, make_desc(ring + koff), make_desc(w + koff), idesc2, (j | k) != 0);
+                    for (int k = 0; k < BK3 / UMMA_K; ++k) {
+                        const uint32_t aoff = (uint32_t)((kh * 2 + k) * UMMA_K * 2), boff = (uint32_t)(k * UMMA_K * 2);
+                        umma(tmem_base, make_desc(ring + aoff), make_desc_sw64(w + boff), idesc1, (j | kh | k) != 0);
                         if (SPLIT == 3) {
-                            umma(d_tmem, make_desc(ring + A_BYTES + koff), make_desc(w + koff), idesc2, 1);
-                            umma(d_tmem, make_desc(ring + koff), make_desc(w + W3_BYTES + koff), idesc2, 1);
+                            umma(tmem_base, make_desc(ring + A_BYTES + aoff), make_desc_sw64(w + boff), idesc1, 1);
+                            umma(tmem_base, make_desc(ring + aoff), make_desc_sw64(w + W3_BYTES + boff), idesc1, 1);
                         }
                     }
                     umma_commit(&bars[B_W3E + s3]);
                     if (++s3 == NSTAGE_3) { s3 = 0; ph3 ^= 1; }
                 }
                 umma_commit(&bars[B_SLOTE + slot]);
+                if (lane == 0) stamp(p, it, 24 + j);
             }
             umma_commit(&bars[B_ACCF]);
+            if (lane == 0) stamp(p, it, 10);                // all second-GEMM MMAs issued
         }
     } else {
         // ===================== epilogue warps =====================
@@ -313,55 +365,59 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
         const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t red = sbase + RED_OFF;              // float red[2][4][128]
         const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
-        const float4* __restrict__ b1v = reinterpret_cast<const float4*>(p.b1);
-        const float4* __restrict__ gv = reinterpret_cast<const float4*>(p.ln_g);
-        const float4* __restrict__ bv = reinterpret_cast<const float4*>(p.ln_b);
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const long long grow = (long long)tile * BM + r;
             const bool row_ok = grow < p.T;
-            mbar_wait(&bars[B_HFULL], it & 1, 9);
-            tc_fence_after();
-            // ---- LayerNorm statistics: two exact passes (mean, then centred sum of squares), 128 columns per thread ----
+            if (e == 0 && lane == 0) stamp(p, it, 0);
+            // ---- LayerNorm statistics in ONE pass over TMEM with shifted data: pivot c = one element of the row,
+            //      S1 = sum(x - c), S2 = sum((x - c)^2); mean = c + S1/n, var = S2/n - (S1/n)^2.  The pivot is a sample of
+            //      the row, so |mean - c| ~ std and the subtraction loses no more than a couple of bits.  Each thread sums
+            //      64 columns of N half 1 as soon as that half has retired (while the MMA warp computes half 0), then 64
+            //      columns of half 0.
             float mean, rstd;
             {
-                float s = 0.f;
+                float s1 = 0.f, s2 = 0.f, piv = 0.f;
 #pragma unroll 1
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int c0 = part * 128 + cc * 32;
-                    uint32_t v[32];
-                    tmem_ld32(tq + c0, v);
+                for (int hh = 1; hh >= 0; --hh) {
+                    if (hh == 1) {
+                        mbar_wait(&bars[B_H1FULL], it & 1, 12);
+                        tc_fence_after();
+                        uint32_t v0[1];
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v0[0]) : "r"(tq + 256));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        piv = __uint_as_float(v0[0]) + tb.b1[256];
+                    } else {
+                        mbar_wait(&bars[B_HFULL], it & 1, 9);
+                        tc_fence_after();
+                        if (e == 0 && lane == 0) stamp(p, it, 1);
+                    }
+#pragma unroll 1
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int c0 = hh * 256 + part * 64 + cc * 32;
+                        uint32_t v[32];
+                        tmem_ld32(tq + c0, v);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 b = __ldg(b1v + (c0 >> 2) + i);
-                        s += (__uint_as_float(v[4 * i]) + b.x) + (__uint_as_float(v[4 * i + 1]) + b.y) +
-                             (__uint_as_float(v[4 * i + 2]) + b.z) + (__uint_as_float(v[4 * i + 3]) + b.w);
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 b = *reinterpret_cast<const float4*>(&tb.b1[c0 + 4 * i]);
+                            const float d0 = __uint_as_float(v[4 * i]) + (b.x - piv), d1 = __uint_as_float(v[4 * i + 1]) + (b.y - piv);
+                            const float d2 = __uint_as_float(v[4 * i + 2]) + (b.z - piv), d3 = __uint_as_float(v[4 * i + 3]) + (b.w - piv);
+                            s1 += (d0 + d1) + (d2 + d3);
+                            s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
+                        }
                     }
                 }
-                sts_f32(red + 4 * (part * 128 + r), s);
+                sts_f32(red + 4 * (part * 128 + r), s1);
+                sts_f32(red + 4 * (512 + part * 128 + r), s2);
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
-                mean = (lds_f32(red + 4 * r) + lds_f32(red + 4 * (128 + r)) + lds_f32(red + 4 * (256 + r)) + lds_f32(red + 4 * (384 + r))) *
-                       (1.f / D_HID);
-                float qs = 0.f;
-#pragma unroll 1
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int c0 = part * 128 + cc * 32;
-                    uint32_t v[32];
-                    tmem_ld32(tq + c0, v);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 b = __ldg(b1v + (c0 >> 2) + i);
-                        const float d0 = __uint_as_float(v[4 * i]) + b.x - mean, d1 = __uint_as_float(v[4 * i + 1]) + b.y - mean;
-                        const float d2 = __uint_as_float(v[4 * i + 2]) + b.z - mean, d3 = __uint_as_float(v[4 * i + 3]) + b.w - mean;
-                        qs += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-                    }
-                }
-                sts_f32(red + 4 * (512 + part * 128 + r), qs);
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
-                const float var = (lds_f32(red + 4 * (512 + r)) + lds_f32(red + 4 * (640 + r)) + lds_f32(red + 4 * (768 + r)) +
-                                   lds_f32(red + 4 * (896 + r))) * (1.f / D_HID);
-                rstd = rsqrtf(var + 1e-5f);
+                const float t1 = (lds_f32(red + 4 * r) + lds_f32(red + 4 * (128 + r)) + lds_f32(red + 4 * (256 + r)) + lds_f32(red + 4 * (384 + r))) *
+                                 (1.f / D_HID);
+                const float t2 = (lds_f32(red + 4 * (512 + r)) + lds_f32(red + 4 * (640 + r)) + lds_f32(red + 4 * (768 + r)) +
+                                  lds_f32(red + 4 * (896 + r))) * (1.f / D_HID);
+                mean = piv + t1;
+                rstd = rsqrtf(fmaxf(t2 - t1 * t1, 0.f) + 1e-5f);
             }
+            if (e == 0 && lane == 0) stamp(p, it, 2);
             // ---- per k-block: LN + GELU + split -> ring slot (SWIZZLE_128B K-major rows), 16 columns per thread ----
 #pragma unroll 1
             for (int j = 0; j < KB2; ++j) {
@@ -372,13 +428,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 b = __ldg(b1v + (c0 >> 2) + i), g = __ldg(gv + (c0 >> 2) + i), be = __ldg(bv + (c0 >> 2) + i);
-                    float y[4] = {(__uint_as_float(v[4 * i]) + b.x - mean) * rstd * g.x + be.x,
-                                  (__uint_as_float(v[4 * i + 1]) + b.y - mean) * rstd * g.y + be.y,
-                                  (__uint_as_float(v[4 * i + 2]) + b.z - mean) * rstd * g.z + be.z,
-                                  (__uint_as_float(v[4 * i + 3]) + b.w - mean) * rstd * g.w + be.w};
+                    const float4 b = *reinterpret_cast<const float4*>(&tb.b1[c0 + 4 * i]);
+                    const float4 g = *reinterpret_cast<const float4*>(&tb.g[c0 + 4 * i]);
+                    const float4 be = *reinterpret_cast<const float4*>(&tb.be[c0 + 4 * i]);
+                    float y[4] = {fmaf(__uint_as_float(v[4 * i]) + (b.x - mean), rstd * g.x, be.x),
+                                  fmaf(__uint_as_float(v[4 * i + 1]) + (b.y - mean), rstd * g.y, be.y),
+                                  fmaf(__uint_as_float(v[4 * i + 2]) + (b.z - mean), rstd * g.z, be.z),
+                                  fmaf(__uint_as_float(v[4 * i + 3]) + (b.w - mean), rstd * g.w, be.w)};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) y[k] = 0.5f * y[k] * (1.f + erf_as(y[k] * 0.70710678118654752440f));
+                    for (int k = 0; k < 4; ++k) y[k] = gelu_fast(y[k]);
                     split2(y[0], y[1], hi[2 * i], lo[2 * i]);
                     split2(y[2], y[3], hi[2 * i + 1], lo[2 * i + 1]);
                 }
@@ -401,37 +459,63 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
                 tc_fence_before();                                            // and this warp's TMEM reads are complete
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[B_SLOTF + slot]);
+                if (e == 0 && lane == 0) stamp(p, it, 16 + j);
             }
-            // ---- phase C: out = acc + b3 + residual -> fp32 + split bf16; 64 columns per thread in two chunks ----
-            float4 rv[8];
-            {
-                const int n0 = part * 64;
+            // ---- phase C: out = acc + b3 + residual -> split bf16 (+ fp32); 64 columns per thread in two chunks ----
+            // residual: fp32 rows when given, else x = hi + lo of this tile's own A rows (just streamed by phase A, L2-hot):
+            // the activation stream then lives in HBM as its two bf16 planes only -- 1 KB per token written per block
+            // instead of 3 KB moved (fp32 read + fp32 write + planes), which was the DRAM burst that stalled all SMs at once
+            auto load_res = [&](int n0, float4 (&rv)[8]) {
+                if (!row_ok) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    rv[i] = (p.res && row_ok) ? __ldg(reinterpret_cast<const float4*>(p.res + grow * p.res_ld + n0) + i)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+                    for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else if (p.res) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rv[i] = __ldg(reinterpret_cast<const float4*>(p.res + grow * p.res_ld + n0) + i);
+                } else {
+                    const uint4* ph = reinterpret_cast<const uint4*>(p.xa_hi + grow * p.lda + n0);
+                    const uint4* pl = reinterpret_cast<const uint4*>(p.xa_lo + grow * p.lda + n0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 h = __ldg(ph + i);
+                        uint4 l = make_uint4(0u, 0u, 0u, 0u);
+                        if (SPLIT == 3) l = __ldg(pl + i);
+                        rv[2 * i] = make_float4(__uint_as_float(h.x << 16) + __uint_as_float(l.x << 16),
+                                                __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u),
+                                                __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16),
+                                                __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u));
+                        rv[2 * i + 1] = make_float4(__uint_as_float(h.z << 16) + __uint_as_float(l.z << 16),
+                                                    __uint_as_float(h.z & 0xffff0000u) + __uint_as_float(l.z & 0xffff0000u),
+                                                    __uint_as_float(h.w << 16) + __uint_as_float(l.w << 16),
+                                                    __uint_as_float(h.w & 0xffff0000u) + __uint_as_float(l.w & 0xffff0000u));
+                    }
+                }
+            };
+            if (e == 0 && lane == 0) stamp(p, it, 3);
+            float4 rv[8];
+            load_res(part * 64, rv);  // independent of the accumulator: overlaps the tail of the second GEMM
             mbar_wait(&bars[B_ACCF], it & 1, 11);
             tc_fence_after();
+            if (e == 0 && lane == 0) stamp(p, it, 4);
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
                 const int n0 = part * 64 + cc * 32;
                 uint32_t v[32];
                 tmem_ld32(tq + n0, v);
                 if (cc == 1) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        rv[i] = (p.res && row_ok) ? __ldg(reinterpret_cast<const float4*>(p.res + grow * p.res_ld + n0) + i)
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                    // the accumulator is in registers: hand TMEM columns 0..255 back to the MMA warp before the stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars[B_ACCE]);
+                    load_res(n0, rv);
                 }
                 if (row_ok) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const uint32_t ba = smem_u32(b3_s) + 4 * (n0 + 4 * i);
-                        const float f0 = __uint_as_float(v[4 * i]) + lds_f32(ba) + rv[i].x;
-                        const float f1 = __uint_as_float(v[4 * i + 1]) + lds_f32(ba + 4) + rv[i].y;
-                        const float f2 = __uint_as_float(v[4 * i + 2]) + lds_f32(ba + 8) + rv[i].z;
-                        const float f3 = __uint_as_float(v[4 * i + 3]) + lds_f32(ba + 12) + rv[i].w;
+                        const float f0 = __uint_as_float(v[4 * i]) + tb.b3[n0 + 4 * i] + rv[i].x;
+                        const float f1 = __uint_as_float(v[4 * i + 1]) + tb.b3[n0 + 4 * i + 1] + rv[i].y;
+                        const float f2 = __uint_as_float(v[4 * i + 2]) + tb.b3[n0 + 4 * i + 2] + rv[i].z;
+                        const float f3 = __uint_as_float(v[4 * i + 3]) + tb.b3[n0 + 4 * i + 3] + rv[i].w;
                         if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + n0 + 4 * i) = make_float4(f0, f1, f2, f3);
                         split2(f0, f1, v[4 * i], v[4 * i + 2]);       // re-use v: [4i] = hi01, [4i+1] = hi23, [4i+2] = lo01, [4i+3] = lo23
                         uint32_t h23, l23;
@@ -450,9 +534,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[B_ACCE]);
+            if (e == 0 && lane == 0) stamp(p, it, 5);
         }
     }
     tc_fence_before();
@@ -482,16 +564,17 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D bf16 row-major matrix [rows][ld] -> boxes of {64 columns, box_rows rows}, SWIZZLE_128B
-static int encode2d(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+static int encode2d(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows,
+                    int box_cols = BK) {
     EncodeTiledFn fn = get_encode();
     if (!fn) return PRAM_ERR_CUDA;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t str[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, str, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? PRAM_OK : PRAM_ERR_CUDA;
 }
 
@@ -502,20 +585,21 @@ struct pram_mlp_block_args {
     const void* a_hi; const void* a_lo;   // bf16 [T][lda]: columns 0..255 = x, 256..511 = attention context (pre-projection)
     long long lda;
     int T;
-    const void* w1_hi; const void* w1_lo; // bf16 [512][512]: mlp.0 with proj folded into its right half
-    const float* b1;                      // [512]
-    const float* ln_g; const float* ln_b; // [512]
-    const void* w3_hi; const void* w3_lo; // bf16 [256][512]: mlp.3
-    const float* b3;                      // [256]
-    const float* res; long long res_ld;   // fp32 residual rows (x), may be NULL
+    const void* w1_hi; const void* w1_lo; // bf16 [8][512][64]: mlp.0 with proj folded into its right half, tiled k-block major
+                                          // (tile kb = W1[:, 64 kb : 64 kb + 64])
+    const void* w3_hi; const void* w3_lo; // bf16 [16][256][32]: mlp.3, tiled half-k-block major (tile s = W3[:, 32 s : 32 s + 32])
+    const float* tables_host;             // HOST pointer, fp32 [b1 512 | ln gamma 512 | ln beta 512 | b3 256]: copied into the
+                                          // kernel's parameter block (constant bank) at launch
+    const float* res; long long res_ld;   // fp32 residual rows, or NULL: the residual is x = hi + lo of columns 0..255 of `a`
     float* out_f32; long long ld_f32;     // may be NULL
     void* out_hi; void* out_lo; long long ld_bf;  // may be NULL
     int split;                            // 1: bf16, 3: bf16x3
+    long long* dbg;                       // optional device buffer [grid][8][32] of SM clock stamps (profiling aid), NULL = off
 };
 
 PRAM_API int pram_mlp_block_tc(const pram_mlp_block_args* a, cudaStream_t stream) {
     using namespace mb;
-    if (!a || !a->a_hi || !a->w1_hi || !a->w3_hi || !a->b1 || !a->ln_g || !a->ln_b || a->T <= 0) return PRAM_ERR_ARG;
+    if (!a || !a->a_hi || !a->w1_hi || !a->w3_hi || !a->tables_host || a->T <= 0) return PRAM_ERR_ARG;
     if (a->split != 1 && a->split != 3) return PRAM_ERR_ARG;
     if (a->split == 3 && (!a->a_lo || !a->w1_lo || !a->w3_lo)) return PRAM_ERR_ARG;
     if (!a->out_f32 && !a->out_hi) return PRAM_ERR_ARG;
@@ -529,13 +613,18 @@ PRAM_API int pram_mlp_block_tc(const pram_mlp_block_args* a, cudaStream_t stream
     int rc;
     if ((rc = encode2d(&ah, a->a_hi, a->T, D_IN, a->lda, BM))) return rc;
     if ((rc = encode2d(&al, a->a_lo ? a->a_lo : a->a_hi, a->T, D_IN, a->lda, BM))) return rc;
-    if ((rc = encode2d(&w1h, a->w1_hi, D_HID, D_IN, D_IN, 256))) return rc;
-    if ((rc = encode2d(&w1l, a->w1_lo ? a->w1_lo : a->w1_hi, D_HID, D_IN, D_IN, 256))) return rc;
-    if ((rc = encode2d(&w3h, a->w3_hi, D_OUT, D_HID, D_HID, 128))) return rc;
-    if ((rc = encode2d(&w3l, a->w3_lo ? a->w3_lo : a->w3_hi, D_OUT, D_HID, D_HID, 128))) return rc;
+    // weights arrive pre-tiled (k-block major): every TMA box is one contiguous 32 KB / 16 KB run of memory
+    if ((rc = encode2d(&w1h, a->w1_hi, (long long)KB1 * D_HID, BK, BK, 256))) return rc;
+    if ((rc = encode2d(&w1l, a->w1_lo ? a->w1_lo : a->w1_hi, (long long)KB1 * D_HID, BK, BK, 256))) return rc;
+    if ((rc = encode2d(&w3h, a->w3_hi, (long long)(D_HID / BK3) * D_OUT, BK3, BK3, 256, BK3))) return rc;
+    if ((rc = encode2d(&w3l, a->w3_lo ? a->w3_lo : a->w3_hi, (long long)(D_HID / BK3) * D_OUT, BK3, BK3, 256, BK3))) return rc;
     Args k;
-    k.T = a->T; k.b1 = a->b1; k.ln_g = a->ln_g; k.ln_b = a->ln_b; k.b3 = a->b3;
+    k.T = a->T;
     k.res = a->res; k.res_ld = a->res_ld; k.out_f32 = a->out_f32; k.ld_f32 = a->ld_f32;
+    k.xa_hi = (const __nv_bfloat16*)a->a_hi; k.xa_lo = (const __nv_bfloat16*)(a->a_lo ? a->a_lo : a->a_hi); k.lda = a->lda;
+    k.dbg = a->dbg;
+    Tables tb;
+    memcpy(&tb, a->tables_host, sizeof(Tables));
     k.out_hi = (__nv_bfloat16*)a->out_hi; k.out_lo = (__nv_bfloat16*)a->out_lo; k.ld_bf = a->ld_bf;
     const int ntiles = (a->T + BM - 1) / BM;
     const int grid = ntiles < sms ? ntiles : sms;
@@ -543,12 +632,12 @@ PRAM_API int pram_mlp_block_tc(const pram_mlp_block_args* a, cudaStream_t stream
         auto kern = mlp_block_kernel<3>;
         static bool attr = false;
         if (!attr) { PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
-        kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ah, al, w1h, w1l, w3h, w3l, k);
+        kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ah, al, w1h, w1l, w3h, w3l, k, tb);
     } else {
         auto kern = mlp_block_kernel<1>;
         static bool attr = false;
         if (!attr) { PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
-        kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ah, al, w1h, w1l, w3h, w3l, k);
+        kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ah, al, w1h, w1l, w3h, w3l, k, tb);
     }
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;

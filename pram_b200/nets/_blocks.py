@@ -98,7 +98,12 @@ def pack_block_tail(proj: nn.Linear, mlp: nn.Sequential) -> Dict[str, torch.Tens
     wp, bp = proj.weight.detach().double(), proj.bias.detach().double()
     w1 = torch.cat([w0[:, :D], w0[:, D:] @ wp], 1)
     b1 = b0 + w0[:, D:] @ bp
-    return {'blk.w1.tc': ops.split_bf16(w1.float().contiguous()), 'blk.b1': b1.float().contiguous()}
+    tables = torch.cat([b1.float(), mlp[1].weight.detach().float(), mlp[1].bias.detach().float(),
+                        mlp[3].bias.detach().float()]).cpu().contiguous()  # host: becomes a kernel parameter block
+    # k-block-major tiles: every TMA box of the kernel is one contiguous run of memory
+    w1t = w1.float().view(2 * D, 8, 64).permute(1, 0, 2).contiguous()                           # [8][512][64]
+    w3t = mlp[3].weight.detach().float().view(D, 16, 32).permute(1, 0, 2).contiguous()          # [16][256][32]
+    return {'blk.w1.tc': ops.split_bf16(w1t), 'blk.w3.tc': ops.split_bf16(w3t), 'blk.tables': tables}
 
 
 def pack_mlp(mlp: nn.Sequential, pre: str) -> Dict[str, torch.Tensor]:
@@ -119,6 +124,7 @@ class Workspace:
         self.split = split  # 0: fp32 CUDA-core path; 1 / 3: tcgen05 path with bf16 / bf16x3 operands
         self.ctx_in_bf = False
         self.fused = bool(split) and FUSED_BLOCK
+        self.keep_f32 = False  # fused path only: also maintain the fp32 activation rows (ws.x) next to the bf16 planes
         if split:
             lo = split == 3
             self.cat_bf = [ops.empty_split((tokens, 2 * D), device, lo), ops.empty_split((tokens, 2 * D), device, lo)]
@@ -187,8 +193,11 @@ def _finish_block(ws: Workspace, pk: Dict[str, torch.Tensor]):
                 cbf.hi[:, D:].copy_(ws.ctx_bf.hi)
                 if cbf.lo is not None:
                     cbf.lo[:, D:].copy_(ws.ctx_bf.lo)
-            ops.mlp_block_tc(cbf, 2 * D, T, pk['blk.w1.tc'], pk['blk.b1'], pk['mlp.ln.g'], pk['mlp.ln.b'], pk['mlp.3.tc'],
-                             pk['mlp.3.b'], cat, 2 * D, nxt, 2 * D, nbf, 2 * D, split=ws.split)
+            # the fp32 copy of the activations is only kept when a CUDA-core consumer needs it (AdaGML's pooling / compaction);
+            # otherwise the stream lives as its two bf16 planes and the kernel takes the residual from them
+            f32 = ws.keep_f32
+            ops.mlp_block_tc(cbf, 2 * D, T, pk['blk.w1.tc'], pk['blk.w3.tc'], pk['blk.tables'], cat if f32 else None, 2 * D,
+                             nxt if f32 else None, 2 * D, nbf, 2 * D, split=ws.split)
             ws.cur ^= 1
             return
         linear(ws, None, ws.ctx_bf, D, T, D, D, pk, 'proj', out_bf=ops.split_cols(cbf, D), ld_bf=2 * D)

@@ -82,6 +82,7 @@ class AdaGML(GML):
         m_full, n_full = d0.shape[1], d1.shape[1]
         cos, sin = self._encode(pk, data)
         ws = B.Workspace(m_full + n_full, dev, self._split)
+        ws.keep_f32 = True  # the pooling MLPs and the token compaction read the fp32 activation rows
         self._input_tokens(pk, ws, d0, d1)
         ind0 = torch.arange(m_full, device=dev)
         ind1 = torch.arange(n_full, device=dev)
@@ -117,6 +118,7 @@ class AdaGML(GML):
                         raise ValueError('AdaGML pruned a keypoint set to zero tokens (the reference raises at '
                                          'nets/adagml.py:500 in the same situation)')
                     ws = B.Workspace(m + n, dev, self._split)
+                    ws.keep_f32 = True
                     ws.x[:, :256] = x
                     if ws.split:
                         xs = ops.split_bf16(x, ws.split == 3)

@@ -350,23 +350,28 @@ def linear_tc(a: Split, lda: int, rows: int, k: int, w: Split, n: int, bias: Opt
             1 if w_batched else 0, bias, res, ldres, relu, out_f32, ld_f32, out_bf, ld_bf, None, 0, False, split, bn, qkv)
 
 
-def mlp_block_tc(a: Split, lda: int, rows: int, w1: Split, b1: Tensor, ln_g: Tensor, ln_b: Tensor, w3: Split, b3: Tensor,
+def mlp_block_tc(a: Split, lda: int, rows: int, w1: Split, w3: Split, tables: Tensor,
                  res: Optional[Tensor], res_ld: int, out_f32: Optional[Tensor], ld_f32: int, out_bf: Optional[Split],
-                 ld_bf: int, split: int = 3):
+                 ld_bf: int, split: int = 3, dbg: Optional[Tensor] = None):
     """Fused transformer-block tail on tensor cores (csrc/mlp_block_tc.cu): a = [x | ctx] rows [rows, 512] (split bf16,
     row stride ``lda``), w1 [512,512] = mlp.0 with the attention projection folded in, LayerNorm + GELU, w3 [256,512] =
-    mlp.3, + residual -> fp32 / split-bf16 rows.  Reference nets/segnetvit.py:104-106, nets/gml.py:135-137, 182-186."""
+    mlp.3, + residual -> fp32 / split-bf16 rows.  ``tables`` = HOST fp32 [b1 512 | LN gamma 512 | LN beta 512 | b3 256]
+    (passed to the kernel as a parameter block).  ``res`` = fp32 residual rows, or None: the residual is x = hi + lo of
+    the left half of ``a``.  Reference nets/segnetvit.py:104-106, nets/gml.py:135-137, 182-186."""
     import ctypes
+    if tables.is_cuda or tables.dtype != torch.float32 or tables.numel() != 1792 or not tables.is_contiguous():
+        raise _lib.PramError('mlp_block_tc: tables must be a contiguous host fp32 tensor of 1792 values')
     A = _lib.MlpBlockArgs()
     A.a_hi, A.a_lo, A.lda, A.T = a.hi.data_ptr(), (a.lo.data_ptr() if a.lo is not None else None), lda, rows
     A.w1_hi, A.w1_lo = w1.hi.data_ptr(), (w1.lo.data_ptr() if w1.lo is not None else None)
-    A.b1, A.ln_g, A.ln_b = b1.data_ptr(), ln_g.data_ptr(), ln_b.data_ptr()
-    A.w3_hi, A.w3_lo, A.b3 = w3.hi.data_ptr(), (w3.lo.data_ptr() if w3.lo is not None else None), b3.data_ptr()
+    A.w3_hi, A.w3_lo = w3.hi.data_ptr(), (w3.lo.data_ptr() if w3.lo is not None else None)
+    A.tables_host = tables.data_ptr()
     A.res, A.res_ld = (res.data_ptr() if res is not None else None), res_ld
     A.out_f32, A.ld_f32 = (out_f32.data_ptr() if out_f32 is not None else None), ld_f32
     if out_bf is not None:
         A.out_hi, A.out_lo, A.ld_bf = out_bf.hi.data_ptr(), (out_bf.lo.data_ptr() if out_bf.lo is not None else None), ld_bf
     A.split = split
+    A.dbg = dbg.data_ptr() if dbg is not None else None
     call('pram_mlp_block_tc', ctypes.byref(A), stream_ptr())
 
 
