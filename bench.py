@@ -24,16 +24,22 @@ FOCAL, MAX_ERROR = 525.0, 8.0
 METRIC = 'localization frames/sec (640x480, 1024 kpts)'
 # BASELINE.json configs: the metric is quoted on the 7Scenes shape; the other two are extra workloads (--workload)
 WORKLOADS = {
-    '7scenes': dict(h=480, w=640, kpts=1024, nclass=113, focal=525.0, max_error=8.0, batch=32),      # configs[1] / [2]
-    'cambridge': dict(h=768, w=1024, kpts=2048, nclass=161, focal=800.0, max_error=12.0, batch=16),  # configs[3]
-    'aachen': dict(h=1200, w=1600, kpts=4096, nclass=513, focal=1200.0, max_error=12.0, batch=8),    # configs[4]
+    '7scenes': dict(h=480, w=640, kpts=1024, nclass=113, focal=525.0, max_error=8.0, batch=32, pool=256),      # configs[1] / [2]
+    'cambridge': dict(h=768, w=1024, kpts=2048, nclass=161, focal=800.0, max_error=12.0, batch=16, pool=128),  # configs[3]
+    'aachen': dict(h=1200, w=1600, kpts=4096, nclass=513, focal=1200.0, max_error=12.0, batch=8, pool=64),     # 4096 x 4096 pair
+    # configs[4] as specified: 10 candidate landmarks per frame, M = 4096 query keypoints against
+    # N = 1024 reference keypoints per landmark, the 10 matcher calls of a frame batched as B = 10
+    'aachen-ml': dict(h=1200, w=1600, kpts=4096, nclass=513, focal=1200.0, max_error=12.0, batch=2, pool=32, landmarks=10,
+                      ref_kpts=1024),
 }
+LANDMARKS, REF_KPTS, POOL = 1, None, 256
 
 
 def set_workload(name, batch):
-    global H, W, KPTS, NCLASS, FOCAL, MAX_ERROR, METRIC
+    global H, W, KPTS, NCLASS, FOCAL, MAX_ERROR, METRIC, LANDMARKS, REF_KPTS, POOL
     wl = WORKLOADS[name]
     H, W, KPTS, NCLASS, FOCAL, MAX_ERROR = wl['h'], wl['w'], wl['kpts'], wl['nclass'], wl['focal'], wl['max_error']
+    LANDMARKS, REF_KPTS, POOL = wl.get('landmarks', 1), wl.get('ref_kpts'), wl['pool']
     METRIC = f'localization frames/sec ({W}x{H}, {KPTS} kpts)'
     return batch if batch > 0 else wl['batch']
 
@@ -49,12 +55,17 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--pool', type=int, default=0, help='distinct synthetic frames per GPU the steps rotate through (default: per workload, 256 for 7scenes)')
+    ap.add_argument('--stage-timers', default=None, metavar='JSONL',
+                    help='after the timed runs, write per-frame stage times (time_feat / time_rec / time_loc, reference loc_by_rec_online.py:108-134, 212-222) to this JSONL file')
     return ap.parse_args()
 
 
 def workload_name(batch):
+    match = ('one matcher call per frame' if LANDMARKS == 1 else
+             f'{LANDMARKS} landmarks per frame matched in one batched call, {KPTS} x {REF_KPTS} keypoints each')
     return (f'full pipeline, synthetic {W}x{H} stream: SFD2 + SegNetViT({NCLASS} classes, 15 layers) + GML(9 layers, '
-            f'Sinkhorn 20, one matcher call per frame, {KPTS} keypoints) + PnP/RANSAC(1024 hypotheses, max_error {MAX_ERROR:g} px), '
+            f'Sinkhorn 20, {match}, {KPTS} keypoints) + PnP/RANSAC(1024 hypotheses, max_error {MAX_ERROR:g} px), '
             f'{batch} frames/GPU/step')
 
 
@@ -62,10 +73,27 @@ def workload_name(batch):
 # inputs / weights (synthetic frames; shipped SFD2+GML checkpoints when staged, seeded random otherwise)
 # ------------------------------------------------------------------------------------------------
 
-def make_frames(batch, seed0=0):
+def make_frames(batch, seed0=0, nbase=32):
+    """``batch`` DISTINCT synthetic frames: seeded polygon frames for the first ``nbase``, then the same
+    scenes mirrored (left-right / up-down) and with their colour channels rotated -- different pixel content and
+    different keypoints for the network at 1/8 of the generation cost (a 640x480 polygon frame takes ~0.25 s of cv2)."""
     import torch
-    import benchdata  # seeded polygon frames; not part of the oracle
-    return torch.cat([benchdata.frame_tensor(H, W, seed=seed0 + i) for i in range(batch)], 0)
+    import benchdata  # not part of the oracle
+    nb = min(batch, nbase)
+    base = [benchdata.frame_tensor(H, W, seed=seed0 + i) for i in range(nb)]
+    out = []
+    for i in range(batch):
+        f, v = base[i % nb], i // nb
+        if v & 1:
+            f = f.flip(-1)
+        if v & 2:
+            f = f.flip(-2)
+        if v & 4:
+            f = f[:, [1, 2, 0]]
+        if v >= 8:
+            f = f.roll(shifts=(7 * (v // 8), 11 * (v // 8)), dims=(-2, -1))
+        out.append(f)
+    return torch.cat(out, 0).contiguous()
 
 
 def states():
@@ -229,12 +257,34 @@ def run_ours(args):
     gml = GML({}); gml.load_state_dict(sd_gml, strict=True)
     for m_ in (sfd2, vit, gml):
         m_.set_precision(args.precision)
-    pipe = LocalizationPipeline(sfd2, vit, gml, max_keypoints=KPTS, focal=FOCAL, ransac_max_error=MAX_ERROR, device=dev)
+    pipe = LocalizationPipeline(sfd2, vit, gml, max_keypoints=KPTS, focal=FOCAL, ransac_max_error=MAX_ERROR, device=dev,
+                                landmarks_per_frame=LANDMARKS)
 
+    from dataclasses import fields
+    from pram_b200.runner import SyntheticMap
     B = args.batch
-    frames_host = make_frames(B, seed0=rank * B).pin_memory()
-    frames_dev = frames_host.to(dev)
-    smap = pipe.build_synthetic_map(frames_dev, seed=rank)
+    pool = max(B, (args.pool or POOL) // B * B)       # distinct frames per GPU, a whole number of steps
+    n_slices = pool // B
+    # ---- inputs: a pool of distinct synthetic frames (pinned host copy for the end-to-end leg, device copy for the
+    # HBM-resident leg) and the synthetic map of every frame, built once, all resident on the device ----
+    frames_host = make_frames(pool, seed0=rank * pool).pin_memory()
+    frames_pool = frames_host.to(dev)
+    parts = [pipe.build_synthetic_map(frames_pool[i * B:(i + 1) * B], seed=rank * n_slices + i, ref_keypoints=REF_KPTS)
+             for i in range(n_slices)]
+    smap_pool = SyntheticMap(*[torch.cat([getattr(p_, f_.name) for p_ in parts], 0) for f_ in fields(SyntheticMap)])
+    del parts
+    RB = B * LANDMARKS                               # reference sets per step
+    smap = SyntheticMap(*[getattr(smap_pool, f_.name)[:RB].clone() for f_ in fields(SyntheticMap)])   # static graph operands
+    frames_dev = frames_pool[:B].clone()             # static graph input
+
+    def load_slice(i, frames_src=None):
+        """Device-to-device copy of slice ``i`` of the pool into the buffers the captured graph reads."""
+        j = i % n_slices
+        if frames_src is None:
+            frames_dev.copy_(frames_pool[j * B:(j + 1) * B], non_blocking=True)
+        for f_ in fields(SyntheticMap):
+            getattr(smap, f_.name).copy_(getattr(smap_pool, f_.name)[j * RB:(j + 1) * RB], non_blocking=True)
+
     # L2 flush buffer (> 126 MB L2); the per-step working set (B x 640x480 activations) is itself > L2
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
     pose_rec = torch.zeros(B, 9, device=dev, dtype=torch.float64)
@@ -244,12 +294,14 @@ def run_ours(args):
     launches_per_step = None
     if use_graph:
         launches_per_step = pipe.capture(frames_dev, smap)
+        frames_in = pipe._static_in                    # the graph's own input buffer
+    else:
+        frames_in = frames_dev
 
-    def step(images):
-        # device-resident leg: the graph reads its static input buffer (already holding these frames)
-        out = pipe.replay(None if images is frames_dev else images) if use_graph else pipe.localize(images, smap)
+    def step(i):
+        out = pipe.replay() if use_graph else pipe.localize(frames_in, smap)
         # fixed-size pose record per frame [id, q(4), t(3), n_inliers]; the single collective of the path
-        pose_rec[:, 0] = torch.arange(B, device=dev, dtype=torch.float64) + rank * B
+        pose_rec[:, 0] = torch.arange(B, device=dev, dtype=torch.float64) + (rank * pool + (i % n_slices) * B)
         pose_rec[:, 1:5] = out['qvec']
         pose_rec[:, 5:8] = out['tvec']
         pose_rec[:, 8] = out['num_inliers'].double()
@@ -262,9 +314,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    def feed(i):
+        """HBM-resident leg: this step's frames and maps are already on the device; bring them to the graph operands."""
+        j = i % n_slices
+        frames_in.copy_(frames_pool[j * B:(j + 1) * B], non_blocking=True)
+        load_slice(i, frames_src=True)
+
+    for i in range(args.warmup):
         flush.zero_()
-        step(frames_dev)
+        feed(i)
+        step(i)
     barrier()
 
     # ---- timed: device-resident inputs ---------------------------------------------------------
@@ -277,7 +336,8 @@ def run_ours(args):
     for i in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the event pair)
         evs[i][0].record()
-        out = step(frames_dev)
+        feed(args.warmup + i)
+        out = step(args.warmup + i)
         evs[i][1].record()
     barrier()
     launches = _lib.launch_count() - l0
@@ -291,38 +351,48 @@ def run_ours(args):
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- timed: end to end through the public API with host buffers --------------------------------
-    res_host = torch.empty(B, KPTS, dtype=torch.int64).pin_memory()
-    lab_host = torch.empty(B, KPTS, dtype=torch.int64).pin_memory()
+    # per step: H2D of that step's frames from pinned host memory (copy stream, double-buffered so that the upload of step
+    # i+1 overlaps step i), and D2H of the step's RESULT: pose records (qvec, tvec, num_inliers), inlier masks, matches
+    # and landmark labels, into pinned host buffers -- all inside the timed region
+    host_out = {
+        'pose': torch.empty(B, 9, dtype=torch.float64).pin_memory(),
+        'inliers': torch.empty(B, KPTS, dtype=torch.bool).pin_memory(),
+        'matches0': torch.empty(RB, KPTS, dtype=torch.int64).pin_memory(),
+        'labels': torch.empty(B, KPTS, dtype=torch.int64).pin_memory(),
+    }
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # every step's frames come from pinned host memory; the H2D copy of step i+1 runs on a copy stream
-    # while step i computes (double buffering through a device staging tensor), all inside the timed region
     main = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(device=dev)
     staging = torch.empty_like(frames_dev)
     ready = [torch.cuda.Event() for _ in range(args.steps)]
     freed = [torch.cuda.Event() for _ in range(args.steps)]
+    base = args.warmup + args.steps
+
+    def host_slice(i):
+        j = (base + i) % n_slices
+        return frames_host[j * B:(j + 1) * B]
+
     e0.record(main)
     copy_stream.wait_event(e0)
     with torch.cuda.stream(copy_stream):
-        staging.copy_(frames_host, non_blocking=True)
+        staging.copy_(host_slice(0), non_blocking=True)
         ready[0].record(copy_stream)
     for i in range(args.steps):
         main.wait_event(ready[i])
-        if use_graph:
-            pipe._static_in.copy_(staging, non_blocking=True)
-            img = None
-        else:
-            img = staging.clone()
+        frames_in.copy_(staging, non_blocking=True)
         freed[i].record(main)
         if i + 1 < args.steps:
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[i])
-                staging.copy_(frames_host, non_blocking=True)
+                staging.copy_(host_slice(i + 1), non_blocking=True)
                 ready[i + 1].record(copy_stream)
-        out = step(frames_dev if use_graph else img)
-        res_host.copy_(out['matches0'], non_blocking=True)
-        lab_host.copy_(out['labels'], non_blocking=True)
+        load_slice(base + i, frames_src=True)
+        out = step(base + i)
+        host_out['pose'].copy_(pose_rec, non_blocking=True)
+        host_out['inliers'].copy_(out['inliers'], non_blocking=True)
+        host_out['matches0'].copy_(out['matches0'], non_blocking=True)
+        host_out['labels'].copy_(out['labels'], non_blocking=True)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -330,6 +400,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e = world * B * args.steps / (float(t.item()) * 1e-3)
     clocks = sampler.stop() if sampler else None
+    last = (base + args.steps - 1) % n_slices      # pool slice of the last step (the one `out` / host_out hold)
 
     if rank == 0:
         roof = roofline_probe(pipe, frames_dev, dev)
@@ -339,37 +410,77 @@ def run_ours(args):
             cpu = {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
                    'sample': f'2 frames x 3 reps (median), oracle torch-CPU fp32, {cores} threads'}
         matched = float((out['matches0'] > -1).float().mean().item())
-        # pose check against the synthetic map's known poses (reported, not timed)
+        # checks on the last step (reported, not timed): pose against the synthetic map's known poses FROM THE HOST COPY of
+        # the result, keypoint budget filled (no padded tokens), no candidate-buffer overflow
         import benchdata as O
-        errs = [O.pose_error(out['qvec'][i].cpu().numpy(), out['tvec'][i].cpu().numpy(),
-                             O.rotmat_to_quat(smap.R[i].double().cpu().numpy()), smap.t[i].double().cpu().numpy())
+        rec = host_out['pose'].numpy()
+        Rk, tk = smap_pool.R[last * RB:(last + 1) * RB:LANDMARKS], smap_pool.t[last * RB:(last + 1) * RB:LANDMARKS]
+        errs = [O.pose_error(rec[i, 1:5], rec[i, 5:8], O.rotmat_to_quat(Rk[i].double().cpu().numpy()), tk[i].double().cpu().numpy())
                 for i in range(B)]
         pose_ok = sum(1 for er, et in errs if er < 5.0 and et < 0.05) / B
+        full_budget = bool((out['num_keypoints'] == KPTS).all().item())
+        overflow = bool(out['cand_overflow'].any().item())
+        stage = stage_timers(args, pipe, frames_pool, smap_pool, B, RB, n_slices, rank, pool) if args.stage_timers else None
         print(json.dumps({
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': pipe.sfd2.compute_dtype,
-            'data': f'synthetic polygon frames; {tag}; seeded random SegNetViT',
-            'config': {'workload': workload_name(B), 'frames_per_gpu_per_step': B, 'l2': 'flushed between timed steps (256 MiB memset)', 'cuda_graph': use_graph, 'precision': args.precision,
-                       'matched_fraction': matched, 'frames_within_5deg_5cm': pose_ok,
+            'data': f'synthetic polygon frames ({pool} distinct per GPU, rotated step by step); {tag}; seeded random SegNetViT',
+            'config': {'workload': workload_name(B), 'frames_per_gpu_per_step': B, 'distinct_frames_per_gpu': pool,
+                       'l2': 'flushed between timed steps (256 MiB memset)', 'cuda_graph': use_graph, 'precision': args.precision,
+                       'matched_fraction': matched, 'frames_within_5deg_5cm': pose_ok, 'keypoint_budget_filled': full_budget,
+                       'candidate_overflow': overflow,
                        'median_inliers': float(out['num_inliers'].float().median().item())},
-            'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': frames_host.numel() * 4,
-                    'd2h_bytes_per_step': res_host.numel() * 8 * 2},
+            'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': B * 3 * H * W * 4,
+                    'd2h_bytes_per_step': sum(v.numel() * v.element_size() for v in host_out.values()),
+                    'd2h': 'pose records (id, qvec, tvec, num_inliers) + inlier masks + matches0 + landmark labels'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
             'whole_step_bound': whole_step_bound(value, world, 3 if args.precision == 'bf16x3' else 1),
+            'stage_timers': stage,
         }))
     if world > 1:
         dist.destroy_process_group()
 
 
-def algorithmic_gflop_per_frame(h, w, k, c):
-    """SURVEY.md section 8d closed forms: SFD2 conv stack (scaled from 132.95 GFLOP @640x480), SegNetViT, one GML pair
-    with M = N = k."""
+def stage_timers(args, pipe, frames_pool, smap_pool, B, RB, n_slices, rank, pool):
+    """Per-stage device times (CUDA events between the stages, eager launches on one stream) for a few batches, written
+    as one JSON line per FRAME with the reference's field names (Frame.time_feat / time_rec / time_loc / time_ref, printed
+    by loc_by_rec_online.py:212-222 as feat/rec/loc/ref/total).  A frame's share of its batch is batch time / B."""
+    import torch
+    from dataclasses import fields
+    from pram_b200.runner import SyntheticMap
+    import benchdata as O
+    rows, agg = [], {'time_feat': 0.0, 'time_rec': 0.0, 'time_loc': 0.0, 'time_ref': 0.0, 'time_total': 0.0}
+    nb = min(n_slices, 4)
+    for j in range(nb + 1):
+        sm = SyntheticMap(*[getattr(smap_pool, f_.name)[(j % n_slices) * RB:((j % n_slices) + 1) * RB] for f_ in fields(SyntheticMap)])
+        out, t = pipe.localize_timed(frames_pool[(j % n_slices) * B:((j % n_slices) + 1) * B], sm)
+        if j == 0:
+            continue  # warm-up batch
+        for k in agg:
+            agg[k] += t[k] / nb
+        q, tv, ni = out['qvec'].cpu().numpy(), out['tvec'].cpu().numpy(), out['num_inliers'].cpu().numpy()
+        for i in range(B):
+            r = (j % n_slices) * RB + i * LANDMARKS
+            er, et = O.pose_error(q[i], tv[i], O.rotmat_to_quat(smap_pool.R[r].double().cpu().numpy()), smap_pool.t[r].double().cpu().numpy())
+            rows.append({'frame': rank * pool + (j % n_slices) * B + i, 'batch': B, **{k: v / B for k, v in t.items()},
+                         'q_err': er, 't_err': et, 'num_inliers': int(ni[i]), 'num_keypoints': int(out['num_keypoints'][i])})
+    with open(args.stage_timers, 'w') as f:
+        for r in rows:
+            f.write(json.dumps(r) + '\n')
+    return {'file': args.stage_timers, 'frames': len(rows), 'mode': 'eager, one stream, CUDA events between stages',
+            'ms_per_batch': {k: v * 1e3 for k, v in agg.items()}}
+
+
+def algorithmic_gflop_per_frame(h, w, k, c, n=None, pairs=1):
+    """SURVEY.md section 8d closed forms: SFD2 conv stack (scaled from 132.95 GFLOP @640x480), SegNetViT, and ``pairs`` GML
+    calls with M = k query and N = n (default k) reference keypoints."""
+    n = k if n is None else n
     sfd2 = 132.95 * (h * w) / (480.0 * 640.0)
     vit = (15 * (1310720.0 * k + 1024.0 * k * k) + 131072.0 * k + 2.0 * k * (262144.0 + 1024.0 * c)) / 1e9
-    per_layer = 1310720.0 * 2 * k + 1024.0 * 2 * k * k + 1179648.0 * 2 * k + 1536.0 * k * k
-    gml = (9 * per_layer + 2 * 128 * 256 * 2 * k + 2 * 256 * 256 * 2 * k + 512.0 * k * k) / 1e9
-    return sfd2 + vit + gml
+    per_layer = 1310720.0 * (k + n) + 1024.0 * (k * k + n * n) + 1179648.0 * (k + n) + 1536.0 * k * n
+    gml = (9 * per_layer + 2 * 128 * 256 * (k + n) + 2 * 256 * 256 * (k + n) + 512.0 * k * n) / 1e9
+    return sfd2 + vit + pairs * gml
 
 
 def whole_step_bound(value_fps, n_gpus, mma_mult):
@@ -378,7 +489,7 @@ def whole_step_bound(value_fps, n_gpus, mma_mult):
     try:
         peaks = json.loads((ROOT / 'MEASURED_PEAKS.json').read_text()) if (ROOT / 'MEASURED_PEAKS.json').exists() else {}
         sustained = float(peaks.get('bf16_tflops_sustained', 1400.0))
-        gf = algorithmic_gflop_per_frame(H, W, KPTS, NCLASS)
+        gf = algorithmic_gflop_per_frame(H, W, KPTS, NCLASS, REF_KPTS, LANDMARKS)
         bound = n_gpus * sustained * 1e3 / (gf * mma_mult)
         return {'algorithmic_gflop_per_frame': gf, 'tensor_flops_issued_per_algorithmic_flop': mma_mult,
                 'tensor_bound_frames_per_s': bound, 'frac_of_tensor_bound': value_fps / bound,

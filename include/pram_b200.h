@@ -48,11 +48,14 @@ int pram_nms_candidates(const float* score, int B, int H, int W, int radius, flo
                         pram_stream_t stream);
 
 /* K7: threshold fallback, border removal, top-k / row-major ordering, (x,y) float output.
- * nets/sfd2.py:38-50, 306-329.  kpts[B][kpad][2], scores[B][kpad], n_out[B]. */
+ * nets/sfd2.py:38-50, 306-329.  kpts[B][kpad][2], scores[B][kpad], n_out[B].  Border window: border <= y < y_hi,
+ * border <= x < x_hi (y_hi / x_hi <= 0 = H - border / W - border; the export path passes the ORIGINAL image's bounds for
+ * a rescaled map, nets/sfd2.py:447-451).  max_keypoints < 0 = unlimited; with more valid keypoints than kpad slots the
+ * best kpad by score are returned and n_valid_out[B] (optional) reports the true count. */
 int pram_select_keypoints(const unsigned long long* cand, int cap, const int* cand_count, const int* count_hi,
                           const float* score, int B, int H, int W, float th_lo, float th_hi, int min_keypoints,
-                          int max_keypoints, int border, float* kpts, float* scores, int* n_out, int kpad,
-                          pram_stream_t stream);
+                          int max_keypoints, int border, int y_hi, int x_hi, float* kpts, float* scores, int* n_out,
+                          int kpad, int* n_valid_out, pram_stream_t stream);
 
 /* K8: bilinear sampling of an NHWC map at keypoints (+ optional L2 norm).  nets/sfd2.py:53-64, 348-363.
  * fmap[B][h][w][C], kpts[B][kpad][2], counts[B] or NULL, out[B][kpad][C]. */
@@ -211,6 +214,15 @@ int pram_ransac_pnp(const float* kpts, const long long* matches, const float* xy
                     double fy, double cx, double cy, double pixel_shift, double max_error, int num_hypotheses,
                     int lo_iters, int final_iters, int min_inliers, unsigned int seed, void* workspace, double* qvec,
                     double* tvec, int* num_inliers, unsigned char* inliers, int* success, pram_stream_t stream);
+
+/* Same estimator on float64 correspondences normalised by the caller: corr [B][n][5] = (x, y, X, Y, Z), (x, y) = undistorted
+ * camera-plane coordinates.  Used by the pycolmap-compatible host call (float64 numpy inputs, COLMAP camera models with
+ * distortion: the call sites above pass SIMPLE_RADIAL cameras on Aachen).  counts [B] or NULL; focal_mean converts max_error
+ * (pixels) into the camera plane like COLMAP's CamFromImgThreshold.  Workspace: pram_ransac_workspace_bytes(B, n, hyp). */
+int pram_ransac_pnp_corr(const double* corr, const int* counts, int B, int n, double focal_mean, double max_error,
+                         int num_hypotheses, int lo_iters, int final_iters, int min_inliers, unsigned int seed, void* workspace,
+                         double* qvec, double* tvec, int* num_inliers, unsigned char* inliers, int* success,
+                         pram_stream_t stream);
 
 /* ---- "next" rows ---- */
 /* Frame.add_segmentations (localization/frame.py:96-121): softmax, background probability, argmax-1, pre-filter mask. */

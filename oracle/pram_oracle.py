@@ -608,7 +608,8 @@ def absolute_pose_estimation(points2D: np.ndarray, points3D: np.ndarray, camera:
     """CPU restatement of the call the reference makes to pycolmap (see section header).
 
     camera: {'model': 'PINHOLE'|'SIMPLE_PINHOLE'|..., 'width','height','params'} with
-    params = (fx,fy,cx,cy) or (f,cx,cy[,k]) -- distortion is ignored here (parity unpinned).
+    params = (fx,fy,cx,cy[,k1,k2,p1,p2]) or (f,cx,cy[,k1[,k2]]); pixels go to the camera plane through the lens model
+    (``cam_from_img``) as COLMAP does.  Parity with pycolmap itself is unpinned.
     Residual = squared reprojection error in normalised camera coordinates, threshold
     (max_error / mean focal)^2 (COLMAP convention).  Returns None on failure, else a dict with
     'qvec' (wxyz), 'tvec', 'num_inliers', 'inliers' (bool[n]).
@@ -619,7 +620,7 @@ def absolute_pose_estimation(points2D: np.ndarray, points3D: np.ndarray, camera:
     if n < 3:
         return None
     fx, fy, cx, cy = camera_intrinsics(camera)
-    x = np.stack([(p2[:, 0] - cx) / fx, (p2[:, 1] - cy) / fy], 1)
+    x = cam_from_img(camera, p2)
     thr = (max_error / (0.5 * (fx + fy))) ** 2
     rng = np.random.RandomState(seed)
     best = (-1, np.inf, None, None)  # inliers, residual sum, R, t
@@ -662,11 +663,66 @@ def camera_intrinsics(camera) -> Tuple[float, float, float, float]:
     """(fx,fy,cx,cy) from a COLMAP-style camera dict / namedtuple (reference
     localization/camera.py:1-11: Camera(id, model, width, height, params))."""
     model = camera['model'] if isinstance(camera, dict) else camera.model
+    model = getattr(model, 'name', model)
     params = camera['params'] if isinstance(camera, dict) else camera.params
     params = [float(v) for v in params]
     if model in ('PINHOLE', 'OPENCV', 'FULL_OPENCV', 'OPENCV_FISHEYE'):
         return params[0], params[1], params[2], params[3]
     return params[0], params[0], params[1], params[2]  # SIMPLE_PINHOLE / SIMPLE_RADIAL / RADIAL
+
+
+def _distort(model: str, extra, u: np.ndarray, v: np.ndarray):
+    """COLMAP sensor/models.h ``Distortion`` of SIMPLE_RADIAL / RADIAL / OPENCV: (du, dv) at camera-plane (u, v)."""
+    r2 = u * u + v * v
+    if model == 'SIMPLE_RADIAL':
+        rad = extra[0] * r2
+        return u * rad, v * rad
+    if model == 'RADIAL':
+        rad = extra[0] * r2 + extra[1] * r2 * r2
+        return u * rad, v * rad
+    if model == 'OPENCV':
+        k1, k2, p1, p2 = extra[:4]
+        rad = k1 * r2 + k2 * r2 * r2
+        return (u * rad + 2 * p1 * u * v + p2 * (r2 + 2 * u * u), v * rad + 2 * p2 * u * v + p1 * (r2 + 2 * v * v))
+    return np.zeros_like(u), np.zeros_like(v)
+
+
+def img_from_cam(camera, uv: np.ndarray) -> np.ndarray:
+    """Camera plane -> pixels with the lens model (COLMAP ``ImgFromCam``); used to synthesise distorted observations."""
+    model = camera['model'] if isinstance(camera, dict) else camera.model
+    params = [float(v) for v in (camera['params'] if isinstance(camera, dict) else camera.params)]
+    fx, fy, cx, cy = camera_intrinsics(camera)
+    extra = params[3:] if model in ('SIMPLE_RADIAL', 'RADIAL') else params[4:]
+    du, dv = _distort(model, extra, uv[:, 0], uv[:, 1])
+    return np.stack([fx * (uv[:, 0] + du) + cx, fy * (uv[:, 1] + dv) + cy], 1)
+
+
+def cam_from_img(camera, xy: np.ndarray) -> np.ndarray:
+    """Pixels -> undistorted camera plane: COLMAP's ``IterativeUndistortion`` -- Newton's method on
+    f(x) = x + d(x) - x0 with a central-difference Jacobian (step 1e-10 relative, at most 100 iterations)."""
+    model = camera['model'] if isinstance(camera, dict) else camera.model
+    params = [float(v) for v in (camera['params'] if isinstance(camera, dict) else camera.params)]
+    fx, fy, cx, cy = camera_intrinsics(camera)
+    p = np.asarray(xy, np.float64)
+    u0, v0 = (p[:, 0] - cx) / fx, (p[:, 1] - cy) / fy
+    if model in ('SIMPLE_PINHOLE', 'PINHOLE'):
+        return np.stack([u0, v0], 1)
+    extra = params[3:] if model in ('SIMPLE_RADIAL', 'RADIAL') else params[4:]
+    u, v = u0.copy(), v0.copy()
+    for _ in range(100):
+        eu, ev = np.maximum(1e-10, np.abs(1e-10 * u)), np.maximum(1e-10, np.abs(1e-10 * v))
+        du, dv = _distort(model, extra, u, v)
+        a = _distort(model, extra, u - eu, v); b = _distort(model, extra, u + eu, v)
+        c = _distort(model, extra, u, v - ev); d = _distort(model, extra, u, v + ev)
+        j00 = 1 + (b[0] - a[0]) / (2 * eu); j01 = (d[0] - c[0]) / (2 * ev)
+        j10 = (b[1] - a[1]) / (2 * eu); j11 = 1 + (d[1] - c[1]) / (2 * ev)
+        f0, f1 = u + du - u0, v + dv - v0
+        det = j00 * j11 - j01 * j10
+        su, sv = (j11 * f0 - j01 * f1) / det, (j00 * f1 - j10 * f0) / det
+        u, v = u - su, v - sv
+        if max(np.abs(su).max(initial=0.0), np.abs(sv).max(initial=0.0)) < 1e-12:
+            break
+    return np.stack([u, v], 1)
 
 
 # --------------------------------------------------------------------------------------------

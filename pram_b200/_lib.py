@@ -29,7 +29,7 @@ SIGNATURES = {
     'pram_score_map': (_I, [_P, _L, _L, _L, _L, _I, _I, _I, _P, _P]),
     'pram_resize_bilinear': (_I, [_P, _I, _I, _I, _P, _I, _I, _P]),
     'pram_nms_candidates': (_I, [_P, _I, _I, _I, _I, _F, _F, _P, _P, _I, _P, _P, _P]),
-    'pram_select_keypoints': (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _F, _F, _I, _I, _I, _P, _P, _P, _I, _P]),
+    'pram_select_keypoints': (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _F, _F, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
     'pram_sample_features': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P]),
     'pram_gather_scores': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P]),
     'pram_posenc': (_I, [_P, _I, _F, _F, _I, _P, _P, _P, _P]),
@@ -91,6 +91,7 @@ _D = C.c_double
 SIGNATURES['pram_ransac_workspace_bytes'] = (_L, [_I, _I, _I])
 SIGNATURES['pram_ransac_pnp'] = (_I, [_P, _P, _P, _I, _I, _I, _D, _D, _D, _D, _D, _D, _I, _I, _I, _I, C.c_uint, _P, _P, _P, _P,
                                       _P, _P, _P])
+SIGNATURES['pram_ransac_pnp_corr'] = (_I, [_P, _P, _I, _I, _D, _D, _I, _I, _I, _I, C.c_uint, _P, _P, _P, _P, _P, _P, _P])
 SIGNATURES['pram_segmentation'] = (_I, [_P, _I, _I, _F, _P, _P, _P, _P, _P])
 SIGNATURES['pram_rank_landmarks'] = (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P])
 SIGNATURES['pram_project_points'] = (_I, [_P, _I, _P, _D, _D, _D, _D, _D, _D, _P, _P, _P])

@@ -537,6 +537,47 @@ PRAM_API long long pram_ransac_workspace_bytes(int B, int cap, int num_hypothese
     return bytes + 64;
 }
 
+__global__ void corr_identity_kernel(int* __restrict__ src_index, int* __restrict__ count, int B, int cap,
+                                     const int* __restrict__ counts_in) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * cap) return;
+    src_index[i] = (int)(i % cap);
+    if (i % cap == 0) { const int b = (int)(i / cap); count[b] = counts_in ? min(max(counts_in[b], 0), cap) : cap; }
+}
+
+// Same estimator on correspondences the caller has already normalised in float64: corr [B][n][5] = (x, y, X, Y, Z) with
+// (x, y) = camera-plane coordinates of the (undistorted) keypoint and (X, Y, Z) the world point.  This is the entry the
+// pycolmap-compatible host call uses (localization/pose_estimator.py): the reference passes float64 numpy arrays and a
+// COLMAP camera with distortion parameters (SIMPLE_RADIAL for Aachen), so pixels -> camera plane happens in float64
+// on the host and nothing is rounded to float32 on the way in.  counts [B] (NULL = n valid rows each), focal_mean scales
+// max_error (pixels) into the camera plane like COLMAP's CamFromImgThreshold.
+PRAM_API int pram_ransac_pnp_corr(const double* corr, const int* counts, int B, int n, double focal_mean, double max_error,
+                                  int num_hypotheses, int lo_iters, int final_iters, int min_inliers, unsigned int seed,
+                                  void* workspace, double* qvec, double* tvec, int* num_inliers, unsigned char* inliers,
+                                  int* success, cudaStream_t stream) {
+    if (!corr || !workspace || !qvec || !tvec || !num_inliers || !inliers || !success) return PRAM_ERR_ARG;
+    if (B <= 0 || n <= 0 || num_hypotheses <= 0 || max_error <= 0 || focal_mean <= 0) return PRAM_ERR_ARG;
+    const int cap = n;
+    const int nblocks = cdiv(num_hypotheses, HYP_THREADS);
+    char* ws = (char*)workspace;
+    int* src_index = (int*)(ws + (long long)B * cap * 5 * 8);
+    int* count = src_index + (long long)B * cap;
+    long long off = (long long)B * cap * 5 * 8 + (long long)B * cap * 4 + (long long)B * 4;
+    off = (off + 15) / 16 * 16;
+    HypBest* bb = (HypBest*)(ws + off);
+    corr_identity_kernel<<<cdiv((long long)B * cap, 256), 256, 0, stream>>>(src_index, count, B, cap, counts);
+    PRAM_CHECK_LAUNCH();
+    const double thr2 = (max_error / focal_mean) * (max_error / focal_mean);
+    dim3 grid(nblocks, B);
+    ransac_hyp_kernel<<<grid, HYP_THREADS, 0, stream>>>(corr, count, cap, thr2, seed, bb);
+    PRAM_CHECK_LAUNCH();
+    const double cs = 1.0 / focal_mean;
+    ransac_finalize_kernel<<<B, FIN_THREADS, 0, stream>>>(corr, src_index, count, cap, bb, nblocks, thr2, cs * cs, lo_iters,
+                                                         final_iters, min_inliers, n, qvec, tvec, num_inliers, inliers, success);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
 // kpts [B][n][2] f32 (pixels), matches [B][n] i64 (index into xyz, -1 = none), xyz [B][nref][3] f32.
 // outputs: qvec [B][4] (wxyz) f64, tvec [B][3] f64, num_inliers [B] i32, inliers [B][n] u8, success [B] i32
 PRAM_API int pram_ransac_pnp(const float* kpts, const long long* matches, const float* xyz, int B, int n, int nref,

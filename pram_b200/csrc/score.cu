@@ -271,18 +271,21 @@ PRAM_API int pram_nms_candidates(const float* score, int B, int H, int W, int ra
 constexpr int SEL_THREADS = 1024;
 constexpr int SEL_MAXK = 4096;
 
-__device__ __forceinline__ bool sel_valid(unsigned long long key, float eff_th, int border, int H,
-                                          int W) {
+// border window: border <= y < y_hi, border <= x < x_hi.  The upper bounds are separate arguments because the export path
+// (nets/sfd2.py:447-451) tests the keypoints of a RESCALED image against the ORIGINAL width / height.
+struct SelWin { int border, y_hi, x_hi, W; };
+__device__ __forceinline__ bool sel_valid(unsigned long long key, float eff_th, const SelWin& w) {
     float v = __uint_as_float((unsigned int)(key >> 32));
     unsigned int idx = (unsigned int)key;
-    int y = idx / W, x = idx - y * W;
-    return v >= eff_th && y >= border && y < H - border && x >= border && x < W - border;
+    int y = idx / w.W, x = idx - y * w.W;
+    return v >= eff_th && y >= w.border && y < w.y_hi && x >= w.border && x < w.x_hi;
 }
 
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(
     const unsigned long long* __restrict__ cand, int cap, const int* __restrict__ cand_count,
-    const int* __restrict__ count_hi, float th_lo, float th_hi, int min_kp, int K, int border, int H,
-    int W, float* __restrict__ kpts, float* __restrict__ scores, int* __restrict__ n_out, int kpad) {
+    const int* __restrict__ count_hi, float th_lo, float th_hi, int min_kp, int K, SelWin win, int H,
+    int W, float* __restrict__ kpts, float* __restrict__ scores, int* __restrict__ n_out, int kpad,
+    int* __restrict__ n_valid_out) {
     __shared__ unsigned long long keys[SEL_MAXK];
     __shared__ int hist[256];
     __shared__ int s_n, s_pos;
@@ -295,11 +298,15 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(
     if (threadIdx.x == 0) { s_n = 0; s_pos = 0; }
     __syncthreads();
     int cnt = 0;
-    for (int i = threadIdx.x; i < n_all; i += SEL_THREADS) cnt += sel_valid(c[i], eff_th, border, H, W);
+    for (int i = threadIdx.x; i < n_all; i += SEL_THREADS) cnt += sel_valid(c[i], eff_th, win);
     cnt = (int)warp_sum((float)cnt);  // exact for counts < 2^24
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_n, cnt);
     __syncthreads();
     const int n_valid = s_n;
+    if (threadIdx.x == 0 && n_valid_out) n_valid_out[b] = n_valid;   // lets the host see "more valid keypoints than slots"
+    // "unlimited" (K < 0) with more valid keypoints than output slots: fall back to the best `kpad` by score -- a
+    // deterministic subset (the gather below would otherwise keep whichever candidates won the atomics)
+    if (K < 0 && n_valid > min(kpad, SEL_MAXK)) K = min(kpad, SEL_MAXK);
     const bool take_all = (K < 0) || (n_valid <= K);
     int n_sel = take_all ? n_valid : K;
     if (n_sel > SEL_MAXK) n_sel = SEL_MAXK;  // host guarantees K <= SEL_MAXK and kpad <= SEL_MAXK
@@ -318,7 +325,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(
             const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
             for (int i = threadIdx.x; i < n_all; i += SEL_THREADS) {
                 unsigned long long k = c[i];
-                if (!sel_valid(k, eff_th, border, H, W)) continue;
+                if (!sel_valid(k, eff_th, win)) continue;
                 unsigned long long ck = (k & 0xffffffff00000000ull) | (unsigned int)(~(unsigned int)k);
                 if ((ck & himask) == prefix) atomicAdd(&hist[(ck >> shift) & 0xff], 1);
             }
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(
     // gather
     for (int i = threadIdx.x; i < n_all; i += SEL_THREADS) {
         unsigned long long k = c[i];
-        if (!sel_valid(k, eff_th, border, H, W)) continue;
+        if (!sel_valid(k, eff_th, win)) continue;
         unsigned long long ck = (k & 0xffffffff00000000ull) | (unsigned int)(~(unsigned int)k);
         if (take_all) {
             // ascending index == descending ~idx: reuse the descending sort on the low word alone
@@ -401,13 +408,17 @@ __global__ void fill_scores_kernel(const float* __restrict__ score, int H, int W
 PRAM_API int pram_select_keypoints(const unsigned long long* cand, int cap, const int* cand_count,
                                    const int* count_hi, const float* score, int B, int H, int W,
                                    float th_lo, float th_hi, int min_keypoints, int max_keypoints,
-                                   int border, float* kpts, float* scores, int* n_out, int kpad,
-                                   cudaStream_t stream) {
+                                   int border, int y_hi, int x_hi, float* kpts, float* scores, int* n_out, int kpad,
+                                   int* n_valid_out, cudaStream_t stream) {
     if (!cand || !cand_count || !count_hi || !score || !kpts || !scores || !n_out) return PRAM_ERR_ARG;
     if (kpad <= 0 || kpad > SEL_MAXK || max_keypoints > SEL_MAXK) return PRAM_ERR_UNSUPPORTED;
+    SelWin win;
+    win.border = border; win.W = W;
+    win.y_hi = y_hi > 0 ? y_hi : H - border;   // <= 0: the symmetric window of extract_local_global (nets/sfd2.py:38-43)
+    win.x_hi = x_hi > 0 ? x_hi : W - border;
     select_kernel<<<B, SEL_THREADS, 0, stream>>>(cand, cap, cand_count, count_hi, th_lo, th_hi,
-                                                 min_keypoints, max_keypoints, border, H, W, kpts,
-                                                 scores, n_out, kpad);
+                                                 min_keypoints, max_keypoints, win, H, W, kpts,
+                                                 scores, n_out, kpad, n_valid_out);
     PRAM_CHECK_LAUNCH();
     fill_scores_kernel<<<cdiv((long long)B * kpad, 256), 256, 0, stream>>>(score, H, W, kpts, n_out,
                                                                           kpad, scores, B * kpad);

@@ -102,7 +102,7 @@ def match_pairs(conf: Dict, pairs: Iterable[Tuple[str, str]], features_q, featur
 def main(conf: Dict, pairs: Union[Path, List[Tuple[str, str]]], features, export_dir: Optional[Path] = None,
          matches: Optional[Path] = None, features_ref=None, overwrite: bool = False):
     """Reference entry point (match_features_batch.py:132-178).  ``pairs`` is a pairs file ("name0 name1" per line) or
-    a list; ``features`` / ``features_ref`` are h5 paths (needs h5py) or in-memory mappings.  Returns the matches path
+    a list; ``features`` / ``features_ref`` are store paths (``h5store.open_store``) or in-memory mappings.  Returns the matches path
     when an h5 file is written, else the dict of records."""
     if isinstance(pairs, (str, Path)):
         pairs = [tuple(l.split()[:2]) for l in Path(pairs).read_text().splitlines() if l.strip()]
@@ -110,11 +110,8 @@ def main(conf: Dict, pairs: Union[Path, List[Tuple[str, str]]], features, export
 
     def open_store(f):
         if isinstance(f, (str, Path)):
-            try:
-                import h5py
-            except ImportError as e:  # noqa: F841
-                raise RuntimeError('reading feature files needs h5py, which is not installed; pass in-memory mappings') from e
-            fd = h5py.File(str(f), 'r')
+            from .h5store import open_store as _open
+            fd = _open(f, 'r')  # HDF5 through h5py when installed, else the .npz-backed store (same interface)
             opened.append(fd)
             return fd
         return f
@@ -129,8 +126,10 @@ def main(conf: Dict, pairs: Union[Path, List[Tuple[str, str]]], features, export
         matches = Path(export_dir, f'{Path(features).stem}-{conf["output"]}.h5')
     if matches is None:
         return recs
-    import h5py
-    with h5py.File(str(matches), 'a', libver='latest') as fd:
+    from .h5store import open_store as _open
+    Path(matches).parent.mkdir(parents=True, exist_ok=True)
+    fd = _open(matches, 'a', libver='latest')
+    try:
         for pair, rec in recs.items():
             if pair in fd:
                 if not overwrite:
@@ -139,4 +138,6 @@ def main(conf: Dict, pairs: Union[Path, List[Tuple[str, str]]], features, export
             grp = fd.create_group(pair)
             for k, v in rec.items():
                 grp.create_dataset(k, data=v)
+    finally:
+        fd.close()
     return matches

@@ -250,6 +250,9 @@ class ResNet4x(nn.Module):
             # plateau image: more NMS survivors than the candidate buffer -- redo with a full buffer
             out = self.extract_batched(data['image'], cfg, cap=data['image'].shape[-1] * data['image'].shape[-2])
             n = out['num_keypoints'].tolist()
+        if cfg['max_keypoints'] < 0 and any(v > out['keypoints'].shape[1] for v in out['num_valid'].tolist()):
+            raise _lib.PramError(f"max_keypoints = -1 (unlimited) found {max(out['num_valid'].tolist())} keypoints, more than "
+                                 f"the selection kernel's {out['keypoints'].shape[1]} slots; pass max_keypoints <= 4096")
         return {
             'score_map': out['score_map'],
             'desc_map': self._nchw(out['desc_map_nhwc']),
@@ -268,14 +271,16 @@ class ResNet4x(nn.Module):
         b, _, ih, iw = image.shape
         t = self._trunk(image)
         score = ops.score_map(t['logits'], ih, iw)
-        kpts, scs, n, cand_count = ops.detect_keypoints(score, cfg['conf_th'], cfg['min_keypoints'],
-                                                        cfg['max_keypoints'], cfg['remove_borders'], radius=4,
-                                                        cap=cap)
+        if cap is None:
+            cap = ops.default_cand_cap(ih, iw, 4)
+        kpts, scs, n, cand_count, n_valid = ops.detect_keypoints(score, cfg['conf_th'], cfg['min_keypoints'],
+                                                                 cfg['max_keypoints'], cfg['remove_borders'], radius=4,
+                                                                 cap=cap, return_valid=True)
         desc = ops.sample_features(t['desc'], kpts, n, 4, True)
         return {'score_map': score, 'desc_map_nhwc': t['desc'], 'mid_features_nhwc': t['out4'],
                 'global_nhwc': [t['out1b'], t['out2b'], t['out3b'], t['out4']],
                 'keypoints': kpts, 'scores': scs, 'descriptors': desc, 'num_keypoints': n,
-                'cand_count': cand_count, 'cand_cap': cap if cap is not None else 1 << 30, 'logits': t['logits']}
+                'cand_count': cand_count, 'cand_cap': cap, 'num_valid': n_valid, 'logits': t['logits']}
 
     @torch.no_grad()
     def sample(self, score_map: torch.Tensor, semi_descs: torch.Tensor, kpts: torch.Tensor, s: int = 4,
@@ -323,7 +328,12 @@ def extract_sfd2_return(model: ResNet4x, img: torch.Tensor, conf_th: float = 0.0
         heat = ops.score_map(t['logits'], nh, nw)
         # every candidate above the threshold, best first (K = 4096 is the kernel's and the
         # reference config's ceiling, extract_features.py:73)
-        kpts, scs, n, _ = ops.detect_keypoints(heat, conf_th, 0, 4096, 4, radius=3, strict=True, fallback=False)
+        # border test against the ORIGINAL width / height even on a rescaled map, as the reference does (:447-451)
+        kpts, scs, n, cc = ops.detect_keypoints(heat, conf_th, 0, 4096, 4, radius=3, strict=True, fallback=False,
+                                                border_hi=(H - 4, W - 4))
+        if int(cc[0]) > ops.default_cand_cap(nh, nw, 3):   # plateau image: redo with a full candidate buffer
+            kpts, scs, n, cc = ops.detect_keypoints(heat, conf_th, 0, 4096, 4, radius=3, strict=True, fallback=False,
+                                                    border_hi=(H - 4, W - 4), cap=nh * nw)
         n0 = int(n[0])
         if n0 == 0:
             continue

@@ -41,10 +41,20 @@ def score_map(logits_nhwc: Tensor, ih: Optional[int] = None, iw: Optional[int] =
 
 # ---- K6 / K7 ----------------------------------------------------------------------------------
 
+def default_cand_cap(h: int, w: int, radius: int = 4) -> int:
+    """Candidate-buffer size per frame: local maxima are >= radius + 1 apart unless the map has exact plateaus."""
+    return max(4096, ((h + radius) // (radius + 1)) * ((w + radius) // (radius + 1)))
+
+
 def detect_keypoints(score: Tensor, conf_th: float, min_keypoints: int, max_keypoints: int, border: int,
                      radius: int = 4, strict: bool = False, fallback: bool = True,
-                     return_nms: bool = False, cap: Optional[int] = None):
-    """score [B,H,W] -> (kpts [B,kpad,2] (x,y) f32, scores [B,kpad], n [B] int32 [, nms [B,H,W]]).
+                     return_nms: bool = False, cap: Optional[int] = None, border_hi: Optional[Tuple[int, int]] = None,
+                     return_valid: bool = False):
+    """score [B,H,W] -> (kpts [B,kpad,2] (x,y) f32, scores [B,kpad], n [B] int32, cand_count [B] [, nms [B,H,W]]
+    [, n_valid [B]]).  ``cand_count`` > the candidate cap (``default_cand_cap`` unless ``cap`` is given) means NMS
+    survivors were dropped (plateau image) and the call must be repeated with ``cap = H * W``; ``n_valid`` > kpad means
+    "unlimited" selection (max_keypoints < 0) found more keypoints than the kernel's 4096 slots and returned the best 4096.
+    ``border_hi`` = exclusive upper bounds (y_hi, x_hi) of the border window when they are not (H - border, W - border).
 
     NMS + threshold + border + top-k on the device with no host sync (reference nets/sfd2.py:305-329).
     ``strict`` selects the ``>`` comparison of the export path (nets/sfd2.py:435); ``fallback`` the
@@ -65,8 +75,7 @@ def detect_keypoints(score: Tensor, conf_th: float, min_keypoints: int, max_keyp
     kpad = max_keypoints if max_keypoints >= 0 else kmax
     kpad = max(kpad, 1)
     if cap is None:
-        # local maxima are >= r+1 apart unless the map has exact plateaus; overflow is detected below
-        cap = max(4096, ((h + radius) // (radius + 1)) * ((w + radius) // (radius + 1)))
+        cap = default_cand_cap(h, w, radius)
     dev = score.device
     cand = torch.empty((b, cap), device=dev, dtype=torch.int64)
     counts = torch.empty((2, b), device=dev, dtype=torch.int32)
@@ -76,12 +85,16 @@ def detect_keypoints(score: Tensor, conf_th: float, min_keypoints: int, max_keyp
     kpts = torch.empty((b, kpad, 2), device=dev, dtype=torch.float32)
     scs = torch.empty((b, kpad), device=dev, dtype=torch.float32)
     n = torch.empty((b,), device=dev, dtype=torch.int32)
+    n_valid = torch.empty((b,), device=dev, dtype=torch.int32) if return_valid else None
+    y_hi, x_hi = border_hi if border_hi is not None else (0, 0)
     call('pram_select_keypoints', ptr(cand), cap, ptr(counts[0]), ptr(counts[1]), ptr(score), b, h, w,
          float(th_lo), float(th_hi), int(min_keypoints) if fallback else -1, int(max_keypoints), int(border),
-         ptr(kpts), ptr(scs), ptr(n), kpad, stream_ptr())
+         int(y_hi), int(x_hi), ptr(kpts), ptr(scs), ptr(n), kpad, ptr(n_valid), stream_ptr())
     out = (kpts, scs, n, counts[0])
     if return_nms:
         out = out + (nms,)
+    if return_valid:
+        out = out + (n_valid,)
     return out
 
 
@@ -470,6 +483,29 @@ def ransac_pnp(kpts: Tensor, matches: Tensor, xyz: Tensor, fx: float, fy: float,
     call('pram_ransac_pnp', ptr(kpts), ptr(matches), ptr(xyz), b, n, nref, float(fx), float(fy), float(cx), float(cy),
          float(pixel_shift), float(max_error), int(num_hypotheses), int(lo_iters), int(final_iters), int(min_inliers),
          int(seed) & 0xffffffff, ptr(ws), ptr(q), ptr(t), ptr(ni), ptr(inl), ptr(ok), stream_ptr())
+    return {'qvec': q, 'tvec': t, 'num_inliers': ni, 'inliers': inl.bool(), 'success': ok.bool()}
+
+
+def ransac_pnp_corr(corr: Tensor, focal_mean: float, max_error: float, num_hypotheses: int = 1024, lo_iters: int = 10,
+                    final_iters: int = 20, min_inliers: int = 3, seed: int = 0, counts: Optional[Tensor] = None):
+    """corr [B,n,5] float64 (x, y, X, Y, Z), (x, y) = undistorted camera-plane coordinates -> same dict as ``ransac_pnp``.
+    Nothing is rounded to float32 on the way in (the pycolmap-compatible entry, localization/pose_estimator.py)."""
+    _lib.require_cuda(corr, 'correspondences')
+    if corr.dtype != torch.float64:
+        raise _lib.PramError('ransac_pnp_corr expects float64 correspondences')
+    corr = corr.contiguous()
+    b, n, _ = corr.shape
+    dev = corr.device
+    nbytes = int(_lib.load().pram_ransac_workspace_bytes(b, n, num_hypotheses))
+    ws = torch.empty((nbytes + 7) // 8, device=dev, dtype=torch.float64)
+    q = torch.empty((b, 4), device=dev, dtype=torch.float64)
+    t = torch.empty((b, 3), device=dev, dtype=torch.float64)
+    ni = torch.empty((b,), device=dev, dtype=torch.int32)
+    inl = torch.empty((b, n), device=dev, dtype=torch.uint8)
+    ok = torch.empty((b,), device=dev, dtype=torch.int32)
+    call('pram_ransac_pnp_corr', ptr(corr), ptr(counts), b, n, float(focal_mean), float(max_error), int(num_hypotheses),
+         int(lo_iters), int(final_iters), int(min_inliers), int(seed) & 0xffffffff, ptr(ws), ptr(q), ptr(t), ptr(ni), ptr(inl),
+         ptr(ok), stream_ptr())
     return {'qvec': q, 'tvec': t, 'num_inliers': ni, 'inliers': inl.bool(), 'success': ok.bool()}
 
 

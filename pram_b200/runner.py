@@ -33,12 +33,16 @@ class SyntheticMap:
 
 class LocalizationPipeline:
     def __init__(self, sfd2: ResNet4x, segnet: SegNetViT, matcher: GML, max_keypoints: int = 1024,
-                 focal: float = 525.0, ransac_max_error: float = 8.0, device='cuda'):
+                 focal: float = 525.0, ransac_max_error: float = 8.0, device='cuda', landmarks_per_frame: int = 1):
         self.dev = torch.device(device)
         self.sfd2 = sfd2.to(self.dev)
         self.segnet = segnet.to(self.dev)
         self.matcher = matcher.to(self.dev)
         self.K = max_keypoints
+        # > 1: every frame is matched against that many candidate landmarks in ONE batched matcher call ("multi-landmark
+        # match_features_batch", BASELINE.json configs[4]; the reference runs these calls one after the other,
+        # multimap3d.py:114-239) and the pose with most inliers wins
+        self.L = landmarks_per_frame
         self.focal = focal
         self.max_error = ransac_max_error
         self.cfg = {'min_keypoints': 128, 'max_keypoints': max_keypoints}
@@ -66,13 +70,17 @@ class LocalizationPipeline:
         including its (1,3,W,H) image_shape convention)."""
         b, _, h, w = image_shape
         shp = (1, 3, w, h)
-        m = self.matcher({'descriptors0': f['descriptors'], 'keypoints0': f['keypoints'],
+        d0, k0 = f['descriptors'], f['keypoints']
+        if self.L > 1:  # pair (frame b, landmark l) = row b * L + l of the reference set
+            d0, k0 = d0.repeat_interleave(self.L, 0), k0.repeat_interleave(self.L, 0)
+        m = self.matcher({'descriptors0': d0, 'keypoints0': k0,
                           'descriptors1': smap.descriptors, 'keypoints1': smap.keypoints,
                           'image_shape0': shp, 'image_shape1': shp})
         # slots j >= num_keypoints[b] of the fixed [B, K] layout are padding (keypoint (0,0), zero descriptor): they must
         # never reach PnP as correspondences.  (They still take part in attention / Sinkhorn as tokens -- see DESIGN.md
         # "padded slots"; the benched frames always fill the budget, which bench.py asserts.)
-        pad = torch.arange(f['keypoints'].shape[1], device=self.dev)[None] >= f['num_keypoints'][:, None]
+        nk = f['num_keypoints'] if self.L == 1 else f['num_keypoints'].repeat_interleave(self.L, 0)
+        pad = torch.arange(f['keypoints'].shape[1], device=self.dev)[None] >= nk[:, None]
         m['matches0'] = m['matches0'].masked_fill(pad, -1)
         m['matching_scores0'] = m['matching_scores0'].masked_fill(pad, 0.0)
         return m
@@ -89,8 +97,11 @@ class LocalizationPipeline:
     def localize(self, images: torch.Tensor, smap: Optional[SyntheticMap] = None) -> Dict[str, torch.Tensor]:
         shape = tuple(images.shape)
         f = self.features(images)
+        # cand_overflow[b]: NMS left more survivors than the candidate buffer holds (exact plateaus in the score map); the
+        # sync-free batched path cannot repeat the frame with a full buffer the way extract_local_global does, so callers
+        # check this flag (bench.py does after the timed region; a true entry means that frame's keypoints are a subset)
         out = {'keypoints': f['keypoints'], 'num_keypoints': f['num_keypoints'], 'scores': f['scores'],
-               'descriptors': f['descriptors']}
+               'descriptors': f['descriptors'], 'cand_overflow': f['cand_count'] > f['cand_cap']}
         if smap is None or not self.two_streams:
             self._recognition(f, shape, out)
             if smap is not None:
@@ -120,10 +131,47 @@ class LocalizationPipeline:
         """2D-3D matches -> absolute pose per frame (reference singlemap3d.py:156-175: matched keypoints
         + 0.5, matched xyz, ransac max_error from the config), entirely on the device."""
         h, w = image_shape[-2:]
-        r = ops.ransac_pnp(f['keypoints'], m['matches0'], smap.xyz, self.focal, self.focal, w / 2.0, h / 2.0,
+        kp = f['keypoints'] if self.L == 1 else f['keypoints'].repeat_interleave(self.L, 0)
+        r = ops.ransac_pnp(kp, m['matches0'], smap.xyz, self.focal, self.focal, w / 2.0, h / 2.0,
                            self.max_error, pixel_shift=0.5, num_hypotheses=self.num_hypotheses, seed=0)
-        return {'qvec': r['qvec'], 'tvec': r['tvec'], 'num_inliers': r['num_inliers'], 'inliers': r['inliers'],
-                'pose_success': r['success']}
+        if self.L > 1:  # per frame: the landmark whose pose has most inliers (ties: the first, like the reference's loop order)
+            b = f['keypoints'].shape[0]
+            best = r['num_inliers'].view(b, self.L).argmax(1)
+            rows = torch.arange(b, device=self.dev) * self.L + best
+            r = {k: v[rows] for k, v in r.items()}
+            r['best_landmark'] = best
+        out = {'qvec': r['qvec'], 'tvec': r['tvec'], 'num_inliers': r['num_inliers'], 'inliers': r['inliers'],
+               'pose_success': r['success']}
+        if self.L > 1:
+            out['best_landmark'] = r['best_landmark']
+        return out
+
+    # -- per-stage device timers (SURVEY.md section 5; reference loc_by_rec_online.py:108-134, 212-222) ---------------------
+    @torch.no_grad()
+    def localize_timed(self, images: torch.Tensor, smap: Optional[SyntheticMap] = None):
+        """``localize`` run eagerly on ONE stream with CUDA events between the stages.  Returns (out, times) with
+        ``times`` = {'time_feat', 'time_rec', 'time_loc', 'time_total'} in SECONDS for the whole batch -- the quantities the
+        reference stores on every Frame (``Frame.time_feat / time_rec / time_loc``; ``time_ref`` = 0: no refinement round in
+        this path) -- measured on the device instead of with time.time() around asynchronous launches."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        shape = tuple(images.shape)
+        ev[0].record()
+        f = self.features(images)
+        ev[1].record()
+        out = {'keypoints': f['keypoints'], 'num_keypoints': f['num_keypoints'], 'scores': f['scores'],
+               'descriptors': f['descriptors'], 'cand_overflow': f['cand_count'] > f['cand_cap']}
+        self._recognition(f, shape, out)
+        ev[2].record()
+        if smap is not None:
+            m = self.match(f, smap, shape)
+            out.update(m)
+            out.update(self.pose(f, m, smap, shape))
+        ev[3].record()
+        torch.cuda.synchronize(self.dev)
+        t = {'time_feat': ev[0].elapsed_time(ev[1]) * 1e-3, 'time_rec': ev[1].elapsed_time(ev[2]) * 1e-3,
+             'time_loc': ev[2].elapsed_time(ev[3]) * 1e-3, 'time_ref': 0.0}
+        t['time_total'] = t['time_feat'] + t['time_rec'] + t['time_loc'] + t['time_ref']
+        return out, t
 
     # -- CUDA graph: one replay per batch instead of ~1000 launches + tensor-map encodes -----------------
     @torch.no_grad()
@@ -154,21 +202,31 @@ class LocalizationPipeline:
 
     # -- synthetic map ------------------------------------------------------------------------
     @torch.no_grad()
-    def build_synthetic_map(self, images: torch.Tensor, seed: int = 0, outlier_frac: float = 0.2) -> SyntheticMap:
+    def build_synthetic_map(self, images: torch.Tensor, seed: int = 0, outlier_frac: float = 0.2,
+                            ref_keypoints: Optional[int] = None) -> SyntheticMap:
+        """One reference set per (frame, landmark): the frame's own keypoints under a seeded permutation (the first
+        ``ref_keypoints`` of it when given: BASELINE.json configs[4] matches 4096 query keypoints against 1024 reference
+        keypoints per landmark), lifted to 3-D with a known pose, ``outlier_frac`` replaced by outliers."""
         f = self.features(images)
+        f = {'keypoints': f['keypoints'].repeat_interleave(self.L, 0), 'descriptors': f['descriptors'].repeat_interleave(self.L, 0)}
         b, k, _ = f['keypoints'].shape
+        nb = b // self.L
         g = torch.Generator(device='cpu').manual_seed(seed)
         perm = torch.stack([torch.randperm(k, generator=g) for _ in range(b)]).to(self.dev)
+        if ref_keypoints is not None and ref_keypoints < k:
+            perm = perm[:, :ref_keypoints].contiguous()
+            k = ref_keypoints
         kp = torch.gather(f['keypoints'], 1, perm[..., None].expand(-1, -1, 2))
         desc = torch.gather(f['descriptors'], 1, perm[..., None].expand(-1, -1, 128)).clone()
         # known pose per frame: small rotation (<= 15 deg) and translation (<= 0.5 m)
-        ax = torch.nn.functional.normalize(torch.randn(b, 3, generator=g), dim=-1)
-        ang = (torch.rand(b, generator=g) * 15.0 * 3.14159265 / 180.0)
+        # one camera pose per FRAME (its landmarks share the world frame)
+        ax = torch.nn.functional.normalize(torch.randn(nb, 3, generator=g), dim=-1).repeat_interleave(self.L, 0)
+        ang = (torch.rand(nb, generator=g) * 15.0 * 3.14159265 / 180.0).repeat_interleave(self.L, 0)
         Kx = torch.zeros(b, 3, 3)
         Kx[:, 0, 1], Kx[:, 0, 2], Kx[:, 1, 0] = -ax[:, 2], ax[:, 1], ax[:, 2]
         Kx[:, 1, 2], Kx[:, 2, 0], Kx[:, 2, 1] = -ax[:, 0], -ax[:, 1], ax[:, 0]
         R = torch.eye(3)[None] + torch.sin(ang)[:, None, None] * Kx + (1 - torch.cos(ang))[:, None, None] * (Kx @ Kx)
-        t = (torch.rand(b, 3, generator=g) - 0.5)
+        t = (torch.rand(nb, 3, generator=g) - 0.5).repeat_interleave(self.L, 0)
         z = 1.0 + 4.0 * torch.rand(b, k, generator=g)
         outl = torch.rand(b, k, generator=g) < outlier_frac
         R, t, z, outl = R.to(self.dev), t.to(self.dev), z.to(self.dev), outl.to(self.dev)

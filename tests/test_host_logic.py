@@ -205,7 +205,7 @@ def test_tracker_track_last_frame_cpu():
         got['p2d'], got['opt'] = p2d.copy(), estimation_options
         return {'cam_from_world': SimpleNamespace(rotation=SimpleNamespace(quat=np.array([0., 0., 0., 1.])), translation=np.zeros(3)),
                 'num_inliers': p2d.shape[0], 'inliers': np.ones(p2d.shape[0], bool)}
-    ret = Tracker({'localization': {'threshold': 12}}, Stub(), device='cpu', pose_fn=pose_fn).track_last_frame(curr, last)
+    ret = Tracker(None, Stub(), {'localization': {'threshold': 12}}, device='cpu', pose_fn=pose_fn).track_last_frame(curr, last)
     q = np.arange(0, n0, 3); r = (q * 7) % n1
     ok = pids[r] >= 0
     q, r = q[ok], r[ok]

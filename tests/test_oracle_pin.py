@@ -188,3 +188,32 @@ def test_nearest_neighbor_oracle_vs_reference_module():
         ours = O.nearest_neighbor_forward(d0, d1, **{**NearestNeighbor.default_conf, **conf})
         assert torch.equal(ref['matches0'], ours['matches0'])
         assert torch.equal(ref['matching_scores0'], ours['matching_scores0'])
+
+
+@needs_ref
+def test_adagml_oracle_vs_reference_module():
+    """O.adagml_forward against the reference's own ``nets.adagml.AdaGML.produce_matches`` (CPU shim of SURVEY.md 8c:
+    nets.adagml.sink_algorithm = nets.gml.sink_algorithm) on a case that really prunes tokens over several layers and
+    exits early: identical pruning trace, identical matches, scores equal to the last float32 bit (torch's threaded CPU
+    reductions are allowed one ulp of run-to-run noise)."""
+    ref = RL.import_reference()
+    sd = RL.calibrated_adagml_state()
+    net = ref.adagml.AdaGML({})
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    g = torch.Generator().manual_seed(0)
+    m = n = 400
+    d0 = torch.nn.functional.normalize(torch.randn(1, m, 128, generator=g), dim=-1)
+    perm = torch.randperm(n, generator=g)
+    d1 = d0[:, perm] + 0.02 * torch.randn(1, n, 128, generator=g)
+    k0 = torch.rand(1, m, 2, generator=g) * torch.tensor([640., 480.])
+    data = {'descriptors0': d0, 'descriptors1': d1, 'keypoints0': k0, 'keypoints1': k0[:, perm],
+            'scores0': torch.rand(1, m, generator=g), 'scores1': torch.rand(1, n, generator=g),
+            'image_shape0': (1, 3, 640, 480), 'image_shape1': (1, 3, 640, 480)}
+    with torch.no_grad():
+        r = net.produce_matches(data)
+    o = O.adagml_forward(sd, data, return_trace=True)
+    assert len(o['trace']) >= 3 and o['trace'][-1][1] < 200 and o['last_layer'] < 8   # pruned and stopped early
+    assert torch.equal(r['matches0'], o['matches0'])
+    assert (r['matching_scores0'] > 0).sum() > 50   # the surviving tokens carry real Sinkhorn scores (seeded weights: no match above 0.2)
+    assert torch.allclose(r['matching_scores0'], o['matching_scores0'], rtol=0, atol=1e-6)
