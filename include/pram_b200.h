@@ -165,6 +165,8 @@ typedef struct pram_tc_args {
     int seg_split, seg_n0, seg_n1, heads;
     int cluster;                          /* 0 = auto, 1 = single CTAs, 2 = 2-CTA clusters, weight tile TMA-multicast */
     int l2_prefetch;                      /* 1 = L2-prefetch the next tile's activation boxes (single-tap layers); default off */
+    int f16;                              /* 1 (split == 1): a / w planes hold IEEE fp16 and out_hi receives fp16 (single-pass fp16 mode) */
+    const void* res_hi; const void* res_lo; /* residual as split-bf16 planes (when res == NULL): r = hi + lo, row stride res_ld */
 } pram_tc_args;
 int pram_gemm_tc(const pram_tc_args* args, pram_stream_t stream);
 
@@ -245,6 +247,9 @@ int pram_projection_top2(const float* sim, int ld, int M, int N, const float* kp
 int pram_nn_match(const float* sim, const float* simT, int B, int N, int M, float ratio_threshold, float distance_threshold,
                   int mutual, long long* matches0, float* scores0, long long* matches1_ws, float* scores1_ws,
                   pram_stream_t stream);
+
+/* fp32 -> one plane of IEEE fp16 (operand of the single-pass fp16 GEMM mode, pram_tc_args.f16). */
+int pram_cast_f16(const float* in, void* out, long long n, pram_stream_t stream);
 
 /* fp32 -> split bf16 planes: hi = bf16(x), lo = bf16(x - hi) (lo may be NULL). */
 int pram_split_bf16(const float* in, void* hi, void* lo, long long n, pram_stream_t stream);

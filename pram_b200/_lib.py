@@ -64,7 +64,7 @@ class TcArgs(C.Structure):
         ('qkv_mode', _I), ('cosb', _P), ('sinb', _P), ('qk_scale', _F),
         ('q_hi', _P), ('q_lo', _P), ('k_hi', _P), ('k_lo', _P), ('v_hi', _P), ('v_lo', _P),
         ('seg_split', _I), ('seg_n0', _I), ('seg_n1', _I), ('heads', _I),
-        ('cluster', _I), ('l2_prefetch', _I),
+        ('cluster', _I), ('l2_prefetch', _I), ('f16', _I), ('res_hi', _P), ('res_lo', _P),
     ]
 
 
@@ -85,6 +85,7 @@ class MlpBlockArgs(C.Structure):
 
 SIGNATURES['pram_mlp_block_tc'] = (_I, [C.POINTER(MlpBlockArgs), _P])
 SIGNATURES['pram_split_bf16'] = (_I, [_P, _P, _P, _L, _P])
+SIGNATURES['pram_cast_f16'] = (_I, [_P, _P, _L, _P])
 SIGNATURES['pram_attention_tc'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I, _I, _I, _I, _P])
 SIGNATURES['pram_attention_prep'] = (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P, _I, _P])
 _D = C.c_double

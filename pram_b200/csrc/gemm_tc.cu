@@ -19,6 +19,7 @@
 //   SPLIT=1: plain bf16.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdio.h>
 
 namespace tc {
@@ -40,6 +41,7 @@ struct Args {
     // epilogue
     const float* bias;
     const float* res; long long res_ld;
+    const __nv_bfloat16* res_hi; const __nv_bfloat16* res_lo;  // residual given as split-bf16 planes (res == NULL): r = hi + lo
     int relu;
     float* out_f32; long long ld_f32;
     __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; long long ld_bf;
@@ -52,6 +54,8 @@ struct Args {
     __nv_bfloat16* q_hi; __nv_bfloat16* q_lo; __nv_bfloat16* k_hi; __nv_bfloat16* k_lo; __nv_bfloat16* v_hi; __nv_bfloat16* v_lo;
     int seg_split, seg_n0, seg_n1, heads;
     int l2_prefetch;     // 1: pull the next tile's activation boxes into L2 one tile ahead (single-tap layers)
+    int f16;             // operands are IEEE fp16 (one MMA per k-step, 11-bit mantissas): A / W planes hold fp16 bits and the
+                         // out_hi plane receives fp16 (out_lo unused) -- the single-pass mode of the descriptor head
 };
 
 // ---------------------------------------------------------------------------------------- PTX
@@ -134,6 +138,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // N>>3 at bit 17, M>>4 at bit 24
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// same with A = B = fp16 (format code 0 in bits 7-9 / 10-12)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // The MMA-issuing WARP runs its loops convergently and elects one lane per instruction (elect.sync): operands that
 // are warp-uniform then stay in uniform registers and each MMA costs a handful of uniform-datapath instructions.
@@ -311,7 +319,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp, one elected lane per instruction) =====================
-        constexpr uint32_t idesc = make_idesc(BM, BN);
+        const uint32_t idesc = p.f16 ? make_idesc_f16(BM, BN) : make_idesc(BM, BN);
         int stage = 0; uint32_t phase = 0;
         int as = 0; uint32_t aphase = 0;
         for (int tile = cid; tile < total; tile += ncl) {
@@ -388,14 +396,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                 for (int i = 0; i < 8; ++i) {
                     const int pixr = lds32(eq_pix + 4 * (i * 4 + g1));
                     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (resp && pixr >= 0 && nb < p.N) {
-                        const float* rp = resp + (long long)pixr * p.res_ld + nb + col1;
-                        if (res_vec && nb + 32 <= p.N) t = __ldg(reinterpret_cast<const float4*>(rp));
-                        else {
-                            if (nb + col1 + 0 < p.N) t.x = __ldg(rp);
-                            if (nb + col1 + 1 < p.N) t.y = __ldg(rp + 1);
-                            if (nb + col1 + 2 < p.N) t.z = __ldg(rp + 2);
-                            if (nb + col1 + 3 < p.N) t.w = __ldg(rp + 3);
+                    if (pixr >= 0 && nb < p.N) {
+                        if (resp) {
+                            const float* rp = resp + (long long)pixr * p.res_ld + nb + col1;
+                            if (res_vec && nb + 32 <= p.N) t = __ldg(reinterpret_cast<const float4*>(rp));
+                            else {
+                                if (nb + col1 + 0 < p.N) t.x = __ldg(rp);
+                                if (nb + col1 + 1 < p.N) t.y = __ldg(rp + 1);
+                                if (nb + col1 + 2 < p.N) t.z = __ldg(rp + 2);
+                                if (nb + col1 + 3 < p.N) t.w = __ldg(rp + 3);
+                            }
+                        } else if (p.res_hi) {
+                            // residual from the producer's split-bf16 planes (host guarantees N % 32 == 0 and res_ld % 4 == 0):
+                            // the activation then never needs an fp32 copy in HBM
+                            const long long o = (long long)pixr * p.res_ld + nb + col1;
+                            const uint2 h = __ldg(reinterpret_cast<const uint2*>(p.res_hi + o));
+                            uint2 l = make_uint2(0u, 0u);
+                            if (p.res_lo) l = __ldg(reinterpret_cast<const uint2*>(p.res_lo + o));
+                            t = make_float4(__uint_as_float(h.x << 16) + __uint_as_float(l.x << 16),
+                                            __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u),
+                                            __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16),
+                                            __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u));
                         }
                     }
                     rv[i] = t;
@@ -529,6 +550,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                             const float fv[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
                             for (int k = 0; k < 8; k += 2) {
+                                if (SPLIT == 1 && p.f16) {  // single fp16 plane
+                                    __half2 h2 = __floats2half2_rn(fv[k], fv[k + 1]);
+                                    hi[k >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+                                    lo[k >> 1] = 0u;
+                                    continue;
+                                }
                                 __nv_bfloat162 h2 = __floats2bfloat162_rn(fv[k], fv[k + 1]);
                                 const uint32_t u = *reinterpret_cast<uint32_t*>(&h2);
                                 __nv_bfloat162 l2 = __floats2bfloat162_rn(fv[k] - __uint_as_float(u << 16),
@@ -651,7 +678,7 @@ static int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMa
         if constexpr (BN == 256) return launch_mode<BN, SPLIT, 2, CL>(ah, al, wh, wl, a, m_tiles, n_tiles, stream);
         else return PRAM_ERR_UNSUPPORTED;
     }
-    if (a.res) return launch_mode<BN, SPLIT, 1, CL>(ah, al, wh, wl, a, m_tiles, n_tiles, stream);
+    if (a.res || a.res_hi) return launch_mode<BN, SPLIT, 1, CL>(ah, al, wh, wl, a, m_tiles, n_tiles, stream);
     return launch_mode<BN, SPLIT, 0, CL>(ah, al, wh, wl, a, m_tiles, n_tiles, stream);
 }
 
@@ -683,6 +710,8 @@ struct pram_tc_args {
     int seg_split, seg_n0, seg_n1, heads;
     int cluster;                          // 0 = auto, 1 = single CTAs, 2 = 2-CTA clusters with a multicast weight tile
     int l2_prefetch;                      // 1 = pull the next tile's activation boxes into L2 one tile ahead (single-tap layers); default off
+    int f16;                              // 1 (split == 1 only): a / w planes hold IEEE fp16, out_hi receives fp16 -- single-pass fp16 mode
+    const void* res_hi; const void* res_lo;  // residual as split-bf16 planes (used when res == NULL; row stride res_ld, N % 32 == 0)
 };
 
 PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
@@ -744,6 +773,10 @@ PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
     k.q_hi = (__nv_bfloat16*)a->q_hi; k.q_lo = (__nv_bfloat16*)a->q_lo; k.k_hi = (__nv_bfloat16*)a->k_hi;
     k.k_lo = (__nv_bfloat16*)a->k_lo; k.v_hi = (__nv_bfloat16*)a->v_hi; k.v_lo = (__nv_bfloat16*)a->v_lo;
     k.seg_split = a->seg_split; k.seg_n0 = a->seg_n0; k.seg_n1 = a->seg_n1; k.heads = a->heads;
+    if (a->f16 && a->split != 1) return PRAM_ERR_ARG;
+    k.f16 = a->f16;
+    k.res_hi = (const __nv_bfloat16*)a->res_hi; k.res_lo = (const __nv_bfloat16*)a->res_lo;
+    if (!a->res && a->res_hi && ((a->N % 32) || (a->res_ld % 4))) return PRAM_ERR_UNSUPPORTED;
     k.l2_prefetch = (a->ntaps == 1) && (a->l2_prefetch == 1);  // measured on B200: no gain (the thin GEMMs are store-bound), off unless asked for
     if (a->qkv_mode) {
         if (bn != 256 || a->heads * 64 != 256 || !a->q_hi || !a->v_hi || a->ps_hi || a->l2norm) return PRAM_ERR_UNSUPPORTED;
@@ -781,6 +814,26 @@ __global__ void split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* _
             if (lo) lo[i] = l;
         }
     }
+}
+
+__global__ void cast_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i >= n) return;
+    if (i + 8 <= n) {
+        const float4 a = *reinterpret_cast<const float4*>(in + i), b = *reinterpret_cast<const float4*>(in + i + 4);
+        __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
+        *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<uint4*>(h);
+    } else {
+        for (; i < n; ++i) out[i] = __float2half_rn(in[i]);
+    }
+}
+
+// fp32 -> IEEE fp16 (operand plane of the single-pass fp16 GEMM mode); n % 8 == 0 rows are moved 32 B -> 16 B per thread
+PRAM_API int pram_cast_f16(const float* in, void* out, long long n, cudaStream_t stream) {
+    if (!in || !out || n <= 0) return PRAM_ERR_ARG;
+    cast_f16_kernel<<<cdiv((n + 7) / 8, 256), 256, 0, stream>>>(in, (__half*)out, n);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
 }
 
 PRAM_API int pram_split_bf16(const float* in, void* hi, void* lo, long long n, cudaStream_t stream) {

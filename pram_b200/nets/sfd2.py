@@ -96,16 +96,21 @@ class ResNet4x(nn.Module):
         # 'bf16'   : tcgen05 tensor cores, plain bf16 operands (fastest; keypoint order not stable)
         # 'fp32'   : CUDA-core fp32 kernels (exact-arithmetic reference path)
         self.precision = 'bf16x3'
+        # precision of the DESCRIPTOR head only (convDa.0, convDa.3, convDb; 46.6 of the 133 GFLOP of the stack): None = same
+        # as the trunk; 'f16' = single-pass IEEE fp16 operands (11-bit mantissas, fp32 accumulation) -- descriptors are
+        # sampled, L2-normalised and matched with a tolerance, they never feed the discontinuous keypoint selection
+        self.desc_precision = None
         self.eval()
 
     @property
     def compute_dtype(self) -> str:
-        return {'bf16x3': 'bf16x3 (split-bf16 tcgen05, fp32 accumulate)', 'bf16': 'bf16', 'fp32': 'f32'}[self.precision]
+        base = {'bf16x3': 'bf16x3 (split-bf16 tcgen05, fp32 accumulate)', 'bf16': 'bf16', 'fp32': 'f32'}[self.precision]
+        return base + (' + fp16 descriptor head' if (self.desc_precision == 'f16' and self.precision != 'fp32') else '')
 
-    def set_precision(self, precision: str):
-        if precision not in ('bf16x3', 'bf16', 'fp32'):
-            raise ValueError(precision)
-        self.precision = precision
+    def set_precision(self, precision: str, desc_precision: Optional[str] = None):
+        if precision not in ('bf16x3', 'bf16', 'fp32') or desc_precision not in (None, 'f16'):
+            raise ValueError((precision, desc_precision))
+        self.precision, self.desc_precision = precision, desc_precision
         return self
 
     # -- weight repacking ---------------------------------------------------------------------
@@ -134,7 +139,10 @@ class ResNet4x(nn.Module):
             # tensor-core layout: [taps, Cout, Cin] (K-major rows), split into bf16 hi/lo planes
             co, ci, kh, kw = w.shape
             if ci % 8 == 0:
-                pk[name + '.tc'] = ops.split_bf16(w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).float().contiguous().to(dev))
+                wt = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).float().contiguous().to(dev)
+                pk[name + '.tc'] = ops.split_bf16(wt)
+                if name in ('convDa.0', 'convDa.3', 'convDb'):
+                    pk[name + '.tc16'] = ops.as_f16_plane(wt)
 
         for name in ('conv1a', 'conv1b', 'conv2a', 'conv2b', 'conv3a', 'conv3b'):
             seq = getattr(self, name)
@@ -199,23 +207,33 @@ class ResNet4x(nn.Module):
         h4, w4 = (h2 - 1) // 2 + 1, (w2 - 1) // 2 + 1
         o2b = ct(ps2a, T('conv2b'), pk['conv2b.b'], 3, 2, True, split, out_shape_hw=(h4, w4))['bf']
         o3a = ct(o2b, T('conv3a'), pk['conv3a.b'], 3, 1, True, split)['bf']
-        o3 = ct(o3a, T('conv3b'), pk['conv3b.b'], 3, 1, True, split, want_f32=True)
-        cur_bf, cur_f32 = o3['bf'], o3['f32']
+        # the ResBlock residuals are taken from the producer's split-bf16 planes (bf16x3 mode: hi + lo carries ~16 mantissa
+        # bits): the 256-channel maps at 1/4 resolution are written as fp32 only once, for out4 (mid_features of the API)
+        planes_res = split == 3
+        o3 = ct(o3a, T('conv3b'), pk['conv3b.b'], 3, 1, True, split, want_f32=not planes_res)
+        cur_bf, cur_f32 = o3['bf'], o3.get('f32')
         o3b_bf = cur_bf
         last = None
         for i in range(3):
             t = ct(cur_bf, T(f'conv4.{i}.c1'), pk[f'conv4.{i}.c1.b'], 1, 1, True, split)['bf']
             t = ops.gconv3x3_tc(t, pk[f'conv4.{i}.c2.w'], pk[f'conv4.{i}.c2.b'], True, split)
-            last = ct(t, T(f'conv4.{i}.c3'), pk[f'conv4.{i}.c3.b'], 1, 1, True, split, res=cur_f32, want_f32=True,
-                      want_ps=(i == 2))
-            cur_bf, cur_f32 = last['bf'], last['f32']
+            last = ct(t, T(f'conv4.{i}.c3'), pk[f'conv4.{i}.c3.b'], 1, 1, True, split, res=None if planes_res else cur_f32,
+                      res_bf=cur_bf if planes_res else None, want_f32=(i == 2) or not planes_res, want_ps=(i == 2))
+            cur_bf, cur_f32 = last['bf'], last.get('f32')
         h8, w8 = (h4 - 1) // 2 + 1, (w4 - 1) // 2 + 1
         p = ct(last['ps'], T('convPa.0'), pk['convPa.0.b'], 3, 2, True, split, out_shape_hw=(h8, w8))['bf']
         p = ct(p, T('convPa.3'), pk['convPa.3.b'], 3, 1, False, split)['bf']
         logits = ct(p, T('convPb'), pk['convPb.b'], 1, 1, False, split, want_f32=True, want_bf=False)['f32']
-        d = ct(cur_bf, T('convDa.0'), pk['convDa.0.b'], 3, 1, True, split)['bf']
-        d = ct(d, T('convDa.3'), pk['convDa.3.b'], 3, 1, False, split)['bf']
-        desc = ct(d, T('convDb'), pk['convDb.b'], 1, 1, False, split, want_f32=True, want_bf=False, l2norm=True)['f32']
+        if self.desc_precision == 'f16':
+            T16 = lambda n: pk[n + '.tc16']
+            d = ops.as_f16_plane(cur_f32)   # out4 as one fp16 plane
+            d = ct(d, T16('convDa.0'), pk['convDa.0.b'], 3, 1, True, 1, f16=True)['bf']
+            d = ct(d, T16('convDa.3'), pk['convDa.3.b'], 3, 1, False, 1, f16=True)['bf']
+            desc = ct(d, T16('convDb'), pk['convDb.b'], 1, 1, False, 1, want_f32=True, want_bf=False, l2norm=True, f16=True)['f32']
+        else:
+            d = ct(cur_bf, T('convDa.0'), pk['convDa.0.b'], 3, 1, True, split)['bf']
+            d = ct(d, T('convDa.3'), pk['convDa.3.b'], 3, 1, False, split)['bf']
+            desc = ct(d, T('convDb'), pk['convDb.b'], 1, 1, False, split, want_f32=True, want_bf=False, l2norm=True)['f32']
         return {'out1b': o1b, 'out2b': o2b, 'out3b': o3b_bf, 'out4': cur_f32, 'logits': logits, 'desc': desc}
 
     @staticmethod

@@ -236,6 +236,15 @@ class Split:
         return self.hi.float() + (self.lo.float() if self.lo is not None else 0)
 
 
+def as_f16_plane(x: Tensor) -> Split:
+    """fp32 -> ONE plane of IEEE fp16 bits (held in a bfloat16-typed tensor: the TMA descriptors move 2-byte elements and
+    do not care) -- operand of the single-pass fp16 mode (``f16=True``, ``split=1``)."""
+    x = _f32c(x)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    call('pram_cast_f16', ptr(x), ptr(out), x.numel(), stream_ptr())
+    return Split(out, None)
+
+
 def split_bf16(x: Tensor, with_lo: bool = True) -> Split:
     x = _f32c(x)
     hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
@@ -279,7 +288,7 @@ def gemm_tc(a: Split, a_ld: int, in_w: int, in_h: int, in_planes: int, cin: int,
             w_batch_mult: int = 0, bias: Optional[Tensor] = None, res: Optional[Tensor] = None, res_ld: int = 0,
             relu: bool = False, out_f32: Optional[Tensor] = None, ld_f32: int = 0, out_bf: Optional[Split] = None,
             ld_bf: int = 0, out_ps: Optional[Split] = None, ld_ps: int = 0, l2norm: bool = False, split: int = 3,
-            bn: int = 0, qkv: Optional[dict] = None):
+            bn: int = 0, qkv: Optional[dict] = None, f16: bool = False, res_bf: Optional[Split] = None):
     """Raw launch of the tcgen05 implicit-GEMM kernel (see include/pram_b200.h: pram_gemm_tc)."""
     A = _lib.TcArgs()
     A.a_hi, A.a_lo, A.a_ld = a.hi.data_ptr(), (a.lo.data_ptr() if a.lo is not None else None), a_ld
@@ -311,13 +320,16 @@ def gemm_tc(a: Split, a_ld: int, in_w: int, in_h: int, in_planes: int, cin: int,
         A.seg_split, A.seg_n0, A.seg_n1 = qkv['seg_split'], qkv['seg_n0'], qkv['seg_n1']
     A.cluster = GEMM_CLUSTER
     A.l2_prefetch = GEMM_L2_PREFETCH
+    A.f16 = int(f16)
+    if res_bf is not None:  # residual from split-bf16 planes instead of an fp32 tensor
+        A.res_hi, A.res_lo = res_bf.hi.data_ptr(), (res_bf.lo.data_ptr() if res_bf.lo is not None else None)
     import ctypes
     call('pram_gemm_tc', ctypes.byref(A), stream_ptr())
 
 
 def conv_tc(x: Split, w: Split, bias: Optional[Tensor], ksize: int, stride: int, relu: bool, split: int,
             res: Optional[Tensor] = None, want_f32: bool = False, want_bf: bool = True, want_ps: bool = False,
-            l2norm: bool = False, out_shape_hw=None, bn: int = 0):
+            l2norm: bool = False, out_shape_hw=None, bn: int = 0, f16: bool = False, res_bf: Optional[Split] = None):
     """3x3 / 1x1 convolution on tensor cores.  x: Split [B,H,W,Cin] NHWC (stride 1) or the 2x2 phase-split
     tensor [B*4,ceil(H/2),ceil(W/2),Cin] of it (stride 2; then ``out_shape_hw`` = (Ho, Wo) of the conv).
     w: Split [taps,Cout,Cin].  Returns dict with any of 'f32' [B,Ho,Wo,Cout], 'bf' Split, 'ps' Split."""
@@ -343,7 +355,7 @@ def conv_tc(x: Split, w: Split, bias: Optional[Tensor], ksize: int, stride: int,
                              zero=bool(ho % 2 or wo % 2))
     tw_log2 = 4 if wo >= 16 else max(0, (wo - 1).bit_length())
     gemm_tc(x, x.shape[-1], in_w, in_h, in_planes, cin, w, taps_n, b, ho, wo, cout, taps, ppi, tw_log2, 0, bias, res,
-            cout, relu, f32, cout, obf, cout, ops_ps, cout, l2norm, split, bn)
+            cout, relu, f32, cout, obf, cout, ops_ps, cout, l2norm, split, bn, f16=f16, res_bf=res_bf)
     if f32 is not None:
         out['f32'] = f32
     if obf is not None:

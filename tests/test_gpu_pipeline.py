@@ -42,8 +42,11 @@ def _build(dev, precision='bf16x3'):
     vit = SegNetViT({'n_class': NCLASS, 'n_layers': 15, 'output_dim': 1024, 'descriptor_dim': 256})
     vit.load_state_dict(sd_vit, strict=True)
     gml = GML({}); gml.load_state_dict(sd_gml, strict=True)
-    for m in (sfd2, vit, gml):
-        m.set_precision(precision)
+    if precision == 'bf16x3+f16desc':   # the mixed mode: single-pass fp16 descriptor head, everything else bf16x3
+        sfd2.set_precision('bf16x3', 'f16'); vit.set_precision('bf16x3'); gml.set_precision('bf16x3')
+    else:
+        for m in (sfd2, vit, gml):
+            m.set_precision(precision)
     pipe = LocalizationPipeline(sfd2, vit, gml, max_keypoints=K, focal=FOCAL, ransac_max_error=MAX_ERROR, device=dev)
     return pipe, (sd_sfd2, sd_vit, sd_gml)
 
@@ -161,6 +164,22 @@ def test_pipeline_batch4_vs_oracle(case):
     for i in range(4):
         _check_frame_against_oracle(i, case['frames'], case['out'], case['smap'], case['sds'], report)
     _dump('pipeline_parity_b4.json', report)
+
+
+def test_pipeline_mixed_precision_vs_oracle(case, dev):
+    """The mixed mode (descriptor head in single-pass fp16, everything that feeds keypoint selection / recognition in
+    bf16x3) must pass the SAME oracle comparison with the SAME tolerances; its keypoints are bit-identical to the parity
+    mode's (the detector branch is untouched)."""
+    pipe, _ = _build(dev, 'bf16x3+f16desc')
+    with torch.no_grad():
+        out = pipe.localize(case['fd'], case['smap'])
+    torch.cuda.synchronize()
+    assert torch.equal(out['keypoints'], case['out']['keypoints']) and torch.equal(out['prediction'], case['out']['prediction'])
+    assert not torch.equal(out['descriptors'], case['out']['descriptors'])   # the fp16 head really ran
+    report = []
+    for i in range(4):
+        _check_frame_against_oracle(i, case['frames'], out, case['smap'], case['sds'], report)
+    _dump('pipeline_parity_b4_mixed.json', report)
 
 
 EXACT_KEYS = ('keypoints', 'num_keypoints', 'prediction', 'labels', 'seg_ids', 'non_bg', 'matches0', 'matches1',

@@ -224,7 +224,7 @@ def test_bench_workloads_and_step_bound():
     assert abs(bench.algorithmic_gflop_per_frame(480, 640, 1024, 113) - 250.8) < 0.1
     assert abs(bench.algorithmic_gflop_per_frame(768, 1024, 2048, 161) - 677.1) < 0.5
     assert abs(bench.algorithmic_gflop_per_frame(1200, 1600, 4096, 513) - 1911.0) < 2.0
-    b = bench.whole_step_bound(1000.0, 2, 3)
+    b = bench.whole_step_bound(1000.0, 2, 'bf16x3')
     json.dumps(b)
     assert b['tensor_bound_frames_per_s'] > 2000 and 0 < b['frac_of_tensor_bound'] < 1
     assert bench.WORKLOADS['7scenes']['kpts'] == 1024 and bench.WORKLOADS['cambridge']['h'] == 768 and bench.WORKLOADS['aachen']['kpts'] == 4096

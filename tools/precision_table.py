@@ -1,0 +1,101 @@
+"""Per-branch precision table (round-1 review item 5): the benched pipeline (640x480, K = 1024, 32 frames, shipped SFD2 + GML,
+seeded SegNetViT) with each branch moved from error-compensated bf16x3 to a cheaper operand format, one branch at a time,
+against the bf16x3 run (which tests/test_gpu_pipeline.py pins to the oracle): keypoint / label / match agreement, largest
+deviations, pose error against the known pose, and frames/s (CUDA-graph replay, CUDA events, L2 flushed).
+
+    python tools/precision_table.py [out.json]      (under gpurun)
+"""
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+import benchdata as BD  # noqa: E402
+from pram_b200.nets.gml import GML  # noqa: E402
+from pram_b200.nets.segnetvit import SegNetViT  # noqa: E402
+from pram_b200.nets.sfd2 import ResNet4x  # noqa: E402
+from pram_b200.runner import LocalizationPipeline  # noqa: E402
+
+dev = torch.device('cuda')
+B, K = 32, 1024
+sd_sfd2, sd_vit, sd_gml, tag = bench.states()
+frames = bench.make_frames(B).to(dev)
+flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+MODES = [
+    ('bf16x3 everywhere (parity mode)', dict(sfd2='bf16x3', desc=None, vit='bf16x3', gml='bf16x3')),
+    ('descriptor head fp16 x1', dict(sfd2='bf16x3', desc='f16', vit='bf16x3', gml='bf16x3')),
+    ('SegNetViT bf16 x1', dict(sfd2='bf16x3', desc=None, vit='bf16', gml='bf16x3')),
+    ('GML bf16 x1', dict(sfd2='bf16x3', desc=None, vit='bf16x3', gml='bf16')),
+    ('descriptor head fp16 + SegNetViT bf16 + GML bf16', dict(sfd2='bf16x3', desc='f16', vit='bf16', gml='bf16')),
+    ('SFD2 trunk + detector bf16 x1 (whole conv stack)', dict(sfd2='bf16', desc=None, vit='bf16x3', gml='bf16x3')),
+    ('bf16 x1 everywhere', dict(sfd2='bf16', desc=None, vit='bf16', gml='bf16')),
+]
+
+
+def build(m):
+    sfd2 = ResNet4x(); sfd2.load_state_dict(sd_sfd2, strict=True)
+    vit = SegNetViT({'n_class': 113, 'n_layers': 15, 'output_dim': 1024, 'descriptor_dim': 256}); vit.load_state_dict(sd_vit, strict=True)
+    gml = GML({}); gml.load_state_dict(sd_gml, strict=True)
+    sfd2.set_precision(m['sfd2'], m['desc']); vit.set_precision(m['vit']); gml.set_precision(m['gml'])
+    return LocalizationPipeline(sfd2, vit, gml, max_keypoints=K, focal=525.0, ransac_max_error=8.0, device=dev)
+
+
+def run(pipe, smap):
+    with torch.no_grad():
+        out = pipe.localize(frames, smap)
+    torch.cuda.synchronize()
+    out = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in out.items()}
+    pipe.capture(frames, smap)
+    ts = []
+    for _ in range(6):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); pipe.replay(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return out, B / (ts[len(ts) // 2] * 1e-3)
+
+
+base_pipe = build(MODES[0][1])
+smap = base_pipe.build_synthetic_map(frames, seed=0)   # ONE map (from the parity-mode features) for every mode
+rows, ref = [], None
+for name, m in MODES:
+    pipe = build(m)
+    out, fps = run(pipe, smap)
+    if ref is None:
+        ref = out
+    kp_same = []
+    for i in range(B):
+        a = {tuple(v) for v in out['keypoints'][i].cpu().tolist()}
+        b = {tuple(v) for v in ref['keypoints'][i].cpu().tolist()}
+        kp_same.append(len(a & b) / len(b))
+    same_kp = torch.tensor([torch.equal(out['keypoints'][i], ref['keypoints'][i]) for i in range(B)], device=dev)
+    r = {'mode': name, 'precisions': m, 'frames_per_s': fps, 'keypoint_overlap_mean': sum(kp_same) / B, 'keypoint_overlap_min': min(kp_same),
+         'frames_with_identical_keypoints': int(same_kp.sum())}
+    if same_kp.any():   # token-wise comparisons only on frames whose keypoint lists are identical
+        s = same_kp
+        top2 = torch.sort(ref['prediction'][s], -1).values[..., -2:]
+        dec = (top2[..., 1] - top2[..., 0]) > 2e-2
+        lab = out['labels'][s] == ref['labels'][s]
+        ms = (ref['matching_scores0'][s] - 0.2).abs() > 1e-2
+        mt = out['matches0'][s] == ref['matches0'][s]
+        r.update({'label_agreement': float(lab.float().mean()), 'decisive_label_agreement': float(lab[dec].float().mean()),
+                  'logit_maxdiff': float((out['prediction'][s] - ref['prediction'][s]).abs().max()),
+                  'descriptor_maxdiff': float((out['descriptors'][s] - ref['descriptors'][s]).abs().max()),
+                  'match_agreement': float(mt.float().mean()), 'decisive_match_agreement': float(mt[ms].float().mean()),
+                  'mscore_maxdiff': float((out['matching_scores0'][s] - ref['matching_scores0'][s]).abs().max())})
+    errs = [BD.pose_error(out['qvec'][i].cpu().numpy(), out['tvec'][i].cpu().numpy(), BD.rotmat_to_quat(smap.R[i].double().cpu().numpy()),
+                          smap.t[i].double().cpu().numpy()) for i in range(B)]
+    r.update({'pose_rot_err_deg_max': max(e[0] for e in errs), 'pose_t_err_m_max': max(e[1] for e in errs),
+              'median_inliers': float(out['num_inliers'].float().median()), 'matched_fraction': float((out['matches0'] > -1).float().mean())})
+    rows.append(r)
+    print(json.dumps(r), flush=True)
+    del pipe
+if len(sys.argv) > 1:
+    Path(sys.argv[1]).write_text(json.dumps({'workload': '640x480, K=1024, 32 frames, shipped SFD2+GML, seeded SegNetViT', 'rows': rows}, indent=1))
