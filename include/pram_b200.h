@@ -133,7 +133,10 @@ int pram_attention_f32(const float* Q, const float* K, const float* V, int B, in
 long long pram_sinkhorn_workspace_floats(int B, int M, int N);
 int pram_sinkhorn_match(const float* dist, int B, int M, int N, const float* bin_score, int iters,
                         float threshold, float* pws, int* iws, float* fws, long long* matches0,
-                        long long* matches1, float* mscores0, float* mscores1, int cluster, pram_stream_t stream);
+                        long long* matches1, float* mscores0, float* mscores1, int cluster,
+                        const int* m_counts, const int* n_counts /* optional [B]: pair b is the (m_counts[b]+1) x (n_counts[b]+1)
+                        problem of its first rows / columns; the rest of the [M, N] block is padding (matches -1, scores 0) */,
+                        pram_stream_t stream);
 
 /* K1-K4, K10-K14 (tensor-core path): tcgen05 implicit GEMM, TMA-fed, accumulators in TMEM.
  *   D[pixel][n] = sum_{tap,c} A[pixel + offset(tap)][c] * W[tap][n][c]  (+bias)(+res)(ReLU)(L2 norm)
@@ -199,7 +202,9 @@ int pram_mlp_block_tc(const pram_mlp_block_args* args, pram_stream_t stream);
  * nets/gml.py:175-181. */
 int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
                       const void* vt_lo, int B, int heads, int Nq, int Nk, int nk_pad, float scale, float* out_f32,
-                      void* out_hi, void* out_lo, int out_ld, int split, int kv_tile /* 0 = auto, 64 (two CTAs per SM) or 128 */, int v_mn, pram_stream_t stream);
+                      void* out_hi, void* out_lo, int out_ld, int split, int kv_tile /* 0 = auto, 64 (two CTAs per SM) or 128 */, int v_mn,
+                      const int* nk_counts /* optional [B]: keys >= nk_counts[b] of batch element b are padding and masked */,
+                      pram_stream_t stream);
 
 /* qkv fp32 rows -> the attention kernel's operands (rotary + scale on q,k; V transposed per head).
  * nets/segnetvit.py:98-103, nets/gml.py:169-174. */

@@ -41,7 +41,7 @@ SIGNATURES = {
     'pram_rotary_split': (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P, _P]),
     'pram_attention_f32': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _P, _P]),
     'pram_sinkhorn_workspace_floats': (_L, [_I, _I, _I]),
-    'pram_sinkhorn_match': (_I, [_P, _I, _I, _I, _P, _I, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    'pram_sinkhorn_match': (_I, [_P, _I, _I, _I, _P, _I, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
 }
 
 
@@ -86,7 +86,7 @@ class MlpBlockArgs(C.Structure):
 SIGNATURES['pram_mlp_block_tc'] = (_I, [C.POINTER(MlpBlockArgs), _P])
 SIGNATURES['pram_split_bf16'] = (_I, [_P, _P, _P, _L, _P])
 SIGNATURES['pram_cast_f16'] = (_I, [_P, _P, _L, _P])
-SIGNATURES['pram_attention_tc'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I, _I, _I, _I, _P])
+SIGNATURES['pram_attention_tc'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I, _I, _I, _I, _P, _P])
 SIGNATURES['pram_attention_prep'] = (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P, _I, _P])
 _D = C.c_double
 SIGNATURES['pram_ransac_workspace_bytes'] = (_L, [_I, _I, _I])

@@ -43,6 +43,7 @@ struct Args {
     float scale_log2;  // softmax scale * log2(e)
     float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_ld;
     int v_mn;          // 1: V given as [BH][Nk][64] (MN-major B operand), 0: V^T [BH][64][nk_pad] (K-major)
+    const int* nk_counts;  // optional [B]: valid keys of batch element b (keys >= nk_counts[b] are padding and masked)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -356,11 +357,14 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
         uint32_t g = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x) {
             const int bh = item / q_tiles, q0 = (item % q_tiles) * BQ;
+            // keys of this batch element that are real tokens: the fixed [B, K] layout of the batched pipeline pads
+            // frames with fewer keypoints; a padded key must not receive attention (the reference runs n[b] tokens)
+            const int nk_b = p.nk_counts ? max(1, min(p.Nk, __ldg(p.nk_counts + bh / p.heads))) : p.Nk;
             float m_used = -INFINITY, l = 0.f;  // l: this thread's partial row sum (its 32 columns)
             for (int j = 0; j < kv_tiles; ++j, ++g) {
                 const int st = g & 1;
                 const uint32_t s_addr = tmem_base + lane_off + (st ? COL_S1 : COL_S0) + part * CPT;
-                const int nvalid = min(BKV, p.Nk - j * BKV) - part * CPT;  // valid columns of this part (may be <= 0)
+                const int nvalid = min(BKV, nk_b - j * BKV) - part * CPT;  // valid columns of this part (may be <= 0)
                 mbar_wait(&s_full[st], (g >> 1) & 1);
                 tc_fence_after();
                 uint32_t v0[32];
@@ -530,7 +534,7 @@ static int encode3(CUtensorMap* m, const void* base, cuuint64_t d0, cuuint64_t d
 PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
                                const void* vt_lo, int B, int heads, int Nq, int Nk, int nk_pad, float scale,
                                float* out_f32, void* out_hi, void* out_lo, int out_ld, int split, int p_swap,
-                               int v_mn, cudaStream_t stream) {
+                               int v_mn, const int* nk_counts, cudaStream_t stream) {
     using namespace fa;
     if (!q_hi || !k_hi || !vt_hi || B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return PRAM_ERR_ARG;
     if (split != 1 && split != 3) return PRAM_ERR_ARG;
@@ -564,6 +568,7 @@ PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k
     a.scale_log2 = scale * 1.4426950408889634f;
     a.out_f32 = out_f32; a.out_hi = (__nv_bfloat16*)out_hi; a.out_lo = (__nv_bfloat16*)out_lo; a.out_ld = out_ld;
     a.v_mn = v_mn;
+    a.nk_counts = nk_counts;
     const int total = BH * ((Nq + BQ - 1) / BQ);
 #define PRAM_ATT_LAUNCH(SPLIT_, BKV_)                                                                                   \
     do {                                                                                                                \

@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
     const float* __restrict__ dist, int M, int N, const float* __restrict__ bin_ptr, int iters,
     float th, float* __restrict__ pws, int ldp, long long* __restrict__ matches0,
     long long* __restrict__ matches1, float* __restrict__ mscores0, float* __restrict__ mscores1,
-    int* __restrict__ idx0_ws, int* __restrict__ idx1_ws, float* __restrict__ max0_ws, int G) {
+    int* __restrict__ idx0_ws, int* __restrict__ idx1_ws, float* __restrict__ max0_ws, int G,
+    const int* __restrict__ m_counts, const int* __restrict__ n_counts) {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) float smem[];
     const int NC = N + 1, MR = M + 1;
@@ -40,6 +41,12 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
     const float* D = dist + (long long)b * M * N;
     float* P = pws + (long long)b * MR * ldp;
     const float eps = 1e-8f;
+    // per-pair problem size inside the padded [M, N] block (the batched pipeline pads frames with fewer keypoints): rows
+    // mb..M-1 and columns nb..N-1 are absent; the dustbin row / column stay at index M / N of the padded layout
+    const int mb = m_counts ? max(1, min(M, m_counts[b])) : M;
+    const int nb = n_counts ? max(1, min(N, n_counts[b])) : N;
+    auto row_ok = [&](int i) { return i < mb || i == M; };
+    auto col_ok = [&](int j) { return j < nb || j == N; };
 
     // ---- phase 0: p = softmax over each augmented row ----
     for (int i = r0 + warp; i < r1; i += WARPS) {
@@ -51,7 +58,7 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
             for (int q = 0; q < 4; ++q) {
                 int j = k * 128 + lane * 4 + q;
                 float val = -INFINITY;
-                if (j < NC) val = (i < M && j < N) ? D[(long long)i * N + j] : bin;
+                if (j < NC && col_ok(j) && row_ok(i)) val = (i < M && j < N) ? D[(long long)i * N + j] : bin;
                 z[k * 4 + q] = val;
                 mx = fmaxf(mx, val);
             }
@@ -63,6 +70,7 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
             sum += z[k];
         }
         sum = warp_sum(sum);
+        if (!row_ok(i)) sum = 1.f;  // absent row: all zeros
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             int j = k * 128 + lane * 4;
@@ -71,7 +79,7 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
                     make_float4(z[k * 4] / sum, z[k * 4 + 1] / sum, z[k * 4 + 2] / sum, z[k * 4 + 3] / sum);
         }
     }
-    for (int j = threadIdx.x; j < ldp; j += WARPS * 32) v_s[j] = (j < NC) ? 1.f : 0.f;
+    for (int j = threadIdx.x; j < ldp; j += WARPS * 32) v_s[j] = (j < NC && col_ok(j)) ? 1.f : 0.f;
     __syncthreads();
 
     const int chunk = (ldp / 4 + G - 1) / G * 4;  // columns reduced by each rank (multiple of 4)
@@ -113,8 +121,8 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
                 }
             }
             s = warp_sum(s);
-            const float ri = (i == M) ? (float)MR : 1.f;
-            const float ui = ri / (s + eps);
+            const float ri = (i == M) ? (float)(mb + 1) : 1.f;
+            const float ui = row_ok(i) ? ri / (s + eps) : 0.f;
             if (lane == 0) u_s[i - r0] = ui;
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
@@ -152,8 +160,8 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
             for (int j = c0 + threadIdx.x; j < c1; j += WARPS * 32) {
                 float s = 0.f;
                 for (int g = 0; g < G; ++g) s += cluster.map_shared_rank(col_s, g)[j];
-                const float cj = (j == N) ? (float)NC : 1.f;
-                const float vj = (j < NC) ? cj / (s + eps) : 0.f;
+                const float cj = (j == N) ? (float)(nb + 1) : 1.f;
+                const float vj = (j < NC && col_ok(j)) ? cj / (s + eps) : 0.f;
                 for (int g = 0; g < G; ++g) cluster.map_shared_rank(v_s, g)[j] = vj;
             }
         }
@@ -174,10 +182,10 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
                 pv.x = (pv.x * ui) * vv.x; pv.y = (pv.y * ui) * vv.y;
                 pv.z = (pv.z * ui) * vv.z; pv.w = (pv.w * ui) * vv.w;
                 *reinterpret_cast<float4*>(P + (long long)i * ldp + j) = pv;
-                if (j < N && pv.x > best) { best = pv.x; bj = j; }
-                if (j + 1 < N && pv.y > best) { best = pv.y; bj = j + 1; }
-                if (j + 2 < N && pv.z > best) { best = pv.z; bj = j + 2; }
-                if (j + 3 < N && pv.w > best) { best = pv.w; bj = j + 3; }
+                if (j < nb && pv.x > best) { best = pv.x; bj = j; }
+                if (j + 1 < nb && pv.y > best) { best = pv.y; bj = j + 1; }
+                if (j + 2 < nb && pv.z > best) { best = pv.z; bj = j + 2; }
+                if (j + 3 < nb && pv.w > best) { best = pv.w; bj = j + 3; }
             }
         }
         // warp arg-max, first index wins ties
@@ -198,7 +206,7 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
         for (int j = c0 + threadIdx.x; j < c1; j += WARPS * 32) {
             float best = -1.f;
             int bi = 0;
-            for (int i = 0; i < M; ++i) {
+            for (int i = 0; i < mb; ++i) {
                 float pv = P[(long long)i * ldp + j];
                 if (pv > best) { best = pv; bi = i; }
             }
@@ -214,16 +222,16 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
     const int gthreads = G * WARPS * 32, gtid = rank * WARPS * 32 + threadIdx.x;
     for (int i = gtid; i < M; i += gthreads) {
         const int j = i0[i];
-        const bool mutual = (i1[j] == i);
+        const bool mutual = (i < mb) && (j < nb) && (i1[j] == i);
         const float s0 = mutual ? m0[i] : 0.f;
         matches0[(long long)b * M + i] = (mutual && s0 > th) ? (long long)j : -1ll;
         mscores0[(long long)b * M + i] = s0;
     }
     for (int j = gtid; j < N; j += gthreads) {
         const int i = i1[j];
-        const bool mutual1 = (i0[i] == j);
+        const bool mutual1 = (j < nb) && (i < mb) && (i0[i] == j);
         // mscores0[i] recomputed locally: s0_i = (i1[i0[i]] == i) ? max0[i] : 0
-        const bool mutual0_i = (i1[i0[i]] == i);
+        const bool mutual0_i = (i < mb) && (i0[i] < nb) && (i1[i0[i]] == i);
         const float s0_i = mutual0_i ? m0[i] : 0.f;
         const bool valid0_i = mutual0_i && s0_i > th;
         if (matches1) matches1[(long long)b * N + j] = (mutual1 && valid0_i) ? (long long)i : -1ll;
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
 template <int NV, int WARPS>
 static int launch_sinkhorn(const float* dist, int B, int M, int N, const float* bin, int iters, float th,
                            float* pws, int ldp, long long* m0, long long* m1, float* s0, float* s1,
-                           int* idx0, int* idx1, float* max0, int G, cudaStream_t stream) {
+                           int* idx0, int* idx1, float* max0, int G, const int* mc, const int* nc, cudaStream_t stream) {
     auto kern = sinkhorn_match_kernel<NV, WARPS>;
     const int rows_per = (M + 1 + G - 1) / G;
     size_t smem = sizeof(float) * (2 * (size_t)ldp + rows_per);
@@ -252,7 +260,7 @@ static int launch_sinkhorn(const float* dist, int B, int M, int N, const float* 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     PRAM_CUDA(cudaLaunchKernelEx(&cfg, kern, dist, M, N, bin, iters, th, pws, ldp, m0, m1, s0, s1, idx0,
-                                 idx1, max0, G));
+                                 idx1, max0, G, mc, nc));
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
 }
@@ -267,7 +275,7 @@ PRAM_API long long pram_sinkhorn_workspace_floats(int B, int M, int N) {
 PRAM_API int pram_sinkhorn_match(const float* dist, int B, int M, int N, const float* bin_score, int iters,
                                  float threshold, float* pws, int* iws, float* fws, long long* matches0,
                                  long long* matches1, float* mscores0, float* mscores1, int cluster,
-                                 cudaStream_t stream) {
+                                 const int* m_counts, const int* n_counts, cudaStream_t stream) {
     if (!dist || !bin_score || !pws || !iws || !fws || !matches0 || !mscores0 || B <= 0 || M <= 0 || N <= 0)
         return PRAM_ERR_ARG;
     int G = cluster;
@@ -286,12 +294,12 @@ PRAM_API int pram_sinkhorn_match(const float* dist, int B, int M, int N, const f
     const int nv = (ldp + 127) / 128;
     if (nv <= 9)
         return launch_sinkhorn<9, 16>(dist, B, M, N, bin_score, iters, threshold, pws, ldp, matches0, matches1,
-                                      mscores0, mscores1, idx0, idx1, fws, G, stream);
+                                      mscores0, mscores1, idx0, idx1, fws, G, m_counts, n_counts, stream);
     if (nv <= 17)
         return launch_sinkhorn<17, 8>(dist, B, M, N, bin_score, iters, threshold, pws, ldp, matches0, matches1,
-                                       mscores0, mscores1, idx0, idx1, fws, G, stream);
+                                       mscores0, mscores1, idx0, idx1, fws, G, m_counts, n_counts, stream);
     if (nv <= 33)
         return launch_sinkhorn<33, 8>(dist, B, M, N, bin_score, iters, threshold, pws, ldp, matches0, matches1,
-                                      mscores0, mscores1, idx0, idx1, fws, G, stream);
+                                      mscores0, mscores1, idx0, idx1, fws, G, m_counts, n_counts, stream);
     return PRAM_ERR_UNSUPPORTED;
 }

@@ -208,13 +208,23 @@ def _finish_block(ws: Workspace, pk: Dict[str, torch.Tensor]):
     ws.cur ^= 1
 
 
+def _no_counts_here(counts):
+    if counts is not None and any(c is not None for c in counts):
+        from .. import _lib
+        raise _lib.PramError('per-frame keypoint counts (padded batches) are only supported on the tensor-core attention path')
+
+
 def self_block(ws: Workspace, pk: Dict[str, torch.Tensor], segments: Sequence[Tuple[int, int, int]],
-               cos: torch.Tensor, sin: torch.Tensor, colmeans: Optional[List[torch.Tensor]] = None):
+               cos: torch.Tensor, sin: torch.Tensor, colmeans: Optional[List[torch.Tensor]] = None,
+               counts: Optional[Sequence[Optional[torch.Tensor]]] = None):
     """One SelfMultiHeadAttention block over all tokens.  ``segments`` = [(token_offset, B, N), ...]:
-    attention is computed independently inside each (segment, batch element).
+    attention is computed independently inside each (segment, batch element).  ``counts[s]`` (optional, [B] int32 per
+    segment): tokens >= counts[s][b] of batch element b are padding and receive no attention.
     Reference nets/segnetvit.py:97-106 == nets/gml.py:128-137."""
     T = ws.T
     use_tc = bool(ws.split) and colmeans is None
+    if not use_tc:
+        _no_counts_here(counts)
     ws.ctx_in_bf = use_tc
     if use_tc:
         # qkv GEMM with the fused epilogue: bias, rotary on q/k, split-bf16 Q/K/V in [B, heads, n, 64]
@@ -223,9 +233,10 @@ def self_block(ws: Workspace, pk: Dict[str, torch.Tensor], segments: Sequence[Tu
                'seg_split': seg_split, 'seg_n0': segments[0][2], 'seg_n1': segments[-1][2]}
         ops.linear_tc(ws.x_bf, 2 * D, T, D, pk['qkv.tc'], 3 * D, pk['qkv.b'], split=ws.split, bn=256, qkv=qkv)
         ctx, ctx_ld = ws.ctx_out()
-        for off, b, n in segments:
+        for si, (off, b, n) in enumerate(segments):
             ops.attention_tc(ops.split_rows(ws.q_bf, off), ops.split_rows(ws.k_bf, off), ops.split_rows(ws.v_bf, off), b, HEADS,
-                             n, n, n, HDIM ** -0.5, None, ops.split_rows(ctx, off), ctx_ld, ws.split, v_mn=True)
+                             n, n, n, HDIM ** -0.5, None, ops.split_rows(ctx, off), ctx_ld, ws.split, v_mn=True,
+                             nk_counts=None if counts is None else counts[si])
         _finish_block(ws, pk)
         return
     linear(ws, ws.x, ws.x_bf if ws.split else None, 2 * D, T, D, 3 * D, pk, 'qkv', out_f32=ws.qkv, ld_f32=3 * D)
@@ -238,7 +249,7 @@ def self_block(ws: Workspace, pk: Dict[str, torch.Tensor], segments: Sequence[Tu
 
 
 def cross_block(ws: Workspace, pk: Dict[str, torch.Tensor], seg0: Tuple[int, int, int], seg1: Tuple[int, int, int],
-                colmeans: Optional[List[torch.Tensor]] = None):
+                colmeans: Optional[List[torch.Tensor]] = None, counts: Optional[Sequence[Optional[torch.Tensor]]] = None):
     """Bidirectional cross attention between segment 0 (B x M tokens) and segment 1 (B x N tokens) with
     the shared qk projection; both directions reuse the same flash kernel (row softmax of sim and of
     sim^T).  Reference nets/gml.py:164-186.  ``colmeans`` = [mean attn10 over queries -> per token of
@@ -249,14 +260,17 @@ def cross_block(ws: Workspace, pk: Dict[str, torch.Tensor], seg0: Tuple[int, int
     sc = (HDIM ** -0.5) ** 0.5  # applied to both qk0 and qk1 (nets/gml.py:174)
     use_tc = bool(ws.split) and colmeans is None
     ws.ctx_in_bf = use_tc
+    if not use_tc:
+        _no_counts_here(counts)
+    c0, c1 = (None, None) if counts is None else counts
     if use_tc:
         fused = {'mode': 2, 'scale': sc, 'q': ws.q_bf, 'v': ws.v_bf, 'seg_split': o1, 'seg_n0': m, 'seg_n1': n}
         ops.linear_tc(ws.x_bf, 2 * D, T, D, pk['qkv.tc'], 2 * D, pk['qkv.b'], split=ws.split, bn=256, qkv=fused)
         q0, q1 = ops.split_rows(ws.q_bf, o0), ops.split_rows(ws.q_bf, o1)
         v0, v1 = ops.split_rows(ws.v_bf, o0), ops.split_rows(ws.v_bf, o1)
         ctx, ctx_ld = ws.ctx_out()
-        ops.attention_tc(q0, q1, v1, b, HEADS, m, n, n, 1.0, None, ops.split_rows(ctx, o0), ctx_ld, ws.split, v_mn=True)
-        ops.attention_tc(q1, q0, v0, b, HEADS, n, m, m, 1.0, None, ops.split_rows(ctx, o1), ctx_ld, ws.split, v_mn=True)
+        ops.attention_tc(q0, q1, v1, b, HEADS, m, n, n, 1.0, None, ops.split_rows(ctx, o0), ctx_ld, ws.split, v_mn=True, nk_counts=c1)
+        ops.attention_tc(q1, q0, v0, b, HEADS, n, m, m, 1.0, None, ops.split_rows(ctx, o1), ctx_ld, ws.split, v_mn=True, nk_counts=c0)
         _finish_block(ws, pk)
         return
     qkv = ws.qkv.view(-1)[:T * 2 * D].view(T, 2 * D)  # (qk | v) rows, 512 wide

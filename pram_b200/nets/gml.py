@@ -120,6 +120,15 @@ class GML(nn.Module):
         return torch.cat([c0, c1], 0), torch.cat([s0, s1], 0)
 
     @staticmethod
+    def _counts(c, b: int, device):
+        if c is None:
+            return None
+        c = torch.as_tensor(c, device=device).to(torch.int32).reshape(-1).contiguous()
+        if c.numel() != b:
+            raise ValueError(f'num_keypoints must have one entry per batch element ({b}), got {c.numel()}')
+        return c
+
+    @staticmethod
     def _input_tokens(pk, ws, d0, d1):
         b, m, dd = d0.shape
         n = d1.shape[1]
@@ -156,9 +165,14 @@ class GML(nn.Module):
         ws = B.Workspace(b * (m + n), d0.device, self._split)
         self._input_tokens(pk, ws, d0, d1)
         seg0, seg1 = (0, b, m), (b * m, b, n)
+        # padded batches (extension of the reference dict, which has no batch-with-padding notion: its callers run one pair
+        # per call): ``num_keypoints0/1`` [B] = real keypoints of each set; the rest of the [B, M|N] slots are padding that
+        # takes no part in attention or in the Sinkhorn normalisation and comes back unmatched
+        cnt = [self._counts(data.get('num_keypoints0'), b, d0.device), self._counts(data.get('num_keypoints1'), b, d0.device)]
+        counts = cnt if (cnt[0] is not None or cnt[1] is not None) else None
         for i in range(self.n_layers):
-            B.self_block(ws, pk['self'][i], (seg0, seg1), cos, sin)
-            B.cross_block(ws, pk['cross'][i], seg0, seg1)
+            B.self_block(ws, pk['self'][i], (seg0, seg1), cos, sin, counts=counts)
+            B.cross_block(ws, pk['cross'][i], seg0, seg1, counts=counts)
         dist = self._distance(pk, self.n_layers - 1, ws, b, m, n)
-        m0, m1, s0, s1 = ops.sinkhorn_match(dist, pk['bin'], self.sinkhorn_iterations, p)
+        m0, m1, s0, s1 = ops.sinkhorn_match(dist, pk['bin'], self.sinkhorn_iterations, p, m_counts=cnt[0], n_counts=cnt[1])
         return {'matches0': m0, 'matches1': m1, 'matching_scores0': s0, 'matching_scores1': s1}

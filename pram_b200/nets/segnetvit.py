@@ -102,8 +102,15 @@ class SegNetViT(nn.Module):
         ws = B.Workspace(T, desc.device, split)
         B.input_tokens(ws, pk, desc.reshape(T, dd), 0)
         seg = [(0, b, n)]
+        # ``num_keypoints`` [B] (extension for padded batches): tokens >= num_keypoints[b] are padding and get no attention
+        cnt = data.get('num_keypoints')
+        counts = None
+        if cnt is not None:
+            counts = [torch.as_tensor(cnt, device=desc.device).to(torch.int32).reshape(-1).contiguous()]
+            if counts[0].numel() != b:
+                raise ValueError(f'num_keypoints must have one entry per batch element ({b})')
         for lp in pk['layers']:
-            B.self_block(ws, lp, seg, cos, sin)
+            B.self_block(ws, lp, seg, cos, sin, counts=counts)
         c = self.config
         out = torch.empty((b, n, c['n_class']), device=desc.device, dtype=torch.float32)
         B.head_mlp(ws, pk, 'seg', c['output_dim'], c['n_class'], out)

@@ -196,9 +196,11 @@ def attention_f32(q: Tensor, k: Tensor, v: Tensor, b: int, heads: int, nq: int, 
 # ---- K15 / K16 --------------------------------------------------------------------------------
 
 def sinkhorn_match(dist: Tensor, bin_score: Tensor, iters: int, threshold: float, cluster: int = 0,
-                   return_P: bool = False):
+                   return_P: bool = False, m_counts: Optional[Tensor] = None, n_counts: Optional[Tensor] = None):
     """dist [B,M,N] f32, bin_score 0-dim device tensor -> matches0 [B,M] i64, matches1 [B,N] i64,
-    mscores0 [B,M], mscores1 [B,N] (+ P [B,M+1,N+1]); reference nets/gml.py:27-46, 304-319."""
+    mscores0 [B,M], mscores1 [B,N] (+ P [B,M+1,N+1]); reference nets/gml.py:27-46, 304-319.
+    ``m_counts`` / ``n_counts`` [B] int32: pair b is the problem of its first m_counts[b] rows / n_counts[b] columns
+    (plus the dustbins); the rest of the block is padding."""
     _lib.require_cuda(dist, 'dist')
     dist = _f32c(dist)
     b, m, n = dist.shape
@@ -213,7 +215,7 @@ def sinkhorn_match(dist: Tensor, bin_score: Tensor, iters: int, threshold: float
     s1 = torch.empty((b, n), device=dev, dtype=torch.float32)
     bs = bin_score.detach().reshape(1).float().contiguous()
     call('pram_sinkhorn_match', ptr(dist), b, m, n, ptr(bs), int(iters), float(threshold), ptr(pws), ptr(iws),
-         ptr(fws), ptr(m0), ptr(m1), ptr(s0), ptr(s1), int(cluster), stream_ptr())
+         ptr(fws), ptr(m0), ptr(m1), ptr(s0), ptr(s1), int(cluster), ptr(m_counts), ptr(n_counts), stream_ptr())
     if return_P:
         return m0, m1, s0, s1, pws[:, :, :n + 1]
     return m0, m1, s0, s1
@@ -464,12 +466,14 @@ def attention_prep(qkv: Tensor, nparts: int, b: int, n: int, heads: int, cos: Op
 
 
 def attention_tc(q: Split, k: Split, vt: Split, b: int, heads: int, nq: int, nk: int, nk_pad: int, scale: float,
-                 out_f32: Optional[Tensor], out_bf: Optional[Split], out_ld: int, split: int, v_mn: bool = False):
-    """``vt`` is V^T [b*heads, 64, nk_pad] (v_mn=False) or V itself [b*heads, nk, 64] (v_mn=True)."""
+                 out_f32: Optional[Tensor], out_bf: Optional[Split], out_ld: int, split: int, v_mn: bool = False,
+                 nk_counts: Optional[Tensor] = None):
+    """``vt`` is V^T [b*heads, 64, nk_pad] (v_mn=False) or V itself [b*heads, nk, 64] (v_mn=True).  ``nk_counts`` [b] int32:
+    keys >= nk_counts[i] of batch element i are padding and receive no attention."""
     call('pram_attention_tc', ptr(q.hi), ptr(q.lo), ptr(k.hi), ptr(k.lo), ptr(vt.hi), ptr(vt.lo), b, heads, nq, nk, nk_pad,
          float(scale), ptr(out_f32), ptr(out_bf.hi) if out_bf is not None else None,
          ptr(out_bf.lo) if (out_bf is not None and out_bf.lo is not None) else None, out_ld, split, ATT_KV_TILE, int(v_mn),
-         stream_ptr())
+         ptr(nk_counts), stream_ptr())
 
 
 # ---- K19: batched PnP RANSAC -------------------------------------------------------------------------

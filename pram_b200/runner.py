@@ -29,6 +29,7 @@ class SyntheticMap:
     outlier: torch.Tensor      # [B,N] bool
     R: torch.Tensor            # [B,3,3]
     t: torch.Tensor            # [B,3]
+    num: Optional[torch.Tensor] = None   # [B] int32: real reference keypoints per set (the rest of the N slots is padding)
 
 
 class LocalizationPipeline:
@@ -63,6 +64,7 @@ class LocalizationPipeline:
     def recognize(self, f: Dict[str, torch.Tensor], image_shape) -> torch.Tensor:
         """-> landmark logits [B,K,n_class] (reference loc_by_rec_online.py:130)."""
         return self.segnet({'seg_descriptors': f['seg_descriptors'], 'keypoints': f['keypoints'],
+                            'num_keypoints': f['num_keypoints'],   # padded slots of the [B, K] layout get no attention
                             'image': torch.empty(image_shape, device='meta')})['prediction']
 
     def match(self, f: Dict[str, torch.Tensor], smap: SyntheticMap, image_shape) -> Dict[str, torch.Tensor]:
@@ -73,17 +75,13 @@ class LocalizationPipeline:
         d0, k0 = f['descriptors'], f['keypoints']
         if self.L > 1:  # pair (frame b, landmark l) = row b * L + l of the reference set
             d0, k0 = d0.repeat_interleave(self.L, 0), k0.repeat_interleave(self.L, 0)
-        m = self.matcher({'descriptors0': d0, 'keypoints0': k0,
-                          'descriptors1': smap.descriptors, 'keypoints1': smap.keypoints,
-                          'image_shape0': shp, 'image_shape1': shp})
-        # slots j >= num_keypoints[b] of the fixed [B, K] layout are padding (keypoint (0,0), zero descriptor): they must
-        # never reach PnP as correspondences.  (They still take part in attention / Sinkhorn as tokens -- see DESIGN.md
-        # "padded slots"; the benched frames always fill the budget, which bench.py asserts.)
+        # slots j >= num_keypoints[b] of the fixed [B, K] layout are padding (keypoint (0,0), zero descriptor): the counts
+        # travel with the batch, so padding gets no attention, is not part of the Sinkhorn problem and comes back unmatched
+        # -- every frame is matched exactly as if it were run alone with its n[b] keypoints, like the reference does
         nk = f['num_keypoints'] if self.L == 1 else f['num_keypoints'].repeat_interleave(self.L, 0)
-        pad = torch.arange(f['keypoints'].shape[1], device=self.dev)[None] >= nk[:, None]
-        m['matches0'] = m['matches0'].masked_fill(pad, -1)
-        m['matching_scores0'] = m['matching_scores0'].masked_fill(pad, 0.0)
-        return m
+        return self.matcher({'descriptors0': d0, 'keypoints0': k0, 'num_keypoints0': nk,
+                             'descriptors1': smap.descriptors, 'keypoints1': smap.keypoints, 'num_keypoints1': smap.num,
+                             'image_shape0': shp, 'image_shape1': shp})
 
     def _recognition(self, f: Dict[str, torch.Tensor], shape, out: Dict[str, torch.Tensor]):
         out['prediction'] = self.recognize(f, shape)
@@ -91,7 +89,8 @@ class LocalizationPipeline:
         # recognition -> matching glue (reference frame.py:96-121, multimap3d.py:348-379), kept on the device
         b, k, c = out['prediction'].shape
         bg, sid, non_bg = ops.segmentation(out['prediction'].reshape(b * k, c), self.pre_filtering_th)
-        out['seg_ids'], out['non_bg'] = sid.view(b, k), non_bg.view(b, k)
+        valid = torch.arange(k, device=self.dev)[None] < f['num_keypoints'][:, None]     # padded slots vote for no landmark
+        out['seg_ids'], out['non_bg'] = sid.view(b, k), non_bg.view(b, k) & valid
         out['landmarks'] = ops.rank_landmarks(out['prediction'], out['non_bg'], self.seg_k, max_ranks=8)
 
     def localize(self, images: torch.Tensor, smap: Optional[SyntheticMap] = None) -> Dict[str, torch.Tensor]:
@@ -208,14 +207,24 @@ class LocalizationPipeline:
         ``ref_keypoints`` of it when given: BASELINE.json configs[4] matches 4096 query keypoints against 1024 reference
         keypoints per landmark), lifted to 3-D with a known pose, ``outlier_frac`` replaced by outliers."""
         f = self.features(images)
+        nkp = f['num_keypoints'].repeat_interleave(self.L, 0).cpu()
         f = {'keypoints': f['keypoints'].repeat_interleave(self.L, 0), 'descriptors': f['descriptors'].repeat_interleave(self.L, 0)}
         b, k, _ = f['keypoints'].shape
         nb = b // self.L
         g = torch.Generator(device='cpu').manual_seed(seed)
-        perm = torch.stack([torch.randperm(k, generator=g) for _ in range(b)]).to(self.dev)
+        perms = []
+        for i in range(b):
+            pm = torch.randperm(k, generator=g)
+            n_i = int(nkp[i])
+            if n_i < k:  # frame with fewer keypoints than slots: its real keypoints first (same relative order), padding last
+                pm = torch.cat([pm[pm < n_i], pm[pm >= n_i]])
+            perms.append(pm)
+        perm = torch.stack(perms).to(self.dev)
+        num = nkp.clamp(max=k).to(torch.int32)
         if ref_keypoints is not None and ref_keypoints < k:
             perm = perm[:, :ref_keypoints].contiguous()
             k = ref_keypoints
+            num = num.clamp(max=k)
         kp = torch.gather(f['keypoints'], 1, perm[..., None].expand(-1, -1, 2))
         desc = torch.gather(f['descriptors'], 1, perm[..., None].expand(-1, -1, 128)).clone()
         # known pose per frame: small rotation (<= 15 deg) and translation (<= 0.5 m)
@@ -239,7 +248,7 @@ class LocalizationPipeline:
         rnd_xyz = (torch.rand(b, k, 3, generator=g) * 4 - 2).to(self.dev)
         desc = torch.where(outl[..., None], rnd_desc, desc)
         xyz = torch.where(outl[..., None], rnd_xyz, xyz)
-        return SyntheticMap(desc.contiguous(), kp.contiguous(), xyz.contiguous(), perm, outl, R, t)
+        return SyntheticMap(desc.contiguous(), kp.contiguous(), xyz.contiguous(), perm, outl, R, t, num.to(self.dev))
 
 
 # ---- frame sharding across ranks (one process per GPU) ---------------------------------------------------

@@ -294,3 +294,84 @@ def test_feature_matching_plugin(lib, dev, golden):
     ok = m >= 0
     assert ok.sum() > 50
     assert np.all(ids[m[ok]] != -1) and np.array_equal(perm[m[ok]], np.nonzero(ok)[0])
+
+
+def test_sinkhorn_per_pair_sizes_vs_oracle(ops, dev):
+    """Padded batch of Sinkhorn problems: pair b is the (m_b + 1) x (n_b + 1) problem of its first rows / columns.  Each
+    must equal the oracle run on the unpadded block alone; padding comes back unmatched with zero scores."""
+    g = torch.Generator().manual_seed(11)
+    B_, M, N = 3, 200, 160
+    dist = torch.randn(B_, M, N, generator=g) * 2
+    mc, nc = [200, 131, 77], [160, 160, 50]
+    for b in range(B_):
+        for i in range(min(mc[b], nc[b]) // 2):
+            dist[b, i, (i * 3) % nc[b]] += 15
+    bs = torch.tensor(0.7)
+    m0, m1, s0, s1, P = ops.sinkhorn_match(dist.to(dev), bs.to(dev), 20, 0.2, return_P=True,
+                                           m_counts=torch.tensor(mc, dtype=torch.int32, device=dev),
+                                           n_counts=torch.tensor(nc, dtype=torch.int32, device=dev))
+    for b in range(B_):
+        Pr = O.sinkhorn_with_dustbin(dist[b:b + 1, :mc[b], :nc[b]], bs, 20)
+        i0, i1, t0, t1 = O.compute_matches(Pr, 0.2)
+        Pb = P[b].cpu()
+        assert torch.allclose(Pb[:mc[b], :nc[b]], Pr[0, :-1, :-1], rtol=5e-4, atol=1e-7)
+        assert torch.allclose(Pb[M, :nc[b]], Pr[0, -1, :-1], rtol=5e-4, atol=1e-7) and torch.allclose(Pb[:mc[b], N], Pr[0, :-1, -1], rtol=5e-4, atol=1e-7)
+        assert (Pb[mc[b]:M] == 0).all() and (Pb[:, nc[b]:N] == 0).all()
+        dec = (t0[0] - 0.2).abs() > 1e-3
+        assert torch.equal(m0[b, :mc[b]].cpu()[dec], i0[0][dec]) and torch.allclose(s0[b, :mc[b]].cpu(), t0[0], rtol=5e-4, atol=1e-6)
+        assert (m0[b, mc[b]:] == -1).all() and (s0[b, mc[b]:] == 0).all() and (m1[b, nc[b]:] == -1).all()
+        assert (i0[0] > -1).sum() > 10
+
+
+@pytest.mark.skipif(RL.weight_path(RL.GML_WEIGHT) is None, reason='GML checkpoint not staged')
+def test_padded_gml_and_segnetvit_equal_unpadded_runs(lib, dev, golden):
+    """GML / SegNetViT on a padded batch with per-element keypoint counts == the same sets run alone without padding."""
+    from pram_b200.nets.gml import GML
+    from pram_b200.nets.segnetvit import SegNetViT
+    g0 = golden('gml_selfmatch.npz')
+    net = GML({})
+    net.load_state_dict(RL.load_gml_state(), strict=True)
+    net = net.to(dev)
+    d = torch.from_numpy(g0['descriptors0'])
+    k = torch.from_numpy(g0['keypoints0'])
+    perm = torch.from_numpy(g0['perm'])
+    n, n1 = d.shape[0], perm.shape[0]
+    sizes = [(n, n1), (n - 17, n1 - 40)]
+    Mp = Np = n + 9                                    # padded slot count
+    D0, D1, K0, K1 = torch.zeros(2, Mp, 128), torch.zeros(2, Np, 128), torch.zeros(2, Mp, 2), torch.zeros(2, Np, 2)
+    alone = []
+    for b, (m_, n_) in enumerate(sizes):
+        d0, k0, d1, k1 = d[:m_], k[:m_], d[perm][:n_], k[perm][:n_]
+        D0[b, :m_], K0[b, :m_], D1[b, :n_], K1[b, :n_] = d0, k0, d1, k1
+        alone.append(net({'descriptors0': d0[None].to(dev), 'keypoints0': k0[None].to(dev), 'descriptors1': d1[None].to(dev),
+                          'keypoints1': k1[None].to(dev), 'image_shape0': (1, 3, 160, 120), 'image_shape1': (1, 3, 160, 120)}))
+    out = net({'descriptors0': D0.to(dev), 'keypoints0': K0.to(dev), 'descriptors1': D1.to(dev), 'keypoints1': K1.to(dev),
+               'num_keypoints0': torch.tensor([s[0] for s in sizes]), 'num_keypoints1': torch.tensor([s[1] for s in sizes]),
+               'image_shape0': (1, 3, 160, 120), 'image_shape1': (1, 3, 160, 120)})
+    for b, (m_, n_) in enumerate(sizes):
+        a = alone[b]
+        assert torch.allclose(out['matching_scores0'][b, :m_], a['matching_scores0'][0], atol=2e-5)
+        dec = (a['matching_scores0'][0] - 0.2).abs() > 1e-3
+        assert torch.equal(out['matches0'][b, :m_][dec], a['matches0'][0][dec]) and (a['matches0'][0] > -1).sum() > 30
+        assert (out['matches0'][b, m_:] == -1).all() and (out['matches1'][b, n_:] == -1).all()
+    with pytest.raises(ValueError):
+        net({'descriptors0': D0.to(dev), 'keypoints0': K0.to(dev), 'descriptors1': D1.to(dev), 'keypoints1': K1.to(dev),
+             'num_keypoints0': torch.tensor([3]), 'image_shape0': (1, 3, 160, 120), 'image_shape1': (1, 3, 160, 120)})
+    # SegNetViT: logits of the real tokens are those of the unpadded run
+    gs = golden('segnetvit_seed0.npz')
+    sd = RL.random_segnetvit_state(int(gs['n_class']), seed=int(gs['seed']))
+    vit = SegNetViT({'n_class': int(gs['n_class']), 'n_layers': 15, 'output_dim': 1024, 'descriptor_dim': 256})
+    vit.load_state_dict(sd, strict=True)
+    vit = vit.to(dev)
+    shape = tuple(int(v) for v in gs['image_shape'])
+    x = torch.from_numpy(gs['seg_descriptors'])
+    kk = torch.from_numpy(gs['keypoints'])
+    n = x.shape[0]
+    X, KK = torch.zeros(2, n + 30, 256), torch.zeros(2, n + 30, 2)
+    X[0, :n], KK[0, :n], X[1, :n - 25], KK[1, :n - 25] = x, kk, x[:n - 25], kk[:n - 25]
+    img = torch.empty(shape, device='meta')
+    pad = vit({'seg_descriptors': X.to(dev), 'keypoints': KK.to(dev), 'num_keypoints': torch.tensor([n, n - 25]), 'image': img})['prediction']
+    a0 = vit({'seg_descriptors': x[None].to(dev), 'keypoints': kk[None].to(dev), 'image': img})['prediction']
+    a1 = vit({'seg_descriptors': x[None, :n - 25].to(dev), 'keypoints': kk[None, :n - 25].to(dev), 'image': img})['prediction']
+    assert torch.allclose(pad[0, :n], a0[0], atol=2e-5) and torch.allclose(pad[1, :n - 25], a1[0], atol=2e-5)
+    assert np.abs(a0[0].cpu().numpy() - gs['prediction']).max() < 5e-3

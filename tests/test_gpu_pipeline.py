@@ -67,8 +67,9 @@ def case(lib, dev):
     return {'pipe': pipe, 'sds': sds, 'frames': frames, 'fd': fd, 'smap': smap, 'out': out}
 
 
-def _check_frame_against_oracle(i, frames, out, smap, sds, report):
+def _check_frame_against_oracle(i, frames, out, smap, sds, report, dims=None):
     """Frame ``i`` of a pipeline result against the oracle; appends the measured deviations to ``report``."""
+    H, W, K, FOCAL = dims or (globals()['H'], globals()['W'], globals()['K'], globals()['FOCAL'])
     sd_sfd2, sd_vit, sd_gml = sds
     img = frames[i:i + 1]
     torch.set_num_threads(os.cpu_count() or 8)
@@ -103,8 +104,9 @@ def _check_frame_against_oracle(i, frames, out, smap, sds, report):
     with torch.no_grad():
         d0 = O.sample_map(kp, ref['desc_map'], 4, True).t()[None]
         dd = (out_desc(out, i, n) - d0[0]).abs().max().item() if 'descriptors' in out else None
+        nr = int(smap.num[i]) if smap.num is not None else smap.descriptors.shape[1]   # real reference keypoints (rest: padding)
         mr = O.gml_forward(sd_gml, {'descriptors0': d0, 'keypoints0': kp[None],
-                                    'descriptors1': smap.descriptors[i:i + 1].cpu(), 'keypoints1': smap.keypoints[i:i + 1].cpu(),
+                                    'descriptors1': smap.descriptors[i:i + 1, :nr].cpu(), 'keypoints1': smap.keypoints[i:i + 1, :nr].cpu(),
                                     'image_shape0': (1, 3, W, H), 'image_shape1': (1, 3, W, H)})
     s0 = out['matching_scores0'][i, :n].cpu()
     ds = (s0 - mr['matching_scores0'][0]).abs().max().item()
@@ -249,3 +251,43 @@ def test_pipeline_batch32_vs_oracle_and_batch4(case, dev):
     for i in (5, 17, 31):
         _check_frame_against_oracle(i, frames, out, smap, sds, report)
     _dump('pipeline_parity_b32.json', report)
+
+
+def test_padded_batch_equals_per_frame_reference(lib, dev):
+    """Frames with FEWER keypoints than the budget, batched in the fixed [B, K] layout (advisor finding of round 1: padded
+    slots took part in attention / Sinkhorn / PnP).  160x120 frames yield ~200-300 keypoints against K = 512, and a
+    different count per frame; with the counts threaded through attention (key masking), Sinkhorn (per-pair problem
+    size) and PnP, every frame must equal the oracle run on that frame alone with exactly its n[b] keypoints -- same
+    checker and tolerances as the full-budget test."""
+    Hs, Ws, Ks, Fs = 120, 160, 512, 150.0
+    from pram_b200.runner import LocalizationPipeline
+    pipe, sds = _build(dev)
+    pipe = LocalizationPipeline(pipe.sfd2, pipe.segnet, pipe.matcher, max_keypoints=Ks, focal=Fs, ransac_max_error=MAX_ERROR, device=dev)
+    pipe.cfg = {'min_keypoints': 32, 'max_keypoints': Ks}
+    frames = torch.cat([O.frame_tensor(Hs, Ws, seed=20 + i) for i in range(3)], 0)
+    fd = frames.to(dev)
+    with torch.no_grad():
+        smap = pipe.build_synthetic_map(fd, seed=1)
+        out = pipe.localize(fd, smap)
+    torch.cuda.synchronize()
+    n = out['num_keypoints'].cpu()
+    assert (n < Ks).all() and len(set(n.tolist())) > 1 and torch.equal(smap.num.cpu(), n)
+    for i in range(3):
+        ni = int(n[i])
+        assert (out['matches0'][i, ni:] == -1).all() and (out['matching_scores0'][i, ni:] == 0).all()
+        assert not out['inliers'][i, ni:].any() and not out['non_bg'][i, ni:].any()
+        assert (out['matches0'][i, :ni] < ni).all()          # nothing is matched to a padded reference slot
+    report = []
+    for i in range(3):
+        _check_frame_against_oracle_small(i, frames, out, smap, sds, report, (Hs, Ws, Ks, Fs))
+    _dump('pipeline_parity_padded.json', report)
+
+
+def _check_frame_against_oracle_small(i, frames, out, smap, sds, report, dims):
+    """Same checker; the oracle's selection uses min_keypoints = 32 like the pipeline of this test."""
+    orig = O.sfd2_extract_local_global
+    try:
+        O.sfd2_extract_local_global = lambda sd, img, cfg: orig(sd, img, {**cfg, 'min_keypoints': 32})
+        _check_frame_against_oracle(i, frames, out, smap, sds, report, dims)
+    finally:
+        O.sfd2_extract_local_global = orig
