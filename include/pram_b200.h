@@ -125,7 +125,11 @@ int pram_rotary_split(const float* qkv, int nparts, int B, int N, int heads, con
 /* K10/K12/K13: softmax(QK^T*scale)V without materialising the N x N matrix; optional per-key mean
  * attention (AdaGML).  nets/segnetvit.py:73-76, nets/gml.py:175-181, nets/adagml.py:148. */
 int pram_attention_f32(const float* Q, const float* K, const float* V, int B, int heads, int Nq, int Nk,
-                       float scale, float* out, int out_stride, float* colmean, pram_stream_t stream);
+                       float scale, float* out, int out_stride, float* colmean,
+                       float* colmean_ws /* pram_attention_f32_colmean_ws_floats() floats when colmean != NULL: per-CTA partials,
+                                            reduced in a fixed order (bit-reproducible pruning decisions in AdaGML) */,
+                       pram_stream_t stream);
+long long pram_attention_f32_colmean_ws_floats(int B, int heads, int Nq, int Nk);
 
 /* K15+K16: dustbin Sinkhorn (probability domain) + mutual arg-max matches in one launch.
  * nets/gml.py:27-46, 304-319.  pws: pram_sinkhorn_workspace_floats() floats (holds P on return),

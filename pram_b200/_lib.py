@@ -39,7 +39,8 @@ SIGNATURES = {
     'pram_l2norm_rows': (_I, [_P, _P, _L, _I, _P]),
     'pram_layernorm_gelu': (_I, [_P, _P, _P, _P, _L, _I, _I, _P]),
     'pram_rotary_split': (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P, _P]),
-    'pram_attention_f32': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _P, _P]),
+    'pram_attention_f32': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _P, _P, _P]),
+    'pram_attention_f32_colmean_ws_floats': (_L, [_I, _I, _I, _I]),
     'pram_sinkhorn_workspace_floats': (_L, [_I, _I, _I]),
     'pram_sinkhorn_match': (_I, [_P, _I, _I, _I, _P, _I, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
 }

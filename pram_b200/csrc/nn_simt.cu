@@ -546,7 +546,7 @@ PRAM_API int pram_rotary_split(const float* qkv, int nparts, int B, int N, int h
 constexpr int AT_BQ = 64, AT_BK = 32;
 __global__ void __launch_bounds__(256) attention_kernel(
     const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int B, int heads,
-    int Nq, int Nk, float scale, float* __restrict__ out, int out_stride, float* __restrict__ colmean) {
+    int Nq, int Nk, float scale, float* __restrict__ out, int out_stride, float* __restrict__ colmean /* partials */) {
     __shared__ float Ks[AT_BK][64 + 1];
     __shared__ float Vs[AT_BK][64 + 1];
     __shared__ float Ps[AT_BQ][AT_BK + 1];
@@ -622,8 +622,9 @@ __global__ void __launch_bounds__(256) attention_kernel(
         for (int d = 0; d < 16; ++d) o[d] = acc[d] * inv;
     }
     if (colmean) {
-        // second sweep: normalised attention weights, summed over this tile's queries and scaled by
-        // 1/(heads*Nq); accumulated over (head, query tile) with atomics.
+        // second sweep: normalised attention weights, summed over this tile's queries and scaled by 1/(heads*Nq), written
+        // as this CTA's partial row [bh][query tile][Nk]; colmean_reduce_kernel adds the partials of one batch element in a
+        // FIXED order (float atomics made AdaGML's pruning decisions near the confidence threshold irreproducible)
         const float inv = (qn < Nq) ? 1.f / l_run : 0.f;
         const float wscale = 1.f / ((float)heads * (float)Nq);
         for (int k0 = 0; k0 < Nk; k0 += AT_BK) {
@@ -647,20 +648,38 @@ __global__ void __launch_bounds__(256) attention_kernel(
             if (tid < AT_BK && k0 + tid < Nk) {
                 float cs = 0.f;
                 for (int r = 0; r < AT_BQ; ++r) cs += Ps[r][tid];
-                atomicAdd(&colmean[(long long)b * Nk + k0 + tid], cs * wscale);
+                colmean[((long long)bh * gridDim.x + blockIdx.x) * Nk + k0 + tid] = cs * wscale;
             }
         }
     }
 }
 
+__global__ void colmean_reduce_kernel(const float* __restrict__ parts, int B, int nparts /* heads * query tiles */, int Nk,
+                                      float* __restrict__ colmean) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * Nk) return;
+    const int b = (int)(i / Nk), k = (int)(i - (long long)b * Nk);
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += parts[((long long)b * nparts + p) * Nk + k];
+    colmean[i] = s;
+}
+
+PRAM_API long long pram_attention_f32_colmean_ws_floats(int B, int heads, int Nq, int Nk) {
+    return (long long)B * heads * cdiv(Nq, AT_BQ) * Nk;
+}
+
 PRAM_API int pram_attention_f32(const float* Q, const float* K, const float* V, int B, int heads, int Nq,
-                                int Nk, float scale, float* out, int out_stride, float* colmean,
+                                int Nk, float scale, float* out, int out_stride, float* colmean, float* colmean_ws,
                                 cudaStream_t stream) {
     if (!Q || !K || !V || !out || B <= 0 || Nq <= 0 || Nk <= 0) return PRAM_ERR_ARG;
-    if (colmean) PRAM_CUDA(cudaMemsetAsync(colmean, 0, sizeof(float) * (size_t)B * Nk, stream));
+    if (colmean && !colmean_ws) return PRAM_ERR_WORKSPACE;
     dim3 grid(cdiv(Nq, AT_BQ), B * heads);
-    attention_kernel<<<grid, 256, 0, stream>>>(Q, K, V, B, heads, Nq, Nk, scale, out, out_stride, colmean);
+    attention_kernel<<<grid, 256, 0, stream>>>(Q, K, V, B, heads, Nq, Nk, scale, out, out_stride, colmean ? colmean_ws : nullptr);
     PRAM_CHECK_LAUNCH();
+    if (colmean) {
+        colmean_reduce_kernel<<<cdiv((long long)B * Nk, 256), 256, 0, stream>>>(colmean_ws, B, heads * (int)grid.x, Nk, colmean);
+        PRAM_CHECK_LAUNCH();
+    }
     return PRAM_OK;
 }
 

@@ -189,8 +189,11 @@ def rotary_split(qkv: Tensor, nparts: int, b: int, n: int, heads: int, cos: Opti
 
 def attention_f32(q: Tensor, k: Tensor, v: Tensor, b: int, heads: int, nq: int, nk: int, scale: float, out: Tensor,
                   out_stride: int, colmean: Optional[Tensor] = None):
+    ws = None
+    if colmean is not None:
+        ws = torch.empty(int(_lib.load().pram_attention_f32_colmean_ws_floats(b, heads, nq, nk)), device=q.device, dtype=torch.float32)
     call('pram_attention_f32', ptr(q), ptr(k), ptr(v), b, heads, nq, nk, float(scale), ptr(out), out_stride,
-         ptr(colmean), stream_ptr())
+         ptr(colmean), ptr(ws), stream_ptr())
 
 
 # ---- K15 / K16 --------------------------------------------------------------------------------
