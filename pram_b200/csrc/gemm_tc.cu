@@ -427,18 +427,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
             // MODE 2: the rotary factors of a row depend on (token, dim pair) only -- not on the head -- and this
             // warp's chunks (c = half*32 + 64 m) all cover dims half*32..+31 of head m: ONE load per tile serves
             // all four chunks and is issued before the accumulator wait (latency hidden behind the MMA).
-            float2 rot_c[MODE == 2 ? 8 : 1], rot_s[MODE == 2 ? 8 : 1];
+            float4 rot_c[MODE == 2 ? 4 : 1], rot_s[MODE == 2 ? 4 : 1];
             if constexpr (MODE == 2) {
                 const bool rot = (p.qkv_mode == 1) && (nt != 2);
-                const int pr0 = (half * 32 + col1) >> 1;
+                const int pr0 = (half * 32 + col2) >> 1;   // 4 consecutive (even, odd) pairs of this lane's 8 columns
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int pixr = lds32(eq_pix + 4 * (i * 4 + g1));
-                    rot_c[i] = make_float2(1.f, 1.f);
-                    rot_s[i] = make_float2(0.f, 0.f);
+                for (int i = 0; i < 4; ++i) {
+                    const int pixr = lds32(eq_pix + 4 * (i * 8 + g2));
+                    rot_c[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    rot_s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (rot && pixr >= 0) {
-                        rot_c[i] = __ldg(reinterpret_cast<const float2*>(p.cosb + (long long)pixr * 32 + pr0));
-                        rot_s[i] = __ldg(reinterpret_cast<const float2*>(p.sinb + (long long)pixr * 32 + pr0));
+                        rot_c[i] = __ldg(reinterpret_cast<const float4*>(p.cosb + (long long)pixr * 32 + pr0));
+                        rot_s[i] = __ldg(reinterpret_cast<const float4*>(p.sinb + (long long)pixr * 32 + pr0));
                     }
                 }
             }
@@ -463,6 +463,70 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                 if (half == 0) sts32(eq_inv + 4 * lane, __float_as_int(fmaxf(sqrtf(ss), 1e-12f)));
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
             }
+            if constexpr (MODE == 2) {
+                // ---- dedicated qkv epilogue: ONE pass in the bf16 mapping (4 lanes per row, 8 columns per lane): bias, rotary on
+                // adjacent pairs, scale, hi / lo split, 16-byte stores into the [B][heads][n][64] operand tensors.  The generic
+                // two-pass loop below spends ~2000 SASS instructions per 32 x 32 chunk on runtime feature checks (ReLU, L2 norm,
+                // fp32 / row / phase-split outputs, ragged N) that never apply here; this path needs ~300 (ncu: the kernel was
+                // bound by the issue of its own epilogue, tensor pipe 30 %).  N is 768 or 512: every chunk is full.
+                const bool is_v = (p.qkv_mode == 1) ? (nt == 2) : (nt == 1);
+                const bool rot = (p.qkv_mode == 1) && !is_v;
+                __nv_bfloat16* qh = is_v ? p.v_hi : (nt == 0 ? p.q_hi : p.k_hi);
+                __nv_bfloat16* ql = is_v ? p.v_lo : (nt == 0 ? p.q_lo : p.k_lo);
+                const float sc = is_v ? 1.f : p.qk_scale;
+                for (int c = half * 32; c < BN; c += 64) {
+                    const int nb = n0 + c;
+                    {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + c, v);
+                        const uint32_t trow = tile_a + (uint32_t)lane * 128u;
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            sts128(trow + (uint32_t)((j4 ^ (lane & 7)) << 4), make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
+                                                                                  __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])));
+                    }
+                    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                    if (biasp) {
+                        b0 = __ldg(reinterpret_cast<const float4*>(biasp + nb + col2));
+                        b1 = __ldg(reinterpret_cast<const float4*>(biasp + nb + col2 + 4));
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = i * 8 + g2;
+                        const int pixr = lds32(eq_pix + 4 * row);
+                        const uint32_t tr = tile_a + (uint32_t)row * 128u;
+                        const float4 a = lds128(tr + (uint32_t)((((col2 >> 2)) ^ (row & 7)) << 4)), bq = lds128(tr + (uint32_t)((((col2 >> 2) + 1) ^ (row & 7)) << 4));
+                        float f[8] = {a.x + b0.x, a.y + b0.y, a.z + b0.z, a.w + b0.w, bq.x + b1.x, bq.y + b1.y, bq.z + b1.z, bq.w + b1.w};
+                        if (rot) {
+                            const float cs[4] = {rot_c[i].x, rot_c[i].y, rot_c[i].z, rot_c[i].w};
+                            const float sn[4] = {rot_s[i].x, rot_s[i].y, rot_s[i].z, rot_s[i].w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float e = f[2 * k], o = f[2 * k + 1];
+                                f[2 * k] = e * cs[k] + (-o) * sn[k];
+                                f[2 * k + 1] = o * cs[k] + e * sn[k];
+                            }
+                        }
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int k = 0; k < 8; k += 2) {
+                            const float x0 = f[k] * sc, x1 = f[k + 1] * sc;
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+                            const uint32_t u = *reinterpret_cast<uint32_t*>(&h2);
+                            __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - __uint_as_float(u << 16), x1 - __uint_as_float(u & 0xffff0000u));
+                            hi[k >> 1] = u;
+                            lo[k >> 1] = *reinterpret_cast<uint32_t*>(&l2);
+                        }
+                        if (pixr >= 0) {
+                            const long long qo = (long long)lds32(eq_ps + 4 * row) + (long long)(c >> 6) * lds32(eq_inv + 4 * row) + (c & 63) + col2;
+                            *reinterpret_cast<uint4*>(qh + qo) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            if (SPLIT == 3) *reinterpret_cast<uint4*>(ql + qo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        }
+                    }
+                    __syncwarp();
+                }
+            } else
             for (int c = half * 32; c < BN; c += 64) {
                 if (n0 + c >= p.N) break;  // warp-uniform
                 const int nb = n0 + c;
@@ -496,19 +560,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                         const float4 tv = lds128(tp);
                         float f[4] = {tv.x + bz[0], tv.y + bz[1], tv.z + bz[2], tv.w + bz[3]};
                         if constexpr (MODE == 1) { f[0] += rcur[i].x; f[1] += rcur[i].y; f[2] += rcur[i].z; f[3] += rcur[i].w; }
-                        if (MODE == 2 && pixr >= 0) {
-                            const bool is_v = (p.qkv_mode == 1) ? (nt == 2) : (nt == 1);
-                            if (!is_v) {
-                                if (p.qkv_mode == 1) {  // rotary on adjacent pairs (2i, 2i+1)
-                                    const float2 cs = rot_c[i], sn = rot_s[i];
-                                    const float a0 = f[0] * cs.x + (-f[1]) * sn.x, a1 = f[1] * cs.x + f[0] * sn.x;
-                                    const float a2 = f[2] * cs.y + (-f[3]) * sn.y, a3 = f[3] * cs.y + f[2] * sn.y;
-                                    f[0] = a0; f[1] = a1; f[2] = a2; f[3] = a3;
-                                }
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) f[k] *= p.qk_scale;
-                            }
-                        }
                         if (p.relu) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) f[k] = fmaxf(f[k], 0.f);
@@ -527,18 +578,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                                 for (int k = 0; k < 4; ++k) if (nb + col1 + k < p.N) op[k] = f[k];
                             }
                         }
-                        if (MODE == 2 || p.out_hi || p.ps_hi) sts128(tp, make_float4(f[0], f[1], f[2], f[3]));
+                        if (p.out_hi || p.ps_hi) sts128(tp, make_float4(f[0], f[1], f[2], f[3]));
                     }
                 }
                 // ---- pass 2 (bf16 mapping: 4 lanes per row): split into hi / lo planes, 16-byte stores ----
-                if (MODE == 2 || p.out_hi || p.ps_hi) {  // requires N % 32 == 0 (checked on the host)
+                if (p.out_hi || p.ps_hi) {  // requires N % 32 == 0 (checked on the host)
                     __syncwarp();
-                    __nv_bfloat16* qh = nullptr; __nv_bfloat16* ql = nullptr;
-                    if (MODE == 2) {  // BN == 256: the N tile index is the part (q | k | v) or (qk | v)
-                        const bool is_v = (p.qkv_mode == 1) ? (nt == 2) : (nt == 1);
-                        qh = is_v ? p.v_hi : (nt == 0 ? p.q_hi : p.k_hi);
-                        ql = is_v ? p.v_lo : (nt == 0 ? p.q_lo : p.k_lo);
-                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int row = i * 8 + g2;
@@ -563,11 +608,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                                 hi[k >> 1] = u;
                                 lo[k >> 1] = *reinterpret_cast<uint32_t*>(&l2);
                             }
-                        }
-                        if (MODE == 2 && pixr >= 0 && qh) {
-                            const long long qo = (long long)lds32(eq_ps + 4 * row) + (long long)(c >> 6) * lds32(eq_inv + 4 * row) + (c & 63) + col2;
-                            *reinterpret_cast<uint4*>(qh + qo) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            if (ql) *reinterpret_cast<uint4*>(ql + qo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
                         if (pixr >= 0) {
                             if (p.out_hi) {
