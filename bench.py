@@ -259,7 +259,7 @@ def run_ours(args):
     vit.load_state_dict(sd_vit, strict=True)
     gml = GML({}); gml.load_state_dict(sd_gml, strict=True)
     if args.precision == 'mixed':
-        sfd2.set_precision('bf16x3', 'f16'); vit.set_precision('bf16x3'); gml.set_precision('bf16x3')
+        sfd2.set_precision('bf16x3', 'f16'); vit.set_precision('bf16x3', 'f16'); gml.set_precision('bf16x3', 'f16')
     else:
         for m_ in (sfd2, vit, gml):
             m_.set_precision(args.precision)

@@ -30,6 +30,11 @@ unsigned long long pram_launch_count(void); /* kernels launched by this library 
 const char* pram_error_string(int code);
 const char* pram_last_cuda_error(void);
 
+/* Device-side early exit (AdaGML's stop test, nets/adagml.py:370-372 `break`): while `flag` (device int) is registered, the
+ * GEMM / attention / block-tail / Linear / LayerNorm / AdaGML-control kernels launched by this thread return immediately when
+ * *flag == 0 at execution time.  NULL clears it.  Host-side state only (no launch, no synchronisation). */
+int pram_set_launch_predicate(const int* flag);
+
 /* K5: softmax(65) -> drop dustbin -> 8x8 pixel shuffle.  nets/sfd2.py:294-300.
  * logits addressed as base + b*batch_stride + hc*y_stride + wc*x_stride + c*ch_stride (floats). */
 int pram_score_map(const float* logits, long long batch_stride, long long y_stride, long long x_stride,
@@ -174,6 +179,7 @@ typedef struct pram_tc_args {
     int l2_prefetch;                      /* 1 = L2-prefetch the next tile's activation boxes (single-tap layers); default off */
     int f16;                              /* 1 (split == 1): a / w planes hold IEEE fp16 and out_hi receives fp16 (single-pass fp16 mode) */
     const void* res_hi; const void* res_lo; /* residual as split-bf16 planes (when res == NULL): r = hi + lo, row stride res_ld */
+    int v_f16;                            /* qkv epilogue: v_hi / v_lo receive IEEE fp16 planes (V operand of pram_attention_tc with v_f16) */
 } pram_tc_args;
 int pram_gemm_tc(const pram_tc_args* args, pram_stream_t stream);
 
@@ -201,7 +207,9 @@ int pram_mlp_block_tc(const pram_mlp_block_args* args, pram_stream_t stream);
 /* K10/K12/K13 (tensor-core path): flash attention on tcgen05, head dim 64.  S = QK^T and O += PV on the
  * tensor cores (P is fed back from TMEM as the A operand), softmax on one thread per query row.
  * q/k: bf16 [B*heads][N][64]; vt: bf16 [B*heads][64][nk_pad] (keys contiguous) when v_mn == 0, or V itself
- * [B*heads][Nk][64] when v_mn == 1 (MN-major UMMA operand); *_lo NULL when split == 1.
+ * [B*heads][Nk][64] when v_mn & 1 (MN-major UMMA operand); *_lo NULL when split == 1.  v_mn & 2: the V planes hold IEEE
+ * fp16 hi / lo (pram_split_f16, pram_tc_args.v_f16) and the probabilities are fed back as ONE fp16 plane (11-bit mantissas,
+ * row sums taken from the rounded values): two PV MMAs per k-step instead of three and half the softmax instructions.
  * Replaces Attention.forward, nets/segnetvit.py:73-76 and the two einsum+softmax pairs of
  * nets/gml.py:175-181. */
 int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
@@ -209,6 +217,49 @@ int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k_hi, cons
                       void* out_hi, void* out_lo, int out_ld, int split, int kv_tile /* 0 = auto, 64 (two CTAs per SM) or 128 */, int v_mn,
                       const int* nk_counts /* optional [B]: keys >= nk_counts[b] of batch element b are padding and masked */,
                       pram_stream_t stream);
+
+/* Same launch, additionally writing the log2-domain log-sum-exp of every query row (softmax prob = exp2(s * scale * log2 e -
+ * lse)) to lse_out [B*heads][ld_lse] (ld_lse % 4 == 0, >= Nq). */
+int pram_attention_tc_lse(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
+                          const void* vt_lo, int B, int heads, int Nq, int Nk, int nk_pad, float scale, float* out_f32,
+                          void* out_hi, void* out_lo, int out_ld, int split, int kv_tile, int v_mn, const int* nk_counts,
+                          float* lse_out, int ld_lse, pram_stream_t stream);
+
+/* K17, Attention.forward's second output (nets/adagml.py:145-148; cross block :229): the attention mass every KEY receives,
+ * colsum[b*heads + h][key] = sum over the valid queries of softmax(query, key), on tcgen05: S^T = K Q^T tiles (one thread per
+ * key row) against the queries' row statistics `lse` of the pram_attention_tc_lse launch (ld_lse >= Nqueries rounded up to
+ * 128).  nq_counts optional [B]: queries >= nq_counts[b] are padding.  Mean attention = pram_colmean_reduce. */
+int pram_attention_colsum_tc(const void* key_hi, const void* key_lo, const void* qry_hi, const void* qry_lo, int B, int heads,
+                             int Nkeys, int Nqueries, float scale, const float* lse, int ld_lse, float* colsum, int ld_colsum,
+                             int split, int kv_tile, const int* nq_counts, pram_stream_t stream);
+/* out[(b*N + j) * out_stride] = sum_h colsum[(b*heads + h) * ld + j] / (heads * queries_b), fixed order (bit-reproducible). */
+int pram_colmean_reduce(const float* colsum, int ld, int B, int heads, int N, int nq, const int* nq_counts, float* out,
+                        int out_stride, pram_stream_t stream);
+
+/* K17, AdaGML's pruning / early-exit control flow on the device (nets/adagml.py:344-372, 516-531) for a BATCH of pairs in the
+ * fixed token layout rows [0, B*M) = set 0, [B*M, B*(M+N)) = set 1, with per-pair token counts cnt0 / cnt1 [B]:
+ *  prune : keep = sigmoid(conf_logits) > threshold for sets with >= n_min_tokens tokens (do_prune), stable compaction
+ *          positions dest[row] (-1 = dropped), counts updated in place, stop test `1 - #(conf < th) / (m + n) > 0.95` ->
+ *          stop_layer[b] = layer (also at the last layer), active[l] (pairs still running at the START of layer l, [n_layers],
+ *          initialised to B: the launch predicate of layer l's kernels) decremented for l > layer, trace[layer][set][b] = counts,
+ *          *err = 1 when a set is pruned to zero tokens (the reference raises);
+ *  move  : kept rows -> their compacted position in the other buffer set (bf16 planes, fp32 rows, rotary cos / sin, index map);
+ *  latch : pairs with stop_layer[b] == layer keep out_proj[layer](tokens) (src planes [T][256]), index map and counts;
+ *  scatter: matches of the compacted problems -> full-size matches0 / matching_scores0 (nets/adagml.py:383-394). */
+int pram_adagml_prune(const float* conf_logits, int B, int M, int N, int* cnt0, int* cnt1, float threshold, int n_min_tokens,
+                      int do_prune, int layer, int n_layers, int* dest, int* stop_layer, int* active, int* trace, int* err,
+                      const int* full0, const int* full1 /* optional [B]: the pairs' original token counts (padded batches) */,
+                      pram_stream_t stream);
+int pram_adagml_move(const int* dest, int B, int M, int N, const void* src_hi, const void* src_lo, void* dst_hi, void* dst_lo,
+                     long long ld_bf, const float* src_f32, float* dst_f32, long long ld_f32, const float* src_cos,
+                     const float* src_sin, float* dst_cos, float* dst_sin, const int* src_ind, int* dst_ind,
+                     pram_stream_t stream);
+int pram_adagml_latch(const int* stop_layer, int layer, int B, int M, int N, const void* src_hi, const void* src_lo, void* dst_hi,
+                      void* dst_lo, const int* src_ind, int* dst_ind, const int* cnt0, const int* cnt1, int* final_cnt0,
+                      int* final_cnt1, pram_stream_t stream);
+int pram_adagml_scatter(const long long* matches0, const float* mscores0, const int* ind, const int* final_cnt0,
+                        const int* final_cnt1, int B, int M, int N, long long* full_matches0, float* full_scores0,
+                        pram_stream_t stream);
 
 /* qkv fp32 rows -> the attention kernel's operands (rotary + scale on q,k; V transposed per head).
  * nets/segnetvit.py:98-103, nets/gml.py:169-174. */
@@ -259,6 +310,9 @@ int pram_nn_match(const float* sim, const float* simT, int B, int N, int M, floa
 
 /* fp32 -> one plane of IEEE fp16 (operand of the single-pass fp16 GEMM mode, pram_tc_args.f16). */
 int pram_cast_f16(const float* in, void* out, long long n, pram_stream_t stream);
+
+/* fp32 -> IEEE fp16 hi / lo planes (lo may be NULL). */
+int pram_split_f16(const float* in, void* hi, void* lo, long long n, pram_stream_t stream);
 
 /* fp32 -> split bf16 planes: hi = bf16(x), lo = bf16(x - hi) (lo may be NULL). */
 int pram_split_bf16(const float* in, void* hi, void* lo, long long n, pram_stream_t stream);

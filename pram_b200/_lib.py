@@ -26,6 +26,7 @@ SIGNATURES = {
     'pram_launch_count': (C.c_ulonglong, []),
     'pram_error_string': (C.c_char_p, [_I]),
     'pram_last_cuda_error': (C.c_char_p, []),
+    'pram_set_launch_predicate': (_I, [_P]),
     'pram_score_map': (_I, [_P, _L, _L, _L, _L, _I, _I, _I, _P, _P]),
     'pram_resize_bilinear': (_I, [_P, _I, _I, _I, _P, _I, _I, _P]),
     'pram_nms_candidates': (_I, [_P, _I, _I, _I, _I, _F, _F, _P, _P, _I, _P, _P, _P]),
@@ -65,7 +66,7 @@ class TcArgs(C.Structure):
         ('qkv_mode', _I), ('cosb', _P), ('sinb', _P), ('qk_scale', _F),
         ('q_hi', _P), ('q_lo', _P), ('k_hi', _P), ('k_lo', _P), ('v_hi', _P), ('v_lo', _P),
         ('seg_split', _I), ('seg_n0', _I), ('seg_n1', _I), ('heads', _I),
-        ('cluster', _I), ('l2_prefetch', _I), ('f16', _I), ('res_hi', _P), ('res_lo', _P),
+        ('cluster', _I), ('l2_prefetch', _I), ('f16', _I), ('res_hi', _P), ('res_lo', _P), ('v_f16', _I),
     ]
 
 
@@ -85,9 +86,17 @@ class MlpBlockArgs(C.Structure):
 
 
 SIGNATURES['pram_mlp_block_tc'] = (_I, [C.POINTER(MlpBlockArgs), _P])
+SIGNATURES['pram_split_f16'] = (_I, [_P, _P, _P, _L, _P])
 SIGNATURES['pram_split_bf16'] = (_I, [_P, _P, _P, _L, _P])
 SIGNATURES['pram_cast_f16'] = (_I, [_P, _P, _L, _P])
 SIGNATURES['pram_attention_tc'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I, _I, _I, _I, _P, _P])
+SIGNATURES['pram_attention_tc_lse'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P])
+SIGNATURES['pram_attention_colsum_tc'] = (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _P, _I, _I, _I, _P, _P])
+SIGNATURES['pram_colmean_reduce'] = (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P])
+SIGNATURES['pram_adagml_prune'] = (_I, [_P, _I, _I, _I, _P, _P, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P])
+SIGNATURES['pram_adagml_move'] = (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _L, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P])
+SIGNATURES['pram_adagml_latch'] = (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P])
+SIGNATURES['pram_adagml_scatter'] = (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P])
 SIGNATURES['pram_attention_prep'] = (_I, [_P, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P, _I, _P])
 _D = C.c_double
 SIGNATURES['pram_ransac_workspace_bytes'] = (_L, [_I, _I, _I])

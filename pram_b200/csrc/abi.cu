@@ -2,6 +2,11 @@
 #include "common.cuh"
 
 unsigned long long g_pram_launches = 0;
+thread_local const int* g_pram_pred = nullptr;
+
+// flag != NULL: kernels launched by this thread from now on (GEMM, attention, block tail, Linear, LayerNorm, the AdaGML
+// control kernels) skip their work when *flag == 0 at execution time; NULL clears the predicate.
+PRAM_API int pram_set_launch_predicate(const int* flag) { g_pram_pred = flag; return PRAM_OK; }
 
 PRAM_API int pram_version(void) { return 100; }  // 0.1.0
 

@@ -13,7 +13,9 @@
 // product is three MMAs (hi*hi + lo*hi + hi*lo) into the same fp32 accumulator.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace fa {
 
@@ -44,6 +46,14 @@ struct Args {
     float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_ld;
     int v_mn;          // 1: V given as [BH][Nk][64] (MN-major B operand), 0: V^T [BH][64][nk_pad] (K-major)
     const int* nk_counts;  // optional [B]: valid keys of batch element b (keys >= nk_counts[b] are padding and masked)
+    // MODE 0, optional: log2-domain log-sum-exp of every query row, [BH][ld_lse] (softmax prob = exp2(s * scale_log2 - lse))
+    float* lse_out;
+    // MODE 1 (column sums of the attention matrix, AdaGML's per-token mean attention, nets/adagml.py:148, 229): the kernel's
+    // ROWS are the keys, its streamed COLUMNS the queries; lse_in [BH][ld_lse] = the row statistics of the queries written
+    // by the MODE 0 launch, colsum [BH][ld_colsum] receives sum_i softmax(i, key) over the valid queries
+    const float* lse_in; int ld_lse;
+    float* colsum; int ld_colsum;
+    const int* pred;   // launch predicate (common.cuh)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -187,7 +197,14 @@ struct Cfg {
     static_assert(SMEM_BYTES <= (BKV == 128 ? 227 : 113) * 1024, "dynamic shared memory budget of sm_100a exceeded");
 };
 
-template <int SPLIT, int BKV>
+// P16: the probabilities go back to TMEM as ONE plane of IEEE fp16 (11-bit mantissas; P lies in [0, 1], far inside fp16's
+// range) instead of bf16 hi / lo planes, and PV is P16 . V_hi + P16 . V_lo with V given as fp16 hi / lo planes (the
+// hardware traps on an fp16 A operand against a bf16 B operand, so the producer of V -- the qkv GEMM epilogue -- writes
+// fp16 planes for this mode).  The row sum is accumulated from the ROUNDED probabilities, so O / l
+// is an exact convex combination of the V rows with weights that are off by <= 2^-12 relative -- the error that matters
+// for a softmax average -- while the softmax warps execute about half the instructions per score and PV needs two MMAs
+// per k-step instead of three.
+template <int SPLIT, int BKV, int MODE, int P16>
 __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) attention_tc_kernel(
     const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
     const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo,
@@ -196,6 +213,7 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
     using Gm = Geo<BKV>;
     constexpr int NPART = Gm::NPART, CPT = Gm::CPT, OPT = Gm::OPT, NUM_SM_WARPS = Gm::NUM_SM_WARPS;
     constexpr uint32_t COL_S0 = Gm::COL_S0, COL_S1 = Gm::COL_S1, COL_O = Gm::COL_O, TMEM_COLS = Gm::TMEM_COLS;
+    if (pram_pred_skip(p.pred)) return;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* q_s = smem;                                  // [NPL][16 KB]
@@ -281,14 +299,15 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
             load_k(0);
             for (int t = 0; t < n_tiles; ++t) {
                 if (t + 1 < n_tiles) load_k(t + 1);  // K runs one tile ahead of V
-                load_v(t);
+                if constexpr (MODE == 0) load_v(t);
                 if ((t + 1) % kv_tiles == 0 && t + 1 < n_tiles) load_q((t + 1) / kv_tiles);
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp, one elected lane per instruction; see gemm_tc.cu) =====================
         constexpr uint32_t idesc_s = make_idesc(BQ, BKV);
-        const uint32_t idesc_o = make_idesc(BQ, HD) | (p.v_mn ? (1u << 16) : 0u);  // bit 16: B is MN-major
+        // bit 16: B is MN-major; P16: A and B formats (bits 7..9, 10..12) = F16 (0) instead of BF16 (1)
+        const uint32_t idesc_o = (make_idesc(BQ, HD) & ~(P16 ? ((7u << 7) | (7u << 10)) : 0u)) | (p.v_mn ? (1u << 16) : 0u);
         uint32_t g = 0, w = 0;
         const uint32_t q_hi = smem_u32(q_s), q_lo = q_hi + C::Q_BYTES;
         auto issue_S = [&](uint32_t gg) {
@@ -320,6 +339,16 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
             for (int j = 0; j < kv_tiles; ++j, ++g) {
                 const int st = g & 1;
                 mbar_wait(&p_full[st], (g >> 1) & 1);
+                if constexpr (MODE == 1) {
+                    // column-sum mode: no P, no PV.  p_full(g) here means "every softmax warp holds S(g) in registers",
+                    // which is what frees the S buffer for tile g + 2
+                    tc_fence_after();
+                    if (j + 2 < kv_tiles) {
+                        issue_S(g + 2);
+                        if (j + 3 == kv_tiles) umma_commit(q_empty);
+                    }
+                    continue;
+                }
                 mbar_wait(&v_full[st], (g >> 1) & 1);
                 tc_fence_after();
                 const uint32_t v_hi = smem_u32(v_s + st * C::V_STAGE), v_lo = v_hi + C::V_BYTES;
@@ -332,7 +361,7 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
                     const uint64_t bh_d = p.v_mn ? make_desc_mn(v_hi + vo) : make_desc(v_hi + vo);
                     umma_ts(d, a_hi, bh_d, idesc_o, (j | ks) != 0);
                     if (SPLIT == 3) {
-                        umma_ts(d, a_lo, bh_d, idesc_o, 1);
+                        if (!P16) umma_ts(d, a_lo, bh_d, idesc_o, 1);
                         umma_ts(d, a_hi, p.v_mn ? make_desc_mn(v_lo + vo) : make_desc(v_lo + vo), idesc_o, 1);
                     }
                 }
@@ -360,6 +389,52 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
             // keys of this batch element that are real tokens: the fixed [B, K] layout of the batched pipeline pads
             // frames with fewer keypoints; a padded key must not receive attention (the reference runs n[b] tokens)
             const int nk_b = p.nk_counts ? max(1, min(p.Nk, __ldg(p.nk_counts + bh / p.heads))) : p.Nk;
+            if constexpr (MODE == 1) {
+                // ---- column sums: this thread's row is a KEY, the streamed columns are the queries whose row statistics are
+                // known (lse_in), so every probability is final the moment its score is read: no running max, no P, no O
+                float acc0 = 0.f, acc1 = 0.f;
+                const float* lrow = p.lse_in + (long long)bh * p.ld_lse + part * CPT;
+                for (int j = 0; j < kv_tiles; ++j, ++g) {
+                    const int st = g & 1;
+                    const uint32_t s_addr = tmem_base + lane_off + (st ? COL_S1 : COL_S0) + part * CPT;
+                    const int nvalid = min(BKV, nk_b - j * BKV) - part * CPT;
+                    float4 L[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) L[i] = __ldg(reinterpret_cast<const float4*>(lrow + j * BKV) + i);
+                    mbar_wait(&s_full[st], (g >> 1) & 1);
+                    tc_fence_after();
+                    uint32_t v0[32];
+                    tmem_ld32(s_addr, v0);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p_full[st]);  // S(g) is in registers: its buffer may be overwritten
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 lv = L[i >> 2];
+                        float e0, e1, e2, e3;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(v0[i]), p.scale_log2, -lv.x)));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(v0[i + 1]), p.scale_log2, -lv.y)));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(__uint_as_float(v0[i + 2]), p.scale_log2, -lv.z)));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fmaf(__uint_as_float(v0[i + 3]), p.scale_log2, -lv.w)));
+                        if (nvalid < CPT) {  // padded / out-of-range queries contribute nothing (their statistics may be garbage)
+                            e0 = (i < nvalid) ? e0 : 0.f; e1 = (i + 1 < nvalid) ? e1 : 0.f;
+                            e2 = (i + 2 < nvalid) ? e2 : 0.f; e3 = (i + 3 < nvalid) ? e3 : 0.f;
+                        }
+                        acc0 += e0 + e1; acc1 += e2 + e3;
+                    }
+                }
+                const uint32_t x = xch + (uint32_t)r * 4u;
+                sts_f32(x + part * 512, acc0 + acc1);
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NPART) : "memory");
+                if (part == 0 && q0 + r < p.Nq) {
+                    float tot = lds_f32(x);
+#pragma unroll
+                    for (int q2 = 1; q2 < NPART; ++q2) tot += lds_f32(x + q2 * 512);  // fixed order: bit-reproducible
+                    p.colsum[(long long)bh * p.ld_colsum + q0 + r] = tot;
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NPART) : "memory");
+                continue;
+            }
             float m_used = -INFINITY, l = 0.f;  // l: this thread's partial row sum (its 32 columns)
             for (int j = 0; j < kv_tiles; ++j, ++g) {
                 const int st = g & 1;
@@ -408,6 +483,13 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
                     float p0, p1;
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v0[i]), p.scale_log2, -m_used)));
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v0[i + 1]), p.scale_log2, -m_used)));
+                    if constexpr (P16) {
+                        const __half2 hh = __floats2half2_rn(p0, p1);
+                        ph[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+                        const float2 pr = __half22float2(hh);  // the row sum follows the rounded weights
+                        ls0 += pr.x; ls1 += pr.y;
+                        continue;
+                    }
                     ls0 += p0; ls1 += p1;
                     __nv_bfloat162 ha = __floats2bfloat162_rn(p0, p1);
                     const uint32_t ua = *reinterpret_cast<uint32_t*>(&ha);
@@ -432,7 +514,7 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
                 // P over S, in place: all four warps of this lane quarter loaded their scores before the bar.sync above
                 const uint32_t p_addr = tmem_base + lane_off + (st ? COL_S1 : COL_S0) + part * (CPT / 2);
                 tmem_st16(p_addr, ph);
-                if (SPLIT == 3) tmem_st16(p_addr + BKV / 2, pl);
+                if (SPLIT == 3 && !P16) tmem_st16(p_addr + BKV / 2, pl);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -446,9 +528,10 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
 #pragma unroll
             for (int q2 = 1; q2 < NPART; ++q2) lsum_all += lds_f32(x + q2 * 512);
             const float inv = 1.f / lsum_all;
+            const int qn = q0 + r;
+            if (p.lse_out && part == 0 && qn < p.Nq) p.lse_out[(long long)bh * p.ld_lse + qn] = m_used + log2f(lsum_all);
             mbar_wait(&o_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
             tc_fence_after();
-            const int qn = q0 + r;
             const int b = bh / p.heads, hh = bh - b * p.heads;
             const long long orow = ((long long)b * p.Nq + qn) * p.out_ld + hh * HD + part * OPT;
             {
@@ -531,16 +614,22 @@ static int encode3(CUtensorMap* m, const void* base, cuuint64_t d0, cuuint64_t d
 // q/k: bf16 [BH][N][64]; v_mn = 0: vt bf16 [BH][64][nk_pad] (keys contiguous, nk_pad % 8 == 0, padding zeroed);
 // v_mn = 1: vt is V itself, bf16 [BH][Nk][64] (consumed as an MN-major UMMA operand, no transposition);
 // *_lo may be NULL when split == 1.  out: f32 and/or split bf16 [B][Nq][out_ld] at column head*64.
-PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
-                               const void* vt_lo, int B, int heads, int Nq, int Nk, int nk_pad, float scale,
-                               float* out_f32, void* out_hi, void* out_lo, int out_ld, int split, int p_swap,
-                               int v_mn, const int* nk_counts, cudaStream_t stream) {
+// mode 1 (column sums): q_* = the KEY operand (rows), k_* = the QUERY operand (columns), no V / out.
+static int attention_launch(int mode, const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
+                            const void* vt_lo, int B, int heads, int Nq, int Nk, int nk_pad, float scale, float* out_f32,
+                            void* out_hi, void* out_lo, int out_ld, int split, int p_swap, int v_mn, const int* nk_counts,
+                            float* lse_out, const float* lse_in, int ld_lse, float* colsum, int ld_colsum, cudaStream_t stream) {
     using namespace fa;
-    if (!q_hi || !k_hi || !vt_hi || B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return PRAM_ERR_ARG;
+    const bool p16 = (v_mn & 2) != 0;  // V planes hold IEEE fp16 hi / lo: probabilities as one fp16 plane (kernel variant P16)
+    v_mn &= 1;
+    if (!q_hi || !k_hi || (mode == 0 && !vt_hi) || B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return PRAM_ERR_ARG;
     if (split != 1 && split != 3) return PRAM_ERR_ARG;
     if (p_swap != 0 && p_swap != 64 && p_swap != 128) return PRAM_ERR_ARG;  // key-tile variant: 0 = auto, 64, 128
-    if (split == 3 && (!q_lo || !k_lo || !vt_lo)) return PRAM_ERR_ARG;
-    if ((!v_mn && ((nk_pad % 8) || nk_pad < Nk)) || (out_ld % 8)) return PRAM_ERR_UNSUPPORTED;
+    if (split == 3 && (!q_lo || !k_lo || (mode == 0 && !vt_lo))) return PRAM_ERR_ARG;
+    if (mode == 0 && ((!v_mn && ((nk_pad % 8) || nk_pad < Nk)) || (out_ld % 8))) return PRAM_ERR_UNSUPPORTED;
+    if (mode == 1 && (!lse_in || !colsum || ld_colsum < Nq)) return PRAM_ERR_ARG;
+    // the statistics rows are read / written in whole key tiles with 16-byte loads
+    if ((lse_out || lse_in) && ((ld_lse % 4) || ld_lse < (mode == 1 ? (Nk + 127) / 128 * 128 : Nq))) return PRAM_ERR_ARG;
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
@@ -559,6 +648,7 @@ PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k
         if (rc) return rc;
         rc = encode3(&mk[i], ks[i], HD, Nk, BH, HD * 2, (cuuint64_t)Nk * HD * 2, HD, bkv);
         if (rc) return rc;
+        if (mode == 1) { mv[i] = mk[i]; continue; }
         if (v_mn) rc = encode3(&mv[i], vs[i], HD, Nk, BH, HD * 2, (cuuint64_t)Nk * HD * 2, HD, bkv);
         else rc = encode3(&mv[i], vs[i], nk_pad, HD, BH, (cuuint64_t)nk_pad * 2, (cuuint64_t)nk_pad * HD * 2, 64, HD);
         if (rc) return rc;
@@ -569,21 +659,55 @@ PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k
     a.out_f32 = out_f32; a.out_hi = (__nv_bfloat16*)out_hi; a.out_lo = (__nv_bfloat16*)out_lo; a.out_ld = out_ld;
     a.v_mn = v_mn;
     a.nk_counts = nk_counts;
+    a.pred = g_pram_pred;
+    a.lse_out = lse_out; a.lse_in = lse_in; a.ld_lse = ld_lse; a.colsum = colsum; a.ld_colsum = ld_colsum;
     const int total = BH * ((Nq + BQ - 1) / BQ);
-#define PRAM_ATT_LAUNCH(SPLIT_, BKV_)                                                                                   \
+#define PRAM_ATT_LAUNCH(SPLIT_, BKV_, MODE_, P16_)                                                                      \
     do {                                                                                                                \
-        auto kern = attention_tc_kernel<SPLIT_, BKV_>;                                                                  \
+        auto kern = attention_tc_kernel<SPLIT_, BKV_, MODE_, P16_>;                                                     \
         static bool attr = false;                                                                                       \
         if (!attr) { PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<SPLIT_, BKV_>::SMEM_BYTES)); attr = true; } \
         const int cap = Geo<BKV_>::CTAS_PER_SM * num_sms;                                                               \
         const int grid = total < cap ? total : cap;                                                                     \
         kern<<<grid, Geo<BKV_>::NUM_THREADS, Cfg<SPLIT_, BKV_>::SMEM_BYTES, stream>>>(mq[0], mq[1], mk[0], mk[1], mv[0], mv[1], a); \
     } while (0)
-    if (split == 3) { if (bkv == 128) PRAM_ATT_LAUNCH(3, 128); else PRAM_ATT_LAUNCH(3, 64); }
-    else { if (bkv == 128) PRAM_ATT_LAUNCH(1, 128); else PRAM_ATT_LAUNCH(1, 64); }
+#define PRAM_ATT_MODE(MODE_, P16_)                                                                                      \
+    do {                                                                                                                \
+        if (split == 3) { if (bkv == 128) PRAM_ATT_LAUNCH(3, 128, MODE_, P16_); else PRAM_ATT_LAUNCH(3, 64, MODE_, P16_); } \
+        else { if (bkv == 128) PRAM_ATT_LAUNCH(1, 128, MODE_, P16_); else PRAM_ATT_LAUNCH(1, 64, MODE_, P16_); }        \
+    } while (0)
+    if (mode == 1) PRAM_ATT_MODE(1, 0); else if (p16) PRAM_ATT_MODE(0, 1); else PRAM_ATT_MODE(0, 0);
+#undef PRAM_ATT_MODE
 #undef PRAM_ATT_LAUNCH
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
+}
+
+PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
+                               const void* vt_lo, int B, int heads, int Nq, int Nk, int nk_pad, float scale,
+                               float* out_f32, void* out_hi, void* out_lo, int out_ld, int split, int p_swap,
+                               int v_mn, const int* nk_counts, cudaStream_t stream) {
+    return attention_launch(0, q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo, B, heads, Nq, Nk, nk_pad, scale, out_f32, out_hi, out_lo,
+                            out_ld, split, p_swap, v_mn, nk_counts, nullptr, nullptr, 0, nullptr, 0, stream);
+}
+
+// same, additionally writing the log2-domain log-sum-exp of every query row to lse_out [B*heads][ld_lse]
+PRAM_API int pram_attention_tc_lse(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
+                                   const void* vt_lo, int B, int heads, int Nq, int Nk, int nk_pad, float scale,
+                                   float* out_f32, void* out_hi, void* out_lo, int out_ld, int split, int p_swap,
+                                   int v_mn, const int* nk_counts, float* lse_out, int ld_lse, cudaStream_t stream) {
+    return attention_launch(0, q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo, B, heads, Nq, Nk, nk_pad, scale, out_f32, out_hi, out_lo,
+                            out_ld, split, p_swap, v_mn, nk_counts, lse_out, nullptr, ld_lse, nullptr, 0, stream);
+}
+
+// AdaGML's per-key attention mass (nets/adagml.py:148, 229) on the tensor cores: colsum[bh][key] = sum over the valid queries
+// of softmax(query, key), from S^T = K Q^T tiles and the queries' row statistics of the pram_attention_tc_lse launch.
+PRAM_API int pram_attention_colsum_tc(const void* key_hi, const void* key_lo, const void* qry_hi, const void* qry_lo, int B,
+                                      int heads, int Nkeys, int Nqueries, float scale, const float* lse, int ld_lse,
+                                      float* colsum, int ld_colsum, int split, int kv_tile, const int* nq_counts,
+                                      cudaStream_t stream) {
+    return attention_launch(1, key_hi, key_lo, qry_hi, qry_lo, nullptr, nullptr, B, heads, Nkeys, Nqueries, 0, scale, nullptr,
+                            nullptr, nullptr, 0, split, kv_tile, 1, nq_counts, nullptr, lse, ld_lse, colsum, ld_colsum, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -30,6 +30,12 @@ extern unsigned long long g_pram_launches;
         if (e__ != cudaSuccess) return PRAM_ERR_CUDA;            \
     } while (0)
 
+// Launch predicate (pram_set_launch_predicate): while a device flag is registered, the kernels that take part in a
+// device-side early exit (AdaGML's stop test, csrc/adagml_ops.cu) are launched with it and return at once when the flag
+// reads 0 -- the device-resident replacement of the reference's host-side `break` (nets/adagml.py:370-372).
+extern thread_local const int* g_pram_pred;
+__device__ __forceinline__ bool pram_pred_skip(const int* pred) { return pred != nullptr && __ldg(pred) == 0; }
+
 __host__ __device__ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -54,6 +54,8 @@ struct Args {
     __nv_bfloat16* q_hi; __nv_bfloat16* q_lo; __nv_bfloat16* k_hi; __nv_bfloat16* k_lo; __nv_bfloat16* v_hi; __nv_bfloat16* v_lo;
     int seg_split, seg_n0, seg_n1, heads;
     int l2_prefetch;     // 1: pull the next tile's activation boxes into L2 one tile ahead (single-tap layers)
+    const int* pred;     // launch predicate (common.cuh): the whole grid returns when *pred == 0
+    int v_f16;           // qkv epilogue: the V planes receive IEEE fp16 hi / lo instead of bf16 hi / lo
     int f16;             // operands are IEEE fp16 (one MMA per k-step, 11-bit mantissas): A / W planes hold fp16 bits and the
                          // out_hi plane receives fp16 (out_lo unused) -- the single-pass mode of the descriptor head
 };
@@ -236,6 +238,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
     const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const Args p) {
     using C = Cfg<BN, SPLIT>;
+    if (pram_pred_skip(p.pred)) return;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -509,14 +512,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                             }
                         }
                         uint32_t hi[4], lo[4];
+                        if (is_v && p.v_f16) {  // V as IEEE fp16 hi / lo planes: operand of the fp16-probability PV (attention_tc.cu, P16)
 #pragma unroll
-                        for (int k = 0; k < 8; k += 2) {
-                            const float x0 = f[k] * sc, x1 = f[k + 1] * sc;
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-                            const uint32_t u = *reinterpret_cast<uint32_t*>(&h2);
-                            __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - __uint_as_float(u << 16), x1 - __uint_as_float(u & 0xffff0000u));
-                            hi[k >> 1] = u;
-                            lo[k >> 1] = *reinterpret_cast<uint32_t*>(&l2);
+                            for (int k = 0; k < 8; k += 2) {
+                                const __half2 h2 = __floats2half2_rn(f[k], f[k + 1]);
+                                const float2 hf = __half22float2(h2);
+                                const __half2 l2 = __floats2half2_rn(f[k] - hf.x, f[k + 1] - hf.y);
+                                hi[k >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                                lo[k >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; k += 2) {
+                                const float x0 = f[k] * sc, x1 = f[k + 1] * sc;
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+                                const uint32_t u = *reinterpret_cast<uint32_t*>(&h2);
+                                __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - __uint_as_float(u << 16), x1 - __uint_as_float(u & 0xffff0000u));
+                                hi[k >> 1] = u;
+                                lo[k >> 1] = *reinterpret_cast<uint32_t*>(&l2);
+                            }
                         }
                         if (pixr >= 0) {
                             const long long qo = (long long)lds32(eq_ps + 4 * row) + (long long)(c >> 6) * lds32(eq_inv + 4 * row) + (c & 63) + col2;
@@ -752,6 +766,7 @@ struct pram_tc_args {
     int l2_prefetch;                      // 1 = pull the next tile's activation boxes into L2 one tile ahead (single-tap layers); default off
     int f16;                              // 1 (split == 1 only): a / w planes hold IEEE fp16, out_hi receives fp16 -- single-pass fp16 mode
     const void* res_hi; const void* res_lo;  // residual as split-bf16 planes (used when res == NULL; row stride res_ld, N % 32 == 0)
+    int v_f16;                            // qkv epilogue: v_hi / v_lo receive IEEE fp16 planes
 };
 
 PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
@@ -815,6 +830,8 @@ PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
     k.seg_split = a->seg_split; k.seg_n0 = a->seg_n0; k.seg_n1 = a->seg_n1; k.heads = a->heads;
     if (a->f16 && a->split != 1) return PRAM_ERR_ARG;
     k.f16 = a->f16;
+    k.pred = g_pram_pred;
+    k.v_f16 = a->v_f16;
     k.res_hi = (const __nv_bfloat16*)a->res_hi; k.res_lo = (const __nv_bfloat16*)a->res_lo;
     if (!a->res && a->res_hi && ((a->N % 32) || (a->res_ld % 4))) return PRAM_ERR_UNSUPPORTED;
     k.l2_prefetch = (a->ntaps == 1) && (a->l2_prefetch == 1);  // measured on B200: no gain (the thin GEMMs are store-bound), off unless asked for
@@ -872,6 +889,23 @@ __global__ void cast_f16_kernel(const float* __restrict__ in, __half* __restrict
 PRAM_API int pram_cast_f16(const float* in, void* out, long long n, cudaStream_t stream) {
     if (!in || !out || n <= 0) return PRAM_ERR_ARG;
     cast_f16_kernel<<<cdiv((n + 7) / 8, 256), 256, 0, stream>>>(in, (__half*)out, n);
+    PRAM_CHECK_LAUNCH();
+    return PRAM_OK;
+}
+
+__global__ void split_f16_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = in[i];
+    const __half h = __float2half_rn(x);
+    hi[i] = h;
+    if (lo) lo[i] = __float2half_rn(x - __half2float(h));
+}
+
+// fp32 -> IEEE fp16 hi / lo planes: hi = fp16(x), lo = fp16(x - hi) (lo may be NULL)
+PRAM_API int pram_split_f16(const float* in, void* hi, void* lo, long long n, cudaStream_t stream) {
+    if (!in || !hi || n <= 0) return PRAM_ERR_ARG;
+    split_f16_kernel<<<cdiv(n, 256), 256, 0, stream>>>(in, (__half*)hi, (__half*)lo, n);
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
 }

@@ -57,6 +57,7 @@ struct Args {
     const __nv_bfloat16* xa_hi; const __nv_bfloat16* xa_lo; long long lda;  // ... residual = hi + lo of the A rows (x)
     float* out_f32; long long ld_f32;
     __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; long long ld_bf;
+    const int* pred;  // launch predicate (common.cuh)
     long long* dbg;   // optional timeline: [CTA][tile iteration (<= 8)][32] SM clock stamps (tools/bench_block.py --timeline)
 };
 __device__ __forceinline__ void stamp(const Args& p, uint32_t it, int slot) {
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
     const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
     const __grid_constant__ CUtensorMap map_w3_hi, const __grid_constant__ CUtensorMap map_w3_lo, const Args p,
     const __grid_constant__ Tables tb) {
+    if (pram_pred_skip(p.pred)) return;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
@@ -623,6 +625,7 @@ PRAM_API int pram_mlp_block_tc(const pram_mlp_block_args* a, cudaStream_t stream
     k.res = a->res; k.res_ld = a->res_ld; k.out_f32 = a->out_f32; k.ld_f32 = a->ld_f32;
     k.xa_hi = (const __nv_bfloat16*)a->a_hi; k.xa_lo = (const __nv_bfloat16*)(a->a_lo ? a->a_lo : a->a_hi); k.lda = a->lda;
     k.dbg = a->dbg;
+    k.pred = g_pram_pred;
     Tables tb;
     memcpy(&tb, a->tables_host, sizeof(Tables));
     k.out_hi = (__nv_bfloat16*)a->out_hi; k.out_lo = (__nv_bfloat16*)a->out_lo; k.ld_bf = a->ld_bf;

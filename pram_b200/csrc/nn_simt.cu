@@ -28,6 +28,7 @@ struct ConvParams {
     int relu;
     int w_layout;              // 0: w[tap][Cin][Cout]   1: w[Cout][Cin] (ksize 1; torch Linear layout)
     long long in_batch_stride, w_batch_stride, out_batch_stride;  // blockIdx.z batching (bmm)
+    const int* pred;           // launch predicate (common.cuh), NULL = always run
 };
 
 __global__ void __launch_bounds__(IG_THREADS) conv_igemm_kernel(ConvParams p) {
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(IG_THREADS) conv_igemm_kernel(ConvParams p) {
     __shared__ float Bs[IG_BK][IG_BN + 4];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, micro-tile 8 (m) x 4 (n)
+    if (pram_pred_skip(p.pred)) return;
     p.in += blockIdx.z * p.in_batch_stride;
     p.w += blockIdx.z * p.w_batch_stride;
     p.out += blockIdx.z * p.out_batch_stride;
@@ -174,6 +176,7 @@ PRAM_API int pram_conv_f32(const float* in, long long in_pix_stride, const float
     p.in_pix_stride = in_pix_stride; p.out_pix_stride = out_pix_stride; p.res_pix_stride = res_pix_stride;
     p.relu = relu; p.w_layout = 0;
     p.in_batch_stride = p.w_batch_stride = p.out_batch_stride = 0;
+    p.pred = nullptr;
     long long M = (long long)B * p.Ho * p.Wo;
     dim3 grid(cdiv(M, IG_BM), cdiv(Cout, IG_BN));
     conv_igemm_kernel<<<grid, IG_THREADS, 0, stream>>>(p);
@@ -194,6 +197,7 @@ PRAM_API int pram_linear_f32(const float* a, long long lda, const float* w, cons
     p.in_pix_stride = lda; p.out_pix_stride = ldo; p.res_pix_stride = ldres;
     p.relu = relu; p.w_layout = 1;
     p.in_batch_stride = a_batch_stride; p.w_batch_stride = w_batch_stride; p.out_batch_stride = out_batch_stride;
+    p.pred = g_pram_pred;
     dim3 grid(cdiv(rows, IG_BM), cdiv(N, IG_BN), batch);
     conv_igemm_kernel<<<grid, IG_THREADS, 0, stream>>>(p);
     PRAM_CHECK_LAUNCH();
@@ -375,8 +379,10 @@ template <int NV, bool FAST_ERF>
 __global__ void __launch_bounds__(256) layernorm_gelu_vec_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, float* __restrict__ out,
                                                                 __nv_bfloat16* __restrict__ out_hi,
-                                                                __nv_bfloat16* __restrict__ out_lo, long long rows, int gelu) {
+                                                                __nv_bfloat16* __restrict__ out_lo, long long rows, int gelu,
+                                                                const int* __restrict__ pred) {
     constexpr int C = NV * 128;
+    if (pram_pred_skip(pred)) return;
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -429,14 +435,14 @@ static bool layernorm_vec_launch(const float* in, const float* gamma, const floa
     // the fp32 output path is the exact-arithmetic mode (erff); split-bf16-only output may use the cheaper erf
     const bool fast = (out == nullptr);
     switch (C) {
-        case 256: if (fast) layernorm_gelu_vec_kernel<2, true><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu);
-                  else layernorm_gelu_vec_kernel<2, false><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu);
+        case 256: if (fast) layernorm_gelu_vec_kernel<2, true><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu, g_pram_pred);
+                  else layernorm_gelu_vec_kernel<2, false><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu, g_pram_pred);
                   return true;
-        case 512: if (fast) layernorm_gelu_vec_kernel<4, true><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu);
-                  else layernorm_gelu_vec_kernel<4, false><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu);
+        case 512: if (fast) layernorm_gelu_vec_kernel<4, true><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu, g_pram_pred);
+                  else layernorm_gelu_vec_kernel<4, false><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu, g_pram_pred);
                   return true;
-        case 1024: if (fast) layernorm_gelu_vec_kernel<8, true><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu);
-                   else layernorm_gelu_vec_kernel<8, false><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu);
+        case 1024: if (fast) layernorm_gelu_vec_kernel<8, true><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu, g_pram_pred);
+                   else layernorm_gelu_vec_kernel<8, false><<<grid, 256, 0, stream>>>(in, gamma, beta, out, h, l, rows, gelu, g_pram_pred);
                    return true;
         default: return false;
     }
@@ -445,10 +451,10 @@ static bool layernorm_vec_launch(const float* in, const float* gamma, const floa
 __global__ void layernorm_gelu_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, float* __restrict__ out,
                                       __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
-                                      long long rows, int C, int gelu) {
+                                      long long rows, int C, int gelu, const int* __restrict__ pred) {
     long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
-    if (row >= rows) return;
+    if (row >= rows || pram_pred_skip(pred)) return;
     const float* p = in + row * C;
     float s = 0.f;
     for (int c = lane; c < C; c += 32) s += p[c];
@@ -472,7 +478,7 @@ PRAM_API int pram_layernorm_gelu(const float* in, const float* gamma, const floa
                                  long long rows, int C, int gelu, cudaStream_t stream) {
     if (!in || !out || !gamma || !beta) return PRAM_ERR_ARG;
     if (!layernorm_vec_launch(in, gamma, beta, out, nullptr, nullptr, rows, C, gelu, stream))
-        layernorm_gelu_kernel<<<cdiv(rows * 32, 256), 256, 0, stream>>>(in, gamma, beta, out, nullptr, nullptr, rows, C, gelu);
+        layernorm_gelu_kernel<<<cdiv(rows * 32, 256), 256, 0, stream>>>(in, gamma, beta, out, nullptr, nullptr, rows, C, gelu, g_pram_pred);
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
 }
@@ -483,7 +489,7 @@ PRAM_API int pram_layernorm_gelu_split(const float* in, const float* gamma, cons
     if (!in || !gamma || !beta || (!out_f32 && !out_hi)) return PRAM_ERR_ARG;
     if (!layernorm_vec_launch(in, gamma, beta, out_f32, out_hi, out_lo, rows, C, gelu, stream))
         layernorm_gelu_kernel<<<cdiv(rows * 32, 256), 256, 0, stream>>>(in, gamma, beta, out_f32, (__nv_bfloat16*)out_hi,
-                                                                       (__nv_bfloat16*)out_lo, rows, C, gelu);
+                                                                       (__nv_bfloat16*)out_lo, rows, C, gelu, g_pram_pred);
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;
 }

@@ -22,6 +22,9 @@ D = 256
 # one fused tcgen05 kernel for proj -> mlp.0 -> LayerNorm + GELU -> mlp.3 (+ residual) (csrc/mlp_block_tc.cu);
 # PRAM_FUSED_BLOCK=0 keeps the four separate launches (A/B timing, bisecting)
 FUSED_BLOCK = os.environ.get('PRAM_FUSED_BLOCK', '1') != '0'
+# AdaGML's per-token mean attention on the tensor cores (attention_tc statistics + pram_attention_colsum_tc);
+# PRAM_COLMEAN_TC=0 falls back to the fp32 CUDA-core attention kernel for those blocks (A/B, bisecting)
+COLMEAN_TC = os.environ.get('PRAM_COLMEAN_TC', '1') != '0'
 
 
 def mlp_holder(d_in: int, d_hid: int, d_out: int) -> nn.Sequential:
@@ -125,6 +128,10 @@ class Workspace:
         self.ctx_in_bf = False
         self.fused = bool(split) and FUSED_BLOCK
         self.keep_f32 = False  # fused path only: also maintain the fp32 activation rows (ws.x) next to the bf16 planes
+        # attention probabilities as ONE IEEE fp16 plane against fp16 hi / lo V planes (written so by the qkv epilogue): two
+        # PV MMAs per k-step instead of three and about half the softmax instructions, weights exact to 2^-12 relative
+        # (set_precision(..., attention_probs='f16')); False: bf16 hi / lo probabilities, bf16 V planes (the parity mode)
+        self.p16 = False
         if split:
             lo = split == 3
             self.cat_bf = [ops.empty_split((tokens, 2 * D), device, lo), ops.empty_split((tokens, 2 * D), device, lo)]
@@ -140,6 +147,13 @@ class Workspace:
         self.q, self.k, self.v = e(tokens, D), e(tokens, D), e(tokens, D)
         self.ctx = e(tokens, D)
         self.hid = e(tokens, 2 * D)
+
+    def stats(self, b: int, nq: int, nk: int):
+        """Scratch of the mean-attention path: (row statistics of the queries [b*heads, lse_ld(nq)], column sums
+        [b*heads, lse_ld(nk)]), fresh per call (stream-ordered allocator; a few hundred KB)."""
+        dev = self.cat[0].device
+        return (torch.empty((b * HEADS, ops.lse_ld(nq)), device=dev, dtype=torch.float32),
+                torch.empty((b * HEADS, ops.lse_ld(nk)), device=dev, dtype=torch.float32))
 
     def ctx_out(self):
         """Where the tensor-core attention writes its context: the right half of the current concat rows when the block
@@ -222,7 +236,7 @@ def self_block(ws: Workspace, pk: Dict[str, torch.Tensor], segments: Sequence[Tu
     segment): tokens >= counts[s][b] of batch element b are padding and receive no attention.
     Reference nets/segnetvit.py:97-106 == nets/gml.py:128-137."""
     T = ws.T
-    use_tc = bool(ws.split) and colmeans is None
+    use_tc = bool(ws.split) and (colmeans is None or COLMEAN_TC)
     if not use_tc:
         _no_counts_here(counts)
     ws.ctx_in_bf = use_tc
@@ -230,13 +244,18 @@ def self_block(ws: Workspace, pk: Dict[str, torch.Tensor], segments: Sequence[Tu
         # qkv GEMM with the fused epilogue: bias, rotary on q/k, split-bf16 Q/K/V in [B, heads, n, 64]
         seg_split = segments[1][0] if len(segments) > 1 else T
         qkv = {'mode': 1, 'scale': 1.0, 'cos': cos, 'sin': sin, 'q': ws.q_bf, 'k': ws.k_bf, 'v': ws.v_bf,
-               'seg_split': seg_split, 'seg_n0': segments[0][2], 'seg_n1': segments[-1][2]}
+               'seg_split': seg_split, 'seg_n0': segments[0][2], 'seg_n1': segments[-1][2], 'v_f16': ws.p16}
         ops.linear_tc(ws.x_bf, 2 * D, T, D, pk['qkv.tc'], 3 * D, pk['qkv.b'], split=ws.split, bn=256, qkv=qkv)
         ctx, ctx_ld = ws.ctx_out()
         for si, (off, b, n) in enumerate(segments):
-            ops.attention_tc(ops.split_rows(ws.q_bf, off), ops.split_rows(ws.k_bf, off), ops.split_rows(ws.v_bf, off), b, HEADS,
-                             n, n, n, HDIM ** -0.5, None, ops.split_rows(ctx, off), ctx_ld, ws.split, v_mn=True,
-                             nk_counts=None if counts is None else counts[si])
+            q, k = ops.split_rows(ws.q_bf, off), ops.split_rows(ws.k_bf, off)
+            cnt = None if counts is None else counts[si]
+            lse, colsum = ws.stats(b, n, n) if colmeans is not None else (None, None)
+            ops.attention_tc(q, k, ops.split_rows(ws.v_bf, off), b, HEADS, n, n, n, HDIM ** -0.5, None,
+                             ops.split_rows(ctx, off), ctx_ld, ws.split, v_mn=True, v_f16=ws.p16, nk_counts=cnt, lse_out=lse)
+            if colmeans is not None:  # AdaGML: mean attention per key token from S^T tiles + the queries' row statistics
+                ops.attention_colmean_tc(k, q, b, HEADS, n, n, HDIM ** -0.5, lse, colsum, colmeans[si], colmeans[si].stride(0),
+                                         ws.split, nq_counts=cnt)
         _finish_block(ws, pk)
         return
     linear(ws, ws.x, ws.x_bf if ws.split else None, 2 * D, T, D, 3 * D, pk, 'qkv', out_f32=ws.qkv, ld_f32=3 * D)
@@ -258,19 +277,30 @@ def cross_block(ws: Workspace, pk: Dict[str, torch.Tensor], seg0: Tuple[int, int
     (o0, b, m), (o1, _, n) = seg0, seg1
     s0, s1 = slice(o0, o0 + b * m), slice(o1, o1 + b * n)
     sc = (HDIM ** -0.5) ** 0.5  # applied to both qk0 and qk1 (nets/gml.py:174)
-    use_tc = bool(ws.split) and colmeans is None
+    use_tc = bool(ws.split) and (colmeans is None or COLMEAN_TC)
     ws.ctx_in_bf = use_tc
     if not use_tc:
         _no_counts_here(counts)
     c0, c1 = (None, None) if counts is None else counts
     if use_tc:
-        fused = {'mode': 2, 'scale': sc, 'q': ws.q_bf, 'v': ws.v_bf, 'seg_split': o1, 'seg_n0': m, 'seg_n1': n}
+        fused = {'mode': 2, 'scale': sc, 'q': ws.q_bf, 'v': ws.v_bf, 'seg_split': o1, 'seg_n0': m, 'seg_n1': n, 'v_f16': ws.p16}
         ops.linear_tc(ws.x_bf, 2 * D, T, D, pk['qkv.tc'], 2 * D, pk['qkv.b'], split=ws.split, bn=256, qkv=fused)
         q0, q1 = ops.split_rows(ws.q_bf, o0), ops.split_rows(ws.q_bf, o1)
         v0, v1 = ops.split_rows(ws.v_bf, o0), ops.split_rows(ws.v_bf, o1)
         ctx, ctx_ld = ws.ctx_out()
-        ops.attention_tc(q0, q1, v1, b, HEADS, m, n, n, 1.0, None, ops.split_rows(ctx, o0), ctx_ld, ws.split, v_mn=True, nk_counts=c1)
-        ops.attention_tc(q1, q0, v0, b, HEADS, n, m, m, 1.0, None, ops.split_rows(ctx, o1), ctx_ld, ws.split, v_mn=True, nk_counts=c0)
+        want = colmeans is not None
+        lse, colsum = ws.stats(b, m, n) if want else (None, None)
+        ops.attention_tc(q0, q1, v1, b, HEADS, m, n, n, 1.0, None, ops.split_rows(ctx, o0), ctx_ld, ws.split, v_mn=True, v_f16=ws.p16,
+                         nk_counts=c1, lse_out=lse)
+        if want:  # mean of attn01 over the queries of set 0 -> per token of set 1
+            ops.attention_colmean_tc(q1, q0, b, HEADS, n, m, 1.0, lse, colsum, colmeans[1], colmeans[1].stride(0), ws.split,
+                                     nq_counts=c0)
+            lse, colsum = ws.stats(b, n, m)
+        ops.attention_tc(q1, q0, v0, b, HEADS, n, m, m, 1.0, None, ops.split_rows(ctx, o1), ctx_ld, ws.split, v_mn=True, v_f16=ws.p16,
+                         nk_counts=c0, lse_out=lse)
+        if want:  # mean of attn10 over the queries of set 1 -> per token of set 0
+            ops.attention_colmean_tc(q0, q1, b, HEADS, m, n, 1.0, lse, colsum, colmeans[0], colmeans[0].stride(0), ws.split,
+                                     nq_counts=c1)
         _finish_block(ws, pk)
         return
     qkv = ws.qkv.view(-1)[:T * 2 * D].view(T, 2 * D)  # (qk | v) rows, 512 wide

@@ -64,10 +64,19 @@ class GML(nn.Module):
         self.precision = 'bf16x3'  # 'bf16x3' | 'bf16' (tcgen05) | 'fp32' (CUDA cores); see nets/sfd2.py
         self.eval()
 
-    def set_precision(self, precision: str):
-        assert precision in ('bf16x3', 'bf16', 'fp32')
+    def set_precision(self, precision: str, attention_probs: str = 'split'):
+        """``attention_probs``: 'split' = the softmax probabilities go to the P.V tensor-core product as bf16 hi / lo planes
+        (parity mode), 'f16' = as one IEEE fp16 plane against fp16 hi / lo V planes (csrc/attention_tc.cu, P16: part of the
+        mixed mode; tensor-core precisions only)."""
+        assert precision in ('bf16x3', 'bf16', 'fp32') and attention_probs in ('split', 'f16')
         self.precision = precision
+        self.attention_probs = attention_probs
         return self
+
+    def _workspace(self, tokens: int, device):
+        ws = B.Workspace(tokens, device, {'fp32': 0, 'bf16': 1, 'bf16x3': 3}[self.precision])
+        ws.p16 = bool(ws.split) and getattr(self, 'attention_probs', 'split') == 'f16' and ops.ATT_P16_ALLOWED
+        return ws
 
     @property
     def _split(self) -> int:
@@ -162,7 +171,7 @@ class GML(nn.Module):
         if m == 0 or n == 0:
             raise ValueError('GML needs at least one keypoint per set (the reference fails on empty sets too)')
         cos, sin = self._encode(pk, data)
-        ws = B.Workspace(b * (m + n), d0.device, self._split)
+        ws = self._workspace(b * (m + n), d0.device)
         self._input_tokens(pk, ws, d0, d1)
         seg0, seg1 = (0, b, m), (b * m, b, n)
         # padded batches (extension of the reference dict, which has no batch-with-padding notion: its callers run one pair

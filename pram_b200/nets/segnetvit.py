@@ -58,10 +58,19 @@ class SegNetViT(nn.Module):
         self.precision = 'bf16x3'  # 'bf16x3' | 'bf16' (tcgen05) | 'fp32' (CUDA cores); see nets/sfd2.py
         self.eval()
 
-    def set_precision(self, precision: str):
-        assert precision in ('bf16x3', 'bf16', 'fp32')
+    def set_precision(self, precision: str, attention_probs: str = 'split'):
+        """``attention_probs``: 'split' = the softmax probabilities go to the P.V tensor-core product as bf16 hi / lo planes
+        (parity mode), 'f16' = as one IEEE fp16 plane against fp16 hi / lo V planes (csrc/attention_tc.cu, P16: part of the
+        mixed mode; tensor-core precisions only)."""
+        assert precision in ('bf16x3', 'bf16', 'fp32') and attention_probs in ('split', 'f16')
         self.precision = precision
+        self.attention_probs = attention_probs
         return self
+
+    def _workspace(self, tokens: int, device):
+        ws = B.Workspace(tokens, device, {'fp32': 0, 'bf16': 1, 'bf16x3': 3}[self.precision])
+        ws.p16 = bool(ws.split) and getattr(self, 'attention_probs', 'split') == 'f16' and ops.ATT_P16_ALLOWED
+        return ws
 
     def _apply(self, fn, *a, **k):
         self._packed = None
@@ -98,8 +107,7 @@ class SegNetViT(nn.Module):
             cos, sin = ops.posenc(data['keypoints'], w, h, pk['Wr'])
         else:
             raise ValueError('Require image shape for keypoint coordinate normalization')
-        split = {'fp32': 0, 'bf16': 1, 'bf16x3': 3}[self.precision]
-        ws = B.Workspace(T, desc.device, split)
+        ws = self._workspace(T, desc.device)
         B.input_tokens(ws, pk, desc.reshape(T, dd), 0)
         seg = [(0, b, n)]
         # ``num_keypoints`` [B] (extension for padded batches): tokens >= num_keypoints[b] are padding and get no attention

@@ -258,6 +258,16 @@ def split_bf16(x: Tensor, with_lo: bool = True) -> Split:
     return Split(hi, lo)
 
 
+def split_f16(x: Tensor, with_lo: bool = True) -> Split:
+    """fp32 -> IEEE fp16 hi / lo planes (held in bfloat16-typed tensors: 2-byte elements for the TMA descriptors) -- the V
+    operand of ``attention_tc(v_f16=True)``."""
+    x = _f32c(x)
+    hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi) if with_lo else None
+    call('pram_split_f16', ptr(x), ptr(hi), ptr(lo), x.numel(), stream_ptr())
+    return Split(hi, lo)
+
+
 def split_bf16_into(x: Tensor, out: Split) -> Split:
     """Same as split_bf16 but into preallocated planes (x contiguous fp32, same numel)."""
     call('pram_split_bf16', ptr(x), ptr(out.hi), ptr(out.lo), x.numel(), stream_ptr())
@@ -323,6 +333,7 @@ def gemm_tc(a: Split, a_ld: int, in_w: int, in_h: int, in_planes: int, cin: int,
                 setattr(A, name + '_hi', sp.hi.data_ptr())
                 setattr(A, name + '_lo', sp.lo.data_ptr() if sp.lo is not None else None)
         A.seg_split, A.seg_n0, A.seg_n1 = qkv['seg_split'], qkv['seg_n0'], qkv['seg_n1']
+        A.v_f16 = int(bool(qkv.get('v_f16', False)))
     A.cluster = GEMM_CLUSTER
     A.l2_prefetch = GEMM_L2_PREFETCH
     A.f16 = int(f16)
@@ -450,6 +461,8 @@ def layernorm_gelu_split(x: Tensor, gamma: Tensor, beta: Tensor, c: int, out: Sp
 # ---- tensor-core flash attention ---------------------------------------------------------------------
 
 ATT_KV_TILE = int(_os.environ.get('PRAM_ATT_KV_TILE', '0'))  # key-tile variant of pram_attention_tc: 0 = auto, 64, 128
+# PRAM_ATT_P16=0 forces bf16 hi / lo attention probabilities even where a network asked for the fp16 plane (A/B, bisecting)
+ATT_P16_ALLOWED = _os.environ.get('PRAM_ATT_P16', '1') != '0' 
 
 
 def attention_prep(qkv: Tensor, nparts: int, b: int, n: int, heads: int, cos: Optional[Tensor], sin: Optional[Tensor],
@@ -468,15 +481,38 @@ def attention_prep(qkv: Tensor, nparts: int, b: int, n: int, heads: int, cos: Op
     return q, k, vt, n_pad
 
 
+def lse_ld(n: int) -> int:
+    """Row stride of the attention row-statistics buffers: whole 128-column tiles (read with 16-byte loads)."""
+    return (n + 127) // 128 * 128
+
+
 def attention_tc(q: Split, k: Split, vt: Split, b: int, heads: int, nq: int, nk: int, nk_pad: int, scale: float,
                  out_f32: Optional[Tensor], out_bf: Optional[Split], out_ld: int, split: int, v_mn: bool = False,
-                 nk_counts: Optional[Tensor] = None):
+                 nk_counts: Optional[Tensor] = None, lse_out: Optional[Tensor] = None, v_f16: bool = False):
     """``vt`` is V^T [b*heads, 64, nk_pad] (v_mn=False) or V itself [b*heads, nk, 64] (v_mn=True).  ``nk_counts`` [b] int32:
-    keys >= nk_counts[i] of batch element i are padding and receive no attention."""
-    call('pram_attention_tc', ptr(q.hi), ptr(q.lo), ptr(k.hi), ptr(k.lo), ptr(vt.hi), ptr(vt.lo), b, heads, nq, nk, nk_pad,
-         float(scale), ptr(out_f32), ptr(out_bf.hi) if out_bf is not None else None,
-         ptr(out_bf.lo) if (out_bf is not None and out_bf.lo is not None) else None, out_ld, split, ATT_KV_TILE, int(v_mn),
-         ptr(nk_counts), stream_ptr())
+    keys >= nk_counts[i] of batch element i are padding and receive no attention.  ``lse_out`` [b*heads, lse_ld(nq)] fp32
+    (optional) receives the log2-domain log-sum-exp of every query row (input of ``attention_colsum_tc``).  ``v_f16``: the V
+    planes hold IEEE fp16 hi / lo (``split_f16`` / the qkv epilogue with ``v_f16``) and P is fed back as one fp16 plane."""
+    args = (ptr(q.hi), ptr(q.lo), ptr(k.hi), ptr(k.lo), ptr(vt.hi), ptr(vt.lo), b, heads, nq, nk, nk_pad,
+            float(scale), ptr(out_f32), ptr(out_bf.hi) if out_bf is not None else None,
+            ptr(out_bf.lo) if (out_bf is not None and out_bf.lo is not None) else None, out_ld, split, ATT_KV_TILE,
+            int(v_mn) | (2 if v_f16 else 0), ptr(nk_counts))
+    if lse_out is None:
+        call('pram_attention_tc', *args, stream_ptr())
+    else:
+        call('pram_attention_tc_lse', *args, ptr(lse_out), lse_out.shape[-1], stream_ptr())
+
+
+def attention_colmean_tc(keys: Split, queries: Split, b: int, heads: int, nkeys: int, nqueries: int, scale: float,
+                         lse: Tensor, colsum: Tensor, out: Tensor, out_stride: int, split: int,
+                         nq_counts: Optional[Tensor] = None):
+    """Mean attention every key receives (over heads and valid queries) -> out[(b*nkeys + j) * out_stride], on tcgen05:
+    column sums of softmax(Q K^T) from S^T tiles and the queries' row statistics ``lse`` (``attention_tc(lse_out=...)``),
+    then a fixed-order reduction over heads.  ``colsum`` [b*heads, >= nkeys] fp32 scratch.  Reference nets/adagml.py:148, 229."""
+    call('pram_attention_colsum_tc', ptr(keys.hi), ptr(keys.lo), ptr(queries.hi), ptr(queries.lo), b, heads, nkeys, nqueries,
+         float(scale), ptr(lse), lse.shape[-1], ptr(colsum), colsum.shape[-1], split, ATT_KV_TILE, ptr(nq_counts), stream_ptr())
+    call('pram_colmean_reduce', ptr(colsum), colsum.shape[-1], b, heads, nkeys, nqueries, ptr(nq_counts), ptr(out), out_stride,
+         stream_ptr())
 
 
 # ---- K19: batched PnP RANSAC -------------------------------------------------------------------------

@@ -250,6 +250,112 @@ def test_adagml_pruning_vs_oracle(lib, dev, precision):
         net({k: (v.to(dev).repeat(2, 1, 1) if torch.is_tensor(v) and v.dim() == 3 else v) for k, v in data.items()})
 
 
+def _adagml_case2(seed, m, n):
+    g = torch.Generator().manual_seed(seed)
+    d0 = torch.nn.functional.normalize(torch.randn(1, m, 128, generator=g), dim=-1)
+    src = torch.randint(0, m, (n,), generator=g)
+    d1 = d0[:, src] + 0.02 * torch.randn(1, n, 128, generator=g)
+    k0 = torch.rand(1, m, 2, generator=g) * torch.tensor([640., 480.])
+    return {'descriptors0': d0, 'descriptors1': d1, 'keypoints0': k0, 'keypoints1': k0[:, src],
+            'scores0': torch.rand(1, m, generator=g), 'scores1': torch.rand(1, n, generator=g),
+            'image_shape0': (1, 3, 640, 480), 'image_shape1': (1, 3, 640, 480)}
+
+
+def _agree(out_i, out_s, ref, min_frac=0.97):
+    """Device result vs the oracle for one pair: a confidence within ~1e-4 of a pruning threshold may flip a token, which
+    perturbs its neighbours' scores slightly -- so almost all (not all) entries must agree."""
+    decisive = (ref['matching_scores0'] - 0.2).abs() > 2e-2
+    same = (out_i[decisive] == ref['matches0'][decisive]).float().mean().item()
+    close = ((out_s - ref['matching_scores0']).abs() < 2e-2).float().mean().item()
+    assert same >= min_frac and close >= min_frac, (same, close)
+
+
+def _adagml_state(kind):
+    """'seeded': random GML + calibrated pooling (prunes over layers 1-2, exits at layer 4, no confident matches);
+    'shipped': the shipped GML weights + calibrated pooling (real matches; pairs exit at layer 1 or run all 9 layers)."""
+    if kind == 'seeded':
+        return RL.calibrated_adagml_state()
+    g = RL.load_gml_state()
+    if g is None:
+        pytest.skip('GML checkpoint not staged')
+    sd = RL.calibrated_adagml_state(gain=8.0, bias=0.15)
+    sd.update(g)
+    return sd
+
+
+@pytest.mark.parametrize('kind', ['seeded', 'shipped'])
+def test_adagml_device_path_vs_oracle_and_host_path(lib, dev, kind):
+    """K17 on the device (csrc/adagml_ops.cu): pruning by stable compaction with per-pair token counts, stop flag + latched
+    exit state, mean attention from the tcgen05 kernel -- against the oracle (pinned to the reference module) and against
+    the reference-structured path of this repo (host decision per layer, boolean-mask gathers)."""
+    from pram_b200.nets.adagml import AdaGML
+    sd = _adagml_state(kind)
+    data = _adagml_case()
+    ref = O.adagml_forward(sd, data, return_trace=True)
+    net = AdaGML({})
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).set_precision('bf16x3')
+    gdata = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}
+    out = net.produce_matches_batched(gdata, check=True)
+    tr = net.last_trace
+    assert int(out['stop_layer'][0]) == ref['last_layer']
+    assert len(tr) == len(ref['trace'])
+    for (l0, a0, b0), (l1, a1, b1) in zip(tr, ref['trace']):
+        assert l0 == l1 and abs(a0 - a1) <= 4 and abs(b0 - b1) <= 4
+    assert int(out['num_tokens0'][0]) == tr[-1][1] and int(out['num_tokens1'][0]) == tr[-1][2]
+    _agree(out['matches0'].cpu(), out['matching_scores0'].cpu(), ref)
+    # pruned tokens come back unmatched with score exactly 0 like the reference's scatter (nets/adagml.py:389-394)
+    gone = ref['matching_scores0'][0] == 0
+    assert gone.sum() >= 400 - ref['trace'][-1][1]
+    assert ((out['matching_scores0'][0].cpu() == 0) == gone).float().mean() > 0.98
+    # the launch predicate (kernels of the layers after the exit return at once) is an optimisation only: the exit state was
+    # latched, so running those layers for nothing gives the same bits
+    net.config['device_early_exit'] = False
+    full = net.produce_matches_batched(gdata, check=True)
+    assert torch.equal(full['matches0'], out['matches0']) and torch.equal(full['matching_scores0'], out['matching_scores0'])
+    net.config['device_pruning'] = False
+    host = net(gdata)
+    assert len(net.last_trace) == len(tr)
+    _agree(out['matches0'].cpu(), out['matching_scores0'].cpu(),
+           {'matches0': host['matches0'].cpu(), 'matching_scores0': host['matching_scores0'].cpu()})
+
+
+def test_adagml_device_path_batched_pairs(lib, dev):
+    """A batch of DIFFERENT pairs (one exits early, one runs on with heavy pruning, one too small to be pruned, padded to the
+    common size) through the device path == each pair alone through the oracle: the reference cannot batch AdaGML at all
+    (boolean-mask indexing, nets/adagml.py:358)."""
+    from pram_b200.nets.adagml import AdaGML
+    sd = _adagml_state('shipped')
+    cases = [_adagml_case(), _adagml_case2(5, 400, 330), _adagml_case2(9, 200, 180), _adagml_case2(13, 300, 300)]
+    refs = [O.adagml_forward(sd, c, return_trace=True) for c in cases]
+    m = max(c['descriptors0'].shape[1] for c in cases)
+    n = max(c['descriptors1'].shape[1] for c in cases)
+
+    def pad(t, size):
+        out = torch.zeros((1, size) + tuple(t.shape[2:]))
+        out[:, :t.shape[1]] = t
+        return out
+    batch = {k: torch.cat([pad(c[k], m if k.endswith('0') else n) for c in cases]).to(dev)
+             for k in ('descriptors0', 'descriptors1', 'keypoints0', 'keypoints1')}
+    batch['image_shape0'] = batch['image_shape1'] = (1, 3, 640, 480)
+    batch['num_keypoints0'] = torch.tensor([c['descriptors0'].shape[1] for c in cases], dtype=torch.int32)
+    batch['num_keypoints1'] = torch.tensor([c['descriptors1'].shape[1] for c in cases], dtype=torch.int32)
+    net = AdaGML({})
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).set_precision('bf16x3')
+    out = net.produce_matches_batched(batch, check=True)
+    stop = out['stop_layer'].cpu().tolist()
+    trace = out['token_trace'].cpu()
+    assert len(set(r['last_layer'] for r in refs)) > 1, 'the cases should exit at different layers'
+    for i, (c, r) in enumerate(zip(cases, refs)):
+        mi = c['descriptors0'].shape[1]
+        assert stop[i] == r['last_layer'], (i, stop, [x['last_layer'] for x in refs])
+        for (l, a, b_) in r['trace']:
+            assert abs(int(trace[l, 0, i]) - a) <= 4 and abs(int(trace[l, 1, i]) - b_) <= 4
+        _agree(out['matches0'][i, :mi].cpu()[None], out['matching_scores0'][i, :mi].cpu()[None], r)
+        assert (out['matches0'][i, mi:] == -1).all() and (out['matching_scores0'][i, mi:] == 0).all()
+
+
 def test_extract_sfd2_return_vs_oracle(lib, dev, golden):
     """Offline export variant (NMS radius 3, strict threshold, score-descending, x/(w/2)-1 sampling)."""
     if RL.weight_path(RL.SFD2_WEIGHT) is None:

@@ -252,10 +252,12 @@ def test_conv1a_tc(ops, dev, split, b, h, w):
     assert _relerr(outs[True], ref) < tol
 
 
+@pytest.mark.parametrize('p16', [False, True])
 @pytest.mark.parametrize('kv_tile', [64, 128])
 @pytest.mark.parametrize('b,nq,nk', [(1, 128, 128), (2, 75, 130), (1, 1024, 1024), (2, 300, 1000), (1, 4096, 1024)])
-def test_attention_tc_kv_tile_variants(ops, dev, kv_tile, b, nq, nk):
-    """Both key-tile variants of the flash-attention kernel (64: two CTAs per SM, 128: one) vs torch fp32."""
+def test_attention_tc_kv_tile_variants(ops, dev, kv_tile, b, nq, nk, p16):
+    """Both key-tile variants of the flash-attention kernel (64: two CTAs per SM, 128: one) vs torch fp32, with the
+    probabilities fed back as bf16 hi / lo planes (V bf16 planes) and as one fp16 plane (V fp16 planes, ``p16``)."""
     g = torch.Generator().manual_seed(nq + nk + kv_tile)
     h = 4
     q, k, v = (torch.randn(b, h, n, 64, generator=g) for n in (nq, nk, nk))
@@ -263,24 +265,26 @@ def test_attention_tc_kv_tile_variants(ops, dev, kv_tile, b, nq, nk):
     ref = torch.einsum('bhij,bhjd->bhid', attn, v).transpose(1, 2).flatten(-2)
     Q = ops.split_bf16(q.reshape(b * h, nq, 64).to(dev), True)
     K = ops.split_bf16(k.reshape(b * h, nk, 64).to(dev), True)
-    V = ops.split_bf16(v.reshape(b * h, nk, 64).to(dev), True)
+    splitv = ops.split_f16 if p16 else ops.split_bf16
+    V = splitv(v.reshape(b * h, nk, 64).to(dev), True)
     nk_pad = (nk + 7) // 8 * 8
     vt = torch.zeros(b, h, 64, nk_pad)
     vt[..., :nk] = v.transpose(-1, -2)
-    VT = ops.split_bf16(vt.reshape(b * h, 64, nk_pad).to(dev), True)
+    VT = splitv(vt.reshape(b * h, 64, nk_pad).to(dev), True)
     ops.ATT_KV_TILE = kv_tile
     try:
         out = torch.zeros(b, nq, 256, device=dev)
         obf = ops.empty_split((b, nq, 256), dev, True)
-        ops.attention_tc(Q, K, V, b, h, nq, nk, nk, 0.125, out, obf, 256, 3, v_mn=True)
+        ops.attention_tc(Q, K, V, b, h, nq, nk, nk, 0.125, out, obf, 256, 3, v_mn=True, v_f16=p16)
         out2 = torch.zeros(b, nq, 256, device=dev)
-        ops.attention_tc(Q, K, VT, b, h, nq, nk, nk_pad, 0.125, out2, None, 256, 3)
+        ops.attention_tc(Q, K, VT, b, h, nq, nk, nk_pad, 0.125, out2, None, 256, 3, v_f16=p16)
         torch.cuda.synchronize()
     finally:
         ops.ATT_KV_TILE = 0
-    assert _relerr(out.cpu(), ref) < 2e-4
-    assert _relerr(obf.float().cpu(), ref) < 2e-4
-    assert _relerr(out2.cpu(), ref) < 2e-4, 'V^T (K-major) operand path'
+    tol = 6e-4 if p16 else 2e-4   # one fp16 probability plane: softmax weights exact to 2^-12 relative (bf16 hi / lo: 2^-17)
+    assert _relerr(out.cpu(), ref) < tol
+    assert _relerr(obf.float().cpu(), ref) < tol
+    assert _relerr(out2.cpu(), ref) < tol, 'V^T (K-major) operand path'
 
 
 @pytest.mark.parametrize('split', [1, 3])
@@ -331,3 +335,51 @@ def test_mlp_block_tc(ops, dev, split, rows):
     assert torch.equal(o1.hi, o2.hi) and (not lo or torch.equal(o1.lo, o2.lo))
     ref_b = (ref - x) + cat_bf.float()[:, :256].cpu()  # residual = hi + lo of x (exact in split 3 up to 2^-17)
     assert _relerr(o1.float()[:, :256].cpu(), ref_b) < (tol if lo else 4e-2)
+
+
+@pytest.mark.parametrize('kv_tile', [64, 128])
+@pytest.mark.parametrize('split', [3, 1])
+@pytest.mark.parametrize('b,nq,nk,counts', [(1, 128, 128, False), (2, 75, 130, False), (2, 300, 1000, True), (1, 1024, 400, True),
+                                            (3, 400, 400, True)])
+def test_attention_colmean_tc(ops, dev, split, kv_tile, b, nq, nk, counts):
+    """AdaGML's mean attention per key (nets/adagml.py:148: mean over heads, then over queries) on the tensor cores: row
+    statistics from the flash kernel + column sums from S^T tiles, vs torch fp32 -- with ragged sizes and with per-batch
+    counts of valid queries / keys (padding takes no part on either side)."""
+    g = torch.Generator().manual_seed(nq * 3 + nk + kv_tile)
+    h = 4
+    q, k, v = (torch.randn(b, h, n, 64, generator=g) for n in (nq, nk, nk))
+    qc = torch.tensor([nq - 17 * i for i in range(b)], dtype=torch.int32) if counts else None
+    kc = torch.tensor([nk - 29 * i - 3 for i in range(b)], dtype=torch.int32) if counts else None
+    ref = torch.zeros(b, nk)
+    ctx_ref = torch.zeros(b, nq, 256)
+    for i in range(b):
+        nqi, nki = (int(qc[i]), int(kc[i])) if counts else (nq, nk)
+        attn = torch.softmax(torch.einsum('hid,hjd->hij', q[i, :, :nqi], k[i, :, :nki]) * 0.125, -1)
+        ref[i, :nki] = attn.mean(0).mean(0)
+        ctx_ref[i, :nqi] = torch.einsum('hij,hjd->hid', attn, v[i, :, :nki]).transpose(0, 1).flatten(-2)
+    lo = split == 3
+    Q = ops.split_bf16(q.reshape(b * h, nq, 64).to(dev), lo)
+    K = ops.split_bf16(k.reshape(b * h, nk, 64).to(dev), lo)
+    p16 = bool(b & 1)  # probabilities as one fp16 plane (V as fp16 planes) on some of the cases
+    V = (ops.split_f16 if p16 else ops.split_bf16)(v.reshape(b * h, nk, 64).to(dev), lo)
+    ops.ATT_KV_TILE = kv_tile
+    try:
+        out = torch.zeros(b, nq, 256, device=dev)
+        lse = torch.full((b * h, ops.lse_ld(nq)), float('nan'), device=dev)
+        colsum = torch.full((b * h, ops.lse_ld(nk)), float('nan'), device=dev)
+        cm = torch.full((b * nk, 2), float('nan'), device=dev)
+        qcd, kcd = (qc.to(dev), kc.to(dev)) if counts else (None, None)
+        ops.attention_tc(Q, K, V, b, h, nq, nk, nk, 0.125, out, None, 256, split, v_mn=True, nk_counts=kcd, lse_out=lse,
+                         v_f16=p16)
+        ops.attention_colmean_tc(K, Q, b, h, nk, nq, 0.125, lse, colsum, cm[:, 1], 2, split, nq_counts=qcd)
+        torch.cuda.synchronize()
+    finally:
+        ops.ATT_KV_TILE = 0
+    got = cm[:, 1].view(b, nk).cpu()
+    tol = (6e-4 if p16 else 2e-4) if split == 3 else 2e-2
+    for i in range(b):
+        nqi, nki = (int(qc[i]), int(kc[i])) if counts else (nq, nk)
+        assert _relerr(out[i, :nqi].cpu(), ctx_ref[i, :nqi]) < tol
+        assert _relerr(got[i, :nki], ref[i, :nki]) < (5e-4 if split == 3 else 3e-2)
+        assert abs(float(got[i, :nki].sum()) - 1.0) < (1e-3 if split == 3 else 2e-2)  # every query row sums to 1
+    assert torch.isnan(cm[:, 0]).all()  # the other column of the [T, 2] pooling input is untouched

@@ -29,6 +29,8 @@ flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 MODES = [
     ('bf16x3 everywhere (parity mode)', dict(sfd2='bf16x3', desc=None, vit='bf16x3', gml='bf16x3')),
     ('descriptor head fp16 x1', dict(sfd2='bf16x3', desc='f16', vit='bf16x3', gml='bf16x3')),
+    ('attention probabilities fp16 x1 (SegNetViT + GML)', dict(sfd2='bf16x3', desc=None, vit='bf16x3', gml='bf16x3', probs='f16')),
+    ('mixed mode = descriptor head fp16 x1 + attention probabilities fp16 x1', dict(sfd2='bf16x3', desc='f16', vit='bf16x3', gml='bf16x3', probs='f16')),
     ('SegNetViT bf16 x1', dict(sfd2='bf16x3', desc=None, vit='bf16', gml='bf16x3')),
     ('GML bf16 x1', dict(sfd2='bf16x3', desc=None, vit='bf16x3', gml='bf16')),
     ('descriptor head fp16 + SegNetViT bf16 + GML bf16', dict(sfd2='bf16x3', desc='f16', vit='bf16', gml='bf16')),
@@ -41,7 +43,7 @@ def build(m):
     sfd2 = ResNet4x(); sfd2.load_state_dict(sd_sfd2, strict=True)
     vit = SegNetViT({'n_class': 113, 'n_layers': 15, 'output_dim': 1024, 'descriptor_dim': 256}); vit.load_state_dict(sd_vit, strict=True)
     gml = GML({}); gml.load_state_dict(sd_gml, strict=True)
-    sfd2.set_precision(m['sfd2'], m['desc']); vit.set_precision(m['vit']); gml.set_precision(m['gml'])
+    sfd2.set_precision(m['sfd2'], m['desc']); vit.set_precision(m['vit'], m.get('probs', 'split')); gml.set_precision(m['gml'], m.get('probs', 'split'))
     return LocalizationPipeline(sfd2, vit, gml, max_keypoints=K, focal=525.0, ransac_max_error=8.0, device=dev)
 
 
