@@ -35,6 +35,12 @@ const char* pram_last_cuda_error(void);
  * *flag == 0 at execution time.  NULL clears it.  Host-side state only (no launch, no synchronisation). */
 int pram_set_launch_predicate(const int* flag);
 
+/* Programmatic dependent launch of the persistent tensor-core kernels (GEMM, attention, block tail, conv1a, grouped conv):
+ * each is scheduled while its predecessor in the stream drains and waits on the device (griddepcontrol.wait) before touching
+ * global memory.  On by default (environment PRAM_PDL=0 or pram_set_pdl(0) turns it off). */
+int pram_set_pdl(int enable);
+int pram_get_pdl(void);
+
 /* K5: softmax(65) -> drop dustbin -> 8x8 pixel shuffle.  nets/sfd2.py:294-300.
  * logits addressed as base + b*batch_stride + hc*y_stride + wc*x_stride + c*ch_stride (floats). */
 int pram_score_map(const float* logits, long long batch_stride, long long y_stride, long long x_stride,

@@ -27,6 +27,8 @@ SIGNATURES = {
     'pram_error_string': (C.c_char_p, [_I]),
     'pram_last_cuda_error': (C.c_char_p, []),
     'pram_set_launch_predicate': (_I, [_P]),
+    'pram_set_pdl': (_I, [_I]),
+    'pram_get_pdl': (_I, []),
     'pram_score_map': (_I, [_P, _L, _L, _L, _L, _I, _I, _I, _P, _P]),
     'pram_resize_bilinear': (_I, [_P, _I, _I, _I, _P, _I, _I, _P]),
     'pram_nms_candidates': (_I, [_P, _I, _I, _I, _I, _F, _F, _P, _P, _I, _P, _P, _P]),

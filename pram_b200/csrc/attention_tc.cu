@@ -54,6 +54,7 @@ struct Args {
     const float* lse_in; int ld_lse;
     float* colsum; int ld_colsum;
     const int* pred;   // launch predicate (common.cuh)
+    int pdl_early;    // 1: release the dependent launch right after this grid's own wait (common.cuh)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
     using Gm = Geo<BKV>;
     constexpr int NPART = Gm::NPART, CPT = Gm::CPT, OPT = Gm::OPT, NUM_SM_WARPS = Gm::NUM_SM_WARPS;
     constexpr uint32_t COL_S0 = Gm::COL_S0, COL_S1 = Gm::COL_S1, COL_O = Gm::COL_O, TMEM_COLS = Gm::TMEM_COLS;
-    if (pram_pred_skip(p.pred)) return;
+    if (p.pred) { pram_pdl_wait(); if (pram_pred_skip(p.pred)) return; }  // the flag is written by a predecessor kernel
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* q_s = smem;                                  // [NPL][16 KB]
@@ -254,6 +255,8 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
+    pram_pdl_wait();     // programmatic dependent launch: everything above overlapped the predecessor's drain
+    if (p.pdl_early) pram_pdl_trigger();  // all CTAs of a persistent grid are resident: the successor may be scheduled as SMs free up
 
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
@@ -660,6 +663,7 @@ static int attention_launch(int mode, const void* q_hi, const void* q_lo, const 
     a.v_mn = v_mn;
     a.nk_counts = nk_counts;
     a.pred = g_pram_pred;
+    a.pdl_early = g_pram_pdl >= 2;
     a.lse_out = lse_out; a.lse_in = lse_in; a.ld_lse = ld_lse; a.colsum = colsum; a.ld_colsum = ld_colsum;
     const int total = BH * ((Nq + BQ - 1) / BQ);
 #define PRAM_ATT_LAUNCH(SPLIT_, BKV_, MODE_, P16_)                                                                      \
@@ -669,7 +673,7 @@ static int attention_launch(int mode, const void* q_hi, const void* q_lo, const 
         if (!attr) { PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<SPLIT_, BKV_>::SMEM_BYTES)); attr = true; } \
         const int cap = Geo<BKV_>::CTAS_PER_SM * num_sms;                                                               \
         const int grid = total < cap ? total : cap;                                                                     \
-        kern<<<grid, Geo<BKV_>::NUM_THREADS, Cfg<SPLIT_, BKV_>::SMEM_BYTES, stream>>>(mq[0], mq[1], mk[0], mk[1], mv[0], mv[1], a); \
+        PRAM_CUDA(pram_launch_pdl(kern, dim3(grid), dim3(Geo<BKV_>::NUM_THREADS), Cfg<SPLIT_, BKV_>::SMEM_BYTES, stream, mq[0], mq[1], mk[0], mk[1], mv[0], mv[1], a)); \
     } while (0)
 #define PRAM_ATT_MODE(MODE_, P16_)                                                                                      \
     do {                                                                                                                \

@@ -36,6 +36,31 @@ extern unsigned long long g_pram_launches;
 extern thread_local const int* g_pram_pred;
 __device__ __forceinline__ bool pram_pred_skip(const int* pred) { return pred != nullptr && __ldg(pred) == 0; }
 
+// Programmatic dependent launch (pram_set_pdl): the persistent tensor-core kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so kernel N + 1 of a stream (also inside a captured CUDA graph) is
+// scheduled while kernel N drains: its CTAs start on every SM the moment N's CTA there exits, set up their barriers / TMEM /
+// descriptors, and only then wait (griddepcontrol.wait) for N to complete and flush.  Every kernel launched that way
+// executes pram_pdl_wait() on all threads before its first global-memory access (results AND visibility: the wait is also
+// what makes the chain N -> N + 1 -> N + 2 transitive), and calls pram_pdl_trigger() right after it so that its own
+// dependents may be scheduled as soon as all of its CTAs are resident.  Both are no-ops for a normally launched kernel.
+extern int g_pram_pdl;
+__device__ __forceinline__ void pram_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pram_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pram_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                          Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pram_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
+
 __host__ __device__ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float warp_max(float v) {

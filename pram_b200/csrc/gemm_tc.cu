@@ -55,6 +55,7 @@ struct Args {
     int seg_split, seg_n0, seg_n1, heads;
     int l2_prefetch;     // 1: pull the next tile's activation boxes into L2 one tile ahead (single-tap layers)
     const int* pred;     // launch predicate (common.cuh): the whole grid returns when *pred == 0
+    int pdl_early;    // 1: release the dependent launch right after this grid's own wait (common.cuh)
     int v_f16;           // qkv epilogue: the V planes receive IEEE fp16 hi / lo instead of bf16 hi / lo
     int f16;             // operands are IEEE fp16 (one MMA per k-step, 11-bit mantissas): A / W planes hold fp16 bits and the
                          // out_hi plane receives fp16 (out_lo unused) -- the single-pass mode of the descriptor head
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
     const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const Args p) {
     using C = Cfg<BN, SPLIT>;
-    if (pram_pred_skip(p.pred)) return;
+    if (p.pred) { pram_pdl_wait(); if (pram_pred_skip(p.pred)) return; }  // the flag is written by a predecessor kernel
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -276,6 +277,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
     if (CL == 2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
+    pram_pdl_wait();     // programmatic dependent launch: everything above overlapped the predecessor's drain
+    if (p.pdl_early) pram_pdl_trigger();  // all CTAs of a persistent grid are resident: the successor may be scheduled as SMs free up
 
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
@@ -701,16 +704,18 @@ static int launch_mode(const CUtensorMap& ah, const CUtensorMap& al, const CUten
     const int items = ((m_tiles + CL - 1) / CL) * n_tiles;
     if (CL == 1) {
         int grid = items < g_num_sms ? items : g_num_sms;
-        kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ah, al, wh, wl, a);
+        PRAM_CUDA(pram_launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, ah, al, wh, wl, a));
     } else {
         cudaLaunchConfig_t cfg = {};
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.blockDim = dim3(NUM_THREADS, 1, 1);
         cfg.dynamicSmemBytes = C::SMEM_BYTES;
         cfg.stream = stream;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        cfg.attrs = at; cfg.numAttrs = g_pram_pdl ? 2 : 1;
         if (!max_clusters) {
             cfg.gridDim = dim3(g_num_sms / CL * CL, 1, 1);
             int n = 0;
@@ -831,6 +836,7 @@ PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
     if (a->f16 && a->split != 1) return PRAM_ERR_ARG;
     k.f16 = a->f16;
     k.pred = g_pram_pred;
+    k.pdl_early = g_pram_pdl >= 2;
     k.v_f16 = a->v_f16;
     k.res_hi = (const __nv_bfloat16*)a->res_hi; k.res_lo = (const __nv_bfloat16*)a->res_lo;
     if (!a->res && a->res_hi && ((a->N % 32) || (a->res_ld % 4))) return PRAM_ERR_UNSUPPORTED;

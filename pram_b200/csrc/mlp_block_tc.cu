@@ -58,6 +58,7 @@ struct Args {
     float* out_f32; long long ld_f32;
     __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; long long ld_bf;
     const int* pred;  // launch predicate (common.cuh)
+    int pdl_early;    // 1: release the dependent launch right after this grid's own wait (common.cuh)
     long long* dbg;   // optional timeline: [CTA][tile iteration (<= 8)][32] SM clock stamps (tools/bench_block.py --timeline)
 };
 __device__ __forceinline__ void stamp(const Args& p, uint32_t it, int slot) {
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
     const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
     const __grid_constant__ CUtensorMap map_w3_hi, const __grid_constant__ CUtensorMap map_w3_lo, const Args p,
     const __grid_constant__ Tables tb) {
-    if (pram_pred_skip(p.pred)) return;
+    if (p.pred) { pram_pdl_wait(); if (pram_pred_skip(p.pred)) return; }  // the flag is written by a predecessor kernel
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
@@ -243,6 +244,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
+    pram_pdl_wait();     // programmatic dependent launch: everything above overlapped the predecessor's drain
+    if (p.pdl_early) pram_pdl_trigger();  // all CTAs of a persistent grid are resident: the successor may be scheduled as SMs free up
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -626,6 +629,7 @@ PRAM_API int pram_mlp_block_tc(const pram_mlp_block_args* a, cudaStream_t stream
     k.xa_hi = (const __nv_bfloat16*)a->a_hi; k.xa_lo = (const __nv_bfloat16*)(a->a_lo ? a->a_lo : a->a_hi); k.lda = a->lda;
     k.dbg = a->dbg;
     k.pred = g_pram_pred;
+    k.pdl_early = g_pram_pdl >= 2;
     Tables tb;
     memcpy(&tb, a->tables_host, sizeof(Tables));
     k.out_hi = (__nv_bfloat16*)a->out_hi; k.out_lo = (__nv_bfloat16*)a->out_lo; k.ld_bf = a->ld_bf;
@@ -635,12 +639,12 @@ PRAM_API int pram_mlp_block_tc(const pram_mlp_block_args* a, cudaStream_t stream
         auto kern = mlp_block_kernel<3>;
         static bool attr = false;
         if (!attr) { PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
-        kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ah, al, w1h, w1l, w3h, w3l, k, tb);
+        PRAM_CUDA(pram_launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, ah, al, w1h, w1l, w3h, w3l, k, tb));
     } else {
         auto kern = mlp_block_kernel<1>;
         static bool attr = false;
         if (!attr) { PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
-        kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ah, al, w1h, w1l, w3h, w3l, k, tb);
+        PRAM_CUDA(pram_launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, ah, al, w1h, w1l, w3h, w3l, k, tb));
     }
     PRAM_CHECK_LAUNCH();
     return PRAM_OK;

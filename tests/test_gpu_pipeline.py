@@ -235,6 +235,28 @@ def test_two_streams_equals_one_stream(case, dev):
     _assert_same(one, case['out'])
 
 
+def test_programmatic_dependent_launch_modes_are_equivalent(case, lib):
+    """pram_set_pdl: 0 = plain stream order, 1 = dependent kernels scheduled during the predecessor's drain (default),
+    2 = released as soon as the predecessor's CTAs are resident.  Only the schedule may change: eager runs and a
+    freshly captured graph must give bit-identical results in every mode."""
+    pipe, fd, smap = case['pipe'], case['fd'], case['smap']
+    saved = lib.pram_get_pdl()
+    try:
+        for mode in (0, 2, 1):
+            assert lib.pram_set_pdl(mode) == 0 and lib.pram_get_pdl() == mode
+            with torch.no_grad():
+                out = pipe.localize(fd, smap)
+            torch.cuda.synchronize()
+            _assert_same(case['out'], out)
+            pipe.capture(fd, smap)
+            for _ in range(3):
+                rep = pipe.replay()
+            torch.cuda.synchronize()
+            _assert_same(case['out'], rep)
+    finally:
+        lib.pram_set_pdl(saved)
+
+
 def test_pipeline_batch32_vs_oracle_and_batch4(case, dev):
     """The bench configuration itself (32 frames per step): frames 0-3 must equal the batch-4 run bit for bit (every
     output element is produced by the same instruction sequence whatever the batch), and three frames spread over the
