@@ -186,6 +186,7 @@ typedef struct pram_tc_args {
     int f16;                              /* 1 (split == 1): a / w planes hold IEEE fp16 and out_hi receives fp16 (single-pass fp16 mode) */
     const void* res_hi; const void* res_lo; /* residual as split-bf16 planes (when res == NULL): r = hi + lo, row stride res_ld */
     int v_f16;                            /* qkv epilogue: v_hi / v_lo receive IEEE fp16 planes (V operand of pram_attention_tc with v_f16) */
+    void* out_h16;                        /* optional extra copy of the output as ONE IEEE fp16 plane (row stride ld_bf, N % 32 == 0): operand of a following f16 layer */
 } pram_tc_args;
 int pram_gemm_tc(const pram_tc_args* args, pram_stream_t stream);
 

@@ -69,6 +69,7 @@ class TcArgs(C.Structure):
         ('q_hi', _P), ('q_lo', _P), ('k_hi', _P), ('k_lo', _P), ('v_hi', _P), ('v_lo', _P),
         ('seg_split', _I), ('seg_n0', _I), ('seg_n1', _I), ('heads', _I),
         ('cluster', _I), ('l2_prefetch', _I), ('f16', _I), ('res_hi', _P), ('res_lo', _P), ('v_f16', _I),
+        ('out_h16', _P),
     ]
 
 

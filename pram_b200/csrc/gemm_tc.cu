@@ -57,6 +57,7 @@ struct Args {
     const int* pred;     // launch predicate (common.cuh): the whole grid returns when *pred == 0
     int pdl_early;    // 1: release the dependent launch right after this grid's own wait (common.cuh)
     int v_f16;           // qkv epilogue: the V planes receive IEEE fp16 hi / lo instead of bf16 hi / lo
+    __half* out_h16;     // optional: the output once more as ONE IEEE fp16 plane (row stride ld_bf) -- feeds a single-pass fp16 layer
     int f16;             // operands are IEEE fp16 (one MMA per k-step, 11-bit mantissas): A / W planes hold fp16 bits and the
                          // out_hi plane receives fp16 (out_lo unused) -- the single-pass mode of the descriptor head
 };
@@ -374,6 +375,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
         const bool res_vec = ((p.res_ld & 3) == 0);
         const int g1 = lane >> 3, col1 = (lane & 7) * 4;   // pass-1 mapping
         const int g2 = lane >> 2, col2 = (lane & 3) * 8;   // pass-2 mapping
+        // one-pass epilogue (chunk loop below) needs 16-byte accesses everywhere: checked once per kernel
+        auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+        const bool fast_ok = !p.l2norm && al16(biasp) && (!p.out_f32 || (al16(p.out_f32) && (p.ld_f32 & 3) == 0)) &&
+                             (!resp || (al16(resp) && (p.res_ld & 3) == 0)) &&
+                             (resp || !p.res_hi || (al16(p.res_hi) && al16(p.res_lo) && (p.res_ld & 7) == 0));
         int as = 0; uint32_t aphase = 0;
         for (int tile = cid; tile < total; tile += ncl) {
             const int nt = tile % n_tiles, mt = (tile / n_tiles) * CL + crank;
@@ -436,8 +442,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                                    __uint_as_float(t.y << 16) + __uint_as_float(t.w << 16),
                                    __uint_as_float(t.y & 0xffff0000u) + __uint_as_float(t.w & 0xffff0000u));
             };
+            // The same residual in the ONE-PASS mapping (4 lanes per row, 8 columns per lane; see the chunk loop): two 16-byte
+            // words per row group -- fp32: columns 0-3 / 4-7; bf16 planes: the hi words / the lo words of the 8 columns.
+            auto load_res_fast = [&](int nb, uint4 (&rf)[MODE == 1 ? 8 : 1]) {
+                if constexpr (MODE != 1) return;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int pixr = lds32(eq_pix + 4 * (i * 8 + g2));
+                    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+                    if (pixr >= 0) {
+                        if (resp) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(resp + (long long)pixr * p.res_ld + nb + col2);
+                            a = __ldg(rp);
+                            b = __ldg(rp + 1);
+                        } else {
+                            const long long o = (long long)pixr * p.res_ld + nb + col2;
+                            a = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o));
+                            if (p.res_lo) b = __ldg(reinterpret_cast<const uint4*>(p.res_lo + o));
+                        }
+                    }
+                    rf[2 * i] = a;
+                    rf[2 * i + 1] = b;
+                }
+            };
             uint4 rv[MODE == 1 ? 8 : 1];
-            if constexpr (MODE == 1) load_res(n0 + half * 32, rv);  // independent of the accumulator: overlaps the MMA tail
+            if constexpr (MODE == 1) {  // independent of the accumulator: overlaps the MMA tail
+                if (fast_ok && n0 + half * 32 + 32 <= p.N) load_res_fast(n0 + half * 32, rv);
+            }
             // MODE 2: the rotary factors of a row depend on (token, dim pair) only -- not on the head -- and this
             // warp's chunks (c = half*32 + 64 m) all cover dims half*32..+31 of head m: ONE load per tile serves
             // all four chunks and is issued before the accumulator wait (latency hidden behind the MMA).
@@ -459,22 +490,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-            if (p.l2norm) {  // both warps of the quarter scan the whole row (N <= BN <= 256)
+            if (p.l2norm) {
+                // Row norms (N <= BN <= 256): each warp of the quarter sums the squares of ITS chunks (the same chunks it
+                // stores below), the partials meet through the staging tiles (idle until the chunk loop), and half 0 publishes
+                // max(sqrt(sum), eps) per row.  The bias comes in as float4 (the per-element predicated LDG chain of the first
+                // version cost 0.33 ms of a 0.44 ms launch at the descriptor head: ncu, long-scoreboard on every FADD).
                 float ss = 0.f;
-                for (int c = 0; c < BN; c += 32) {
+                const bool bias_vec = biasp && ((reinterpret_cast<uintptr_t>(biasp) & 15) == 0);
+                for (int c = half * 32; c < BN; c += 64) {
                     if (n0 + c >= p.N) break;
                     uint32_t v[32];
                     tmem_ld32(taddr + c, v);
+                    if (n0 + c + 32 <= p.N && (bias_vec || !biasp)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        int n = n0 + c + j;
-                        if (n < p.N) {
-                            float f = __uint_as_float(v[j]) + (biasp ? __ldg(biasp + n) : 0.f);
-                            ss += f * f;
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 bb = biasp ? __ldg(reinterpret_cast<const float4*>(biasp + n0 + c) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float f0 = __uint_as_float(v[4 * j4]) + bb.x, f1 = __uint_as_float(v[4 * j4 + 1]) + bb.y;
+                            const float f2 = __uint_as_float(v[4 * j4 + 2]) + bb.z, f3 = __uint_as_float(v[4 * j4 + 3]) + bb.w;
+                            ss += f0 * f0; ss += f1 * f1; ss += f2 * f2; ss += f3 * f3;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = n0 + c + j;
+                            if (n < p.N) {
+                                const float f = __uint_as_float(v[j]) + (biasp ? __ldg(biasp + n) : 0.f);
+                                ss += f * f;
+                            }
                         }
                     }
                 }
-                if (half == 0) sts32(eq_inv + 4 * lane, __float_as_int(fmaxf(sqrtf(ss), 1e-12f)));
+                sts32(tile_a + 4 * lane, __float_as_int(ss));
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                if (half == 0) {
+                    const float other = __int_as_float(lds32(tile_a + 4u * 4096u + 4 * lane));  // the partner warp's tile
+                    sts32(eq_inv + 4 * lane, __float_as_int(fmaxf(sqrtf(ss + other), 1e-12f)));
+                }
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
             }
             if constexpr (MODE == 2) {
@@ -565,12 +616,97 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                         sts128(trow + (uint32_t)((j4 ^ (lane & 7)) << 4), make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
                                                                               __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])));
                 }
-                uint4 rcur[MODE == 1 ? 8 : 1];
-                if constexpr (MODE == 1) {
+                if (fast_ok && full32) {
+                    // ---- ONE pass in the 16-byte-store mapping (4 lanes per row, 8 columns per lane): bias, residual, ReLU, fp32 /
+                    // split-bf16 / phase-split / fp16 stores.  Covers every layer of the networks except ragged N and the L2 norm;
+                    // the generic two-pass loop below costs ~3x the instructions per chunk (ncu: the 1x1 ResBlock convolutions
+                    // were bound by the issue of their own epilogue, short-scoreboard chains on the staging tile).
+                    uint4 rcur[MODE == 1 ? 8 : 1];
+                    if constexpr (MODE == 1) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) rcur[i] = rv[i];
-                    if (c + 64 < BN) load_res(nb + 64, rv);  // prefetch the next chunk's residual
+                        for (int i = 0; i < 8; ++i) rcur[i] = rv[i];
+                        if (c + 64 < BN && nb + 64 + 32 <= p.N) load_res_fast(nb + 64, rv);  // next chunk's residual stays in flight
+                    }
+                    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                    if (biasp) {
+                        b0 = __ldg(reinterpret_cast<const float4*>(biasp + nb + col2));
+                        b1 = __ldg(reinterpret_cast<const float4*>(biasp + nb + col2 + 4));
+                    }
+                    const bool want_planes = p.out_hi || p.ps_hi;
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = i * 8 + g2;
+                        const int pixr = lds32(eq_pix + 4 * row);
+                        const uint32_t tr = tile_a + (uint32_t)row * 128u;
+                        const float4 a = lds128(tr + (uint32_t)((((col2 >> 2)) ^ (row & 7)) << 4)), bq = lds128(tr + (uint32_t)((((col2 >> 2) + 1) ^ (row & 7)) << 4));
+                        float f[8] = {a.x + b0.x, a.y + b0.y, a.z + b0.z, a.w + b0.w, bq.x + b1.x, bq.y + b1.y, bq.z + b1.z, bq.w + b1.w};
+                        if constexpr (MODE == 1) {
+                            const uint4 ra = rcur[2 * i], rb = rcur[2 * i + 1];
+                            if (resp) {
+                                f[0] += __uint_as_float(ra.x); f[1] += __uint_as_float(ra.y); f[2] += __uint_as_float(ra.z); f[3] += __uint_as_float(ra.w);
+                                f[4] += __uint_as_float(rb.x); f[5] += __uint_as_float(rb.y); f[6] += __uint_as_float(rb.z); f[7] += __uint_as_float(rb.w);
+                            } else {
+                                const uint32_t hw[4] = {ra.x, ra.y, ra.z, ra.w}, lw[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    f[2 * k] += __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
+                                    f[2 * k + 1] += __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u);
+                                }
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+                        }
+                        if (pixr < 0) continue;
+                        if (p.out_f32) {
+                            float4* op = reinterpret_cast<float4*>(p.out_f32 + (long long)pixr * p.ld_f32 + nb + col2);
+                            op[0] = make_float4(f[0], f[1], f[2], f[3]);
+                            op[1] = make_float4(f[4], f[5], f[6], f[7]);
+                        }
+                        if (p.out_h16 || (SPLIT == 1 && p.f16 && want_planes)) {
+                            uint32_t hh[4];
+#pragma unroll
+                            for (int k = 0; k < 8; k += 2) {
+                                const __half2 h2 = __floats2half2_rn(f[k], f[k + 1]);
+                                hh[k >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                            }
+                            const uint4 hv = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                            if (p.out_h16) *reinterpret_cast<uint4*>(p.out_h16 + (long long)pixr * p.ld_bf + nb + col2) = hv;
+                            if (SPLIT == 1 && p.f16) {  // single-pass fp16 layer: the hi plane carries fp16, no lo plane
+                                if (p.out_hi) *reinterpret_cast<uint4*>(p.out_hi + (long long)pixr * p.ld_bf + nb + col2) = hv;
+                                if (p.ps_hi) *reinterpret_cast<uint4*>(p.ps_hi + (long long)lds32(eq_ps + 4 * row) * p.ld_ps + nb + col2) = hv;
+                                continue;
+                            }
+                        }
+                        if (want_planes) {
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int k = 0; k < 8; k += 2) {
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[k], f[k + 1]);
+                                const uint32_t u = *reinterpret_cast<uint32_t*>(&h2);
+                                __nv_bfloat162 l2 = __floats2bfloat162_rn(f[k] - __uint_as_float(u << 16), f[k + 1] - __uint_as_float(u & 0xffff0000u));
+                                hi[k >> 1] = u;
+                                lo[k >> 1] = *reinterpret_cast<uint32_t*>(&l2);
+                            }
+                            const uint4 hv = make_uint4(hi[0], hi[1], hi[2], hi[3]), lv = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            if (p.out_hi) {
+                                *reinterpret_cast<uint4*>(p.out_hi + (long long)pixr * p.ld_bf + nb + col2) = hv;
+                                if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + (long long)pixr * p.ld_bf + nb + col2) = lv;
+                            }
+                            if (p.ps_hi) {
+                                const long long pp = lds32(eq_ps + 4 * row);
+                                *reinterpret_cast<uint4*>(p.ps_hi + pp * p.ld_ps + nb + col2) = hv;
+                                if (p.ps_lo) *reinterpret_cast<uint4*>(p.ps_lo + pp * p.ld_ps + nb + col2) = lv;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    continue;
                 }
+                uint4 rcur[MODE == 1 ? 8 : 1];
+                if constexpr (MODE == 1) load_res(nb, rcur);  // generic path (ragged N, L2 norm, unaligned rows): loaded in place
                 __syncwarp();
                 // ---- pass 1 (fp32 mapping: 8 lanes per row): bias, residual, ReLU, L2 norm, fp32 store ----
                 {
@@ -603,17 +739,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                                 for (int k = 0; k < 4; ++k) if (nb + col1 + k < p.N) op[k] = f[k];
                             }
                         }
-                        if (p.out_hi || p.ps_hi) sts128(tp, make_float4(f[0], f[1], f[2], f[3]));
+                        if (p.out_hi || p.ps_hi || p.out_h16) sts128(tp, make_float4(f[0], f[1], f[2], f[3]));
                     }
                 }
                 // ---- pass 2 (bf16 mapping: 4 lanes per row): split into hi / lo planes, 16-byte stores ----
-                if (p.out_hi || p.ps_hi) {  // requires N % 32 == 0 (checked on the host)
+                if (p.out_hi || p.ps_hi || p.out_h16) {  // requires N % 32 == 0 (checked on the host)
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int row = i * 8 + g2;
                         const int pixr = lds32(eq_pix + 4 * row);
-                        uint32_t hi[4], lo[4];
+                        uint32_t hi[4], lo[4], hh[4] = {0u, 0u, 0u, 0u};
                         {
                             const uint32_t tr = tile_a + (uint32_t)row * 128u;
                             const float4 a = lds128(tr + (uint32_t)((((col2 >> 2)) ^ (row & 7)) << 4)), bq = lds128(tr + (uint32_t)((((col2 >> 2) + 1) ^ (row & 7)) << 4));
@@ -633,8 +769,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                                 hi[k >> 1] = u;
                                 lo[k >> 1] = *reinterpret_cast<uint32_t*>(&l2);
                             }
+                            if (p.out_h16) {
+#pragma unroll
+                                for (int k = 0; k < 8; k += 2) {
+                                    const __half2 h2 = __floats2half2_rn(fv[k], fv[k + 1]);
+                                    hh[k >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                                }
+                            }
                         }
                         if (pixr >= 0) {
+                            if (p.out_h16) {
+                                *reinterpret_cast<uint4*>(p.out_h16 + (long long)pixr * p.ld_bf + nb + col2) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                            }
                             if (p.out_hi) {
                                 *reinterpret_cast<uint4*>(p.out_hi + (long long)pixr * p.ld_bf + nb + col2) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                                 if (p.out_lo)
@@ -780,6 +926,7 @@ struct pram_tc_args {
     int f16;                              // 1 (split == 1 only): a / w planes hold IEEE fp16, out_hi receives fp16 -- single-pass fp16 mode
     const void* res_hi; const void* res_lo;  // residual as split-bf16 planes (used when res == NULL; row stride res_ld, N % 32 == 0)
     int v_f16;                            // qkv epilogue: v_hi / v_lo receive IEEE fp16 planes
+    void* out_h16;                        // optional extra output: one IEEE fp16 plane, row stride ld_bf (N % 32 == 0)
 };
 
 PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
@@ -846,6 +993,8 @@ PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
     k.pred = g_pram_pred;
     k.pdl_early = g_pram_pdl >= 2;
     k.v_f16 = a->v_f16;
+    k.out_h16 = (__half*)a->out_h16;
+    if (a->out_h16 && ((a->N % 32) || (a->ld_bf % 8))) return PRAM_ERR_UNSUPPORTED;
     k.res_hi = (const __nv_bfloat16*)a->res_hi; k.res_lo = (const __nv_bfloat16*)a->res_lo;
     if (!a->res && a->res_hi && ((a->N % 32) || (a->res_ld % 4))) return PRAM_ERR_UNSUPPORTED;
     k.l2_prefetch = (a->ntaps == 1) && (a->l2_prefetch == 1);  // measured on B200: no gain (the thin GEMMs are store-bound), off unless asked for

@@ -217,16 +217,21 @@ class ResNet4x(nn.Module):
         for i in range(3):
             t = ct(cur_bf, T(f'conv4.{i}.c1'), pk[f'conv4.{i}.c1.b'], 1, 1, True, split)['bf']
             t = ops.gconv3x3_tc(t, pk[f'conv4.{i}.c2.w'], pk[f'conv4.{i}.c2.b'], True, split)
+            # the last block feeds convPa (phase-split planes), the API's mid_features (fp32) and the descriptor head: as
+            # ONE fp16 plane written by the same epilogue when that head runs single-pass fp16 (no separate cast kernel,
+            # and no hi / lo planes that nobody reads)
+            f16_tail = (i == 2) and planes_res and self.desc_precision == 'f16'
             last = ct(t, T(f'conv4.{i}.c3'), pk[f'conv4.{i}.c3.b'], 1, 1, True, split, res=None if planes_res else cur_f32,
-                      res_bf=cur_bf if planes_res else None, want_f32=(i == 2) or not planes_res, want_ps=(i == 2))
-            cur_bf, cur_f32 = last['bf'], last.get('f32')
+                      res_bf=cur_bf if planes_res else None, want_f32=(i == 2) or not planes_res, want_ps=(i == 2),
+                      want_bf=not f16_tail, want_h16=f16_tail)
+            cur_bf, cur_f32 = last.get('bf'), last.get('f32')
         h8, w8 = (h4 - 1) // 2 + 1, (w4 - 1) // 2 + 1
         p = ct(last['ps'], T('convPa.0'), pk['convPa.0.b'], 3, 2, True, split, out_shape_hw=(h8, w8))['bf']
         p = ct(p, T('convPa.3'), pk['convPa.3.b'], 3, 1, False, split)['bf']
         logits = ct(p, T('convPb'), pk['convPb.b'], 1, 1, False, split, want_f32=True, want_bf=False)['f32']
         if self.desc_precision == 'f16':
             T16 = lambda n: pk[n + '.tc16']
-            d = ops.as_f16_plane(cur_f32)   # out4 as one fp16 plane
+            d = last['h16'] if 'h16' in last else ops.as_f16_plane(cur_f32)   # out4 as one fp16 plane
             d = ct(d, T16('convDa.0'), pk['convDa.0.b'], 3, 1, True, 1, f16=True)['bf']
             d = ct(d, T16('convDa.3'), pk['convDa.3.b'], 3, 1, False, 1, f16=True)['bf']
             desc = ct(d, T16('convDb'), pk['convDb.b'], 1, 1, False, 1, want_f32=True, want_bf=False, l2norm=True, f16=True)['f32']

@@ -303,7 +303,8 @@ def gemm_tc(a: Split, a_ld: int, in_w: int, in_h: int, in_planes: int, cin: int,
             w_batch_mult: int = 0, bias: Optional[Tensor] = None, res: Optional[Tensor] = None, res_ld: int = 0,
             relu: bool = False, out_f32: Optional[Tensor] = None, ld_f32: int = 0, out_bf: Optional[Split] = None,
             ld_bf: int = 0, out_ps: Optional[Split] = None, ld_ps: int = 0, l2norm: bool = False, split: int = 3,
-            bn: int = 0, qkv: Optional[dict] = None, f16: bool = False, res_bf: Optional[Split] = None):
+            bn: int = 0, qkv: Optional[dict] = None, f16: bool = False, res_bf: Optional[Split] = None,
+            out_h16: Optional[Tensor] = None):
     """Raw launch of the tcgen05 implicit-GEMM kernel (see include/pram_b200.h: pram_gemm_tc)."""
     A = _lib.TcArgs()
     A.a_hi, A.a_lo, A.a_ld = a.hi.data_ptr(), (a.lo.data_ptr() if a.lo is not None else None), a_ld
@@ -339,13 +340,18 @@ def gemm_tc(a: Split, a_ld: int, in_w: int, in_h: int, in_planes: int, cin: int,
     A.f16 = int(f16)
     if res_bf is not None:  # residual from split-bf16 planes instead of an fp32 tensor
         A.res_hi, A.res_lo = res_bf.hi.data_ptr(), (res_bf.lo.data_ptr() if res_bf.lo is not None else None)
+    if out_h16 is not None:  # extra copy of the output as one IEEE fp16 plane (row stride ld_bf)
+        A.out_h16 = out_h16.data_ptr()
+        if out_bf is None:
+            A.ld_bf = ld_bf
     import ctypes
     call('pram_gemm_tc', ctypes.byref(A), stream_ptr())
 
 
 def conv_tc(x: Split, w: Split, bias: Optional[Tensor], ksize: int, stride: int, relu: bool, split: int,
             res: Optional[Tensor] = None, want_f32: bool = False, want_bf: bool = True, want_ps: bool = False,
-            l2norm: bool = False, out_shape_hw=None, bn: int = 0, f16: bool = False, res_bf: Optional[Split] = None):
+            l2norm: bool = False, out_shape_hw=None, bn: int = 0, f16: bool = False, res_bf: Optional[Split] = None,
+            want_h16: bool = False):
     """3x3 / 1x1 convolution on tensor cores.  x: Split [B,H,W,Cin] NHWC (stride 1) or the 2x2 phase-split
     tensor [B*4,ceil(H/2),ceil(W/2),Cin] of it (stride 2; then ``out_shape_hw`` = (Ho, Wo) of the conv).
     w: Split [taps,Cout,Cin].  Returns dict with any of 'f32' [B,Ho,Wo,Cout], 'bf' Split, 'ps' Split."""
@@ -369,9 +375,13 @@ def conv_tc(x: Split, w: Split, bias: Optional[Tensor], ksize: int, stride: int,
     if want_ps:
         ops_ps = empty_split((b * 4, (ho + 1) // 2, (wo + 1) // 2, cout), dev, with_lo=(split == 3),
                              zero=bool(ho % 2 or wo % 2))
+    # 'h16': the output once more as ONE plane of IEEE fp16 bits (bfloat16-typed storage, like as_f16_plane)
+    h16 = torch.empty((b, ho, wo, cout), device=dev, dtype=torch.bfloat16) if want_h16 else None
     tw_log2 = 4 if wo >= 16 else max(0, (wo - 1).bit_length())
     gemm_tc(x, x.shape[-1], in_w, in_h, in_planes, cin, w, taps_n, b, ho, wo, cout, taps, ppi, tw_log2, 0, bias, res,
-            cout, relu, f32, cout, obf, cout, ops_ps, cout, l2norm, split, bn, f16=f16, res_bf=res_bf)
+            cout, relu, f32, cout, obf, cout, ops_ps, cout, l2norm, split, bn, f16=f16, res_bf=res_bf, out_h16=h16)
+    if h16 is not None:
+        out['h16'] = Split(h16, None)
     if f32 is not None:
         out['f32'] = f32
     if obf is not None:

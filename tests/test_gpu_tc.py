@@ -383,3 +383,34 @@ def test_attention_colmean_tc(ops, dev, split, kv_tile, b, nq, nk, counts):
         assert _relerr(got[i, :nki], ref[i, :nki]) < (5e-4 if split == 3 else 3e-2)
         assert abs(float(got[i, :nki].sum()) - 1.0) < (1e-3 if split == 3 else 2e-2)  # every query row sums to 1
     assert torch.isnan(cm[:, 0]).all()  # the other column of the [T, 2] pooling input is untouched
+
+
+def test_conv1x1_residual_planes_fp16_copy_and_l2norm(ops, dev):
+    """ResBlock tail as the mixed mode runs it: 1x1 conv + residual from split-bf16 planes + ReLU, with the fp32 map, the
+    phase-split planes and ONE fp16 plane written by the same epilogue -- the fp16 plane must equal the separate cast of the
+    fp32 output bit for bit; then the L2-normalised descriptor projection (vector-bias row norms) on that plane."""
+    g = torch.Generator().manual_seed(5)
+    b, h, w, c = 2, 30, 40, 256
+    x = torch.randn(b, h, w, c, generator=g)
+    r = torch.randn(b, h, w, c, generator=g)
+    wt = torch.randn(1, c, c, generator=g) / c ** 0.5
+    bias = torch.randn(c, generator=g)
+    X, R, Wp = ops.split_bf16(x.to(dev)), ops.split_bf16(r.to(dev)), ops.split_bf16(wt.to(dev))
+    out = ops.conv_tc(X, Wp, bias.to(dev), 1, 1, True, 3, res_bf=R, want_f32=True, want_bf=False, want_ps=True, want_h16=True)
+    both = ops.conv_tc(X, Wp, bias.to(dev), 1, 1, True, 3, res_bf=R, want_f32=True, want_bf=True)
+    torch.cuda.synchronize()
+    ref = torch.relu(X.float().cpu() @ wt[0].t() + bias + R.float().cpu())
+    assert _relerr(out['f32'].cpu(), ref) < TOL[3]
+    assert torch.equal(out['f32'], both['f32'])
+    assert torch.equal(out['h16'].hi.view(torch.float16), ops.as_f16_plane(out['f32']).hi.view(torch.float16))
+    assert 'bf' not in out
+    # descriptor projection: fp16 plane in, fp32 L2-normalised rows out (N = 128 <= BN)
+    wd = (torch.randn(1, 128, c, generator=g) / c ** 0.5)
+    bd = torch.randn(128, generator=g)
+    Wd = ops.Split(wd.half().to(dev).view(torch.bfloat16), None)
+    d = ops.conv_tc(out['h16'], Wd, bd.to(dev), 1, 1, False, 1, want_f32=True, want_bf=False, l2norm=True, f16=True)['f32']
+    torch.cuda.synchronize()
+    a16 = out['h16'].hi.view(torch.float16).float().cpu()
+    dref = torch.nn.functional.normalize(a16 @ wd.half().float()[0].t() + bd, dim=-1)
+    assert (d.cpu() - dref).abs().max().item() < 2e-5
+    assert (d.cpu().norm(dim=-1) - 1).abs().max().item() < 1e-5
