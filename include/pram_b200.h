@@ -225,6 +225,14 @@ int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k_hi, cons
                       const int* nk_counts /* optional [B]: keys >= nk_counts[b] of batch element b are padding and masked */,
                       pram_stream_t stream);
 
+/* Same launch with rotated key / value batches: query batch element b attends to the keys / values (and nk_counts entry) of
+ * batch element (b + kv_shift) mod B.  With B = 2 x pairs, kv_shift = pairs and q = k = [set 0 | set 1] this is both directions
+ * of the bidirectional cross attention (nets/gml.py:175-181) in one launch. */
+int pram_attention_tc_shift(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
+                            const void* vt_lo, int B, int heads, int Nq, int Nk, int nk_pad, float scale, float* out_f32,
+                            void* out_hi, void* out_lo, int out_ld, int split, int kv_tile, int v_mn, const int* nk_counts,
+                            int kv_shift, pram_stream_t stream);
+
 /* Same launch, additionally writing the log2-domain log-sum-exp of every query row (softmax prob = exp2(s * scale * log2 e -
  * lse)) to lse_out [B*heads][ld_lse] (ld_lse % 4 == 0, >= Nq). */
 int pram_attention_tc_lse(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,

@@ -93,6 +93,7 @@ SIGNATURES['pram_split_f16'] = (_I, [_P, _P, _P, _L, _P])
 SIGNATURES['pram_split_bf16'] = (_I, [_P, _P, _P, _L, _P])
 SIGNATURES['pram_cast_f16'] = (_I, [_P, _P, _L, _P])
 SIGNATURES['pram_attention_tc'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I, _I, _I, _I, _P, _P])
+SIGNATURES['pram_attention_tc_shift'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P])
 SIGNATURES['pram_attention_tc_lse'] = (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P])
 SIGNATURES['pram_attention_colsum_tc'] = (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _P, _I, _I, _I, _P, _P])
 SIGNATURES['pram_colmean_reduce'] = (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P])

@@ -46,6 +46,8 @@ struct Args {
     float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_ld;
     int v_mn;          // 1: V given as [BH][Nk][64] (MN-major B operand), 0: V^T [BH][64][nk_pad] (K-major)
     const int* nk_counts;  // optional [B]: valid keys of batch element b (keys >= nk_counts[b] are padding and masked)
+    int kv_shift;          // keys / values (and nk_counts) of (batch, head) index bh come from index (bh + kv_shift) mod BH:
+                           // B/2 * heads turns ONE launch over [set 0 | set 1] into both directions of the cross attention
     // MODE 0, optional: log2-domain log-sum-exp of every query row, [BH][ld_lse] (softmax prob = exp2(s * scale_log2 - lse))
     float* lse_out;
     // MODE 1 (column sums of the attention matrix, AdaGML's per-token mean attention, nets/adagml.py:148, 229): the kernel's
@@ -271,8 +273,9 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
             tma_load_3d(q_s, &map_q_hi, q_full, 0, q0, bh);
             if (SPLIT == 3) tma_load_3d(q_s + C::Q_BYTES, &map_q_lo, q_full, 0, q0, bh);
         };
+        auto kv_of = [&](int bh) { const int s = bh + p.kv_shift; return s >= p.BH ? s - p.BH : s; };
         auto load_k = [&](int t) {
-            const int bh = item_of(t / kv_tiles) / q_tiles, k0 = (t % kv_tiles) * BKV;
+            const int bh = kv_of(item_of(t / kv_tiles) / q_tiles), k0 = (t % kv_tiles) * BKV;
             const int st = t % C::K_STAGES;
             mbar_wait(&k_empty[st], ((t / C::K_STAGES) & 1) ^ 1);
             uint8_t* ks = k_s + st * C::K_STAGE;
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
             if (SPLIT == 3) tma_load_3d(ks + C::K_BYTES, &map_k_lo, &k_full[st], 0, k0, bh);
         };
         auto load_v = [&](int t) {
-            const int bh = item_of(t / kv_tiles) / q_tiles, k0 = (t % kv_tiles) * BKV;
+            const int bh = kv_of(item_of(t / kv_tiles) / q_tiles), k0 = (t % kv_tiles) * BKV;
             const int st = t & 1;
             mbar_wait(&v_empty[st], ((t >> 1) & 1) ^ 1);
             uint8_t* vs = v_s + st * C::V_STAGE;
@@ -391,7 +394,8 @@ __global__ void __launch_bounds__(Geo<BKV>::NUM_THREADS, Geo<BKV>::CTAS_PER_SM) 
             const int bh = item / q_tiles, q0 = (item % q_tiles) * BQ;
             // keys of this batch element that are real tokens: the fixed [B, K] layout of the batched pipeline pads
             // frames with fewer keypoints; a padded key must not receive attention (the reference runs n[b] tokens)
-            const int nk_b = p.nk_counts ? max(1, min(p.Nk, __ldg(p.nk_counts + bh / p.heads))) : p.Nk;
+            const int kvbh = (bh + p.kv_shift >= p.BH) ? bh + p.kv_shift - p.BH : bh + p.kv_shift;
+            const int nk_b = p.nk_counts ? max(1, min(p.Nk, __ldg(p.nk_counts + kvbh / p.heads))) : p.Nk;
             if constexpr (MODE == 1) {
                 // ---- column sums: this thread's row is a KEY, the streamed columns are the queries whose row statistics are
                 // known (lse_in), so every probability is final the moment its score is read: no running max, no P, no O
@@ -621,7 +625,8 @@ static int encode3(CUtensorMap* m, const void* base, cuuint64_t d0, cuuint64_t d
 static int attention_launch(int mode, const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
                             const void* vt_lo, int B, int heads, int Nq, int Nk, int nk_pad, float scale, float* out_f32,
                             void* out_hi, void* out_lo, int out_ld, int split, int p_swap, int v_mn, const int* nk_counts,
-                            float* lse_out, const float* lse_in, int ld_lse, float* colsum, int ld_colsum, cudaStream_t stream) {
+                            float* lse_out, const float* lse_in, int ld_lse, float* colsum, int ld_colsum, cudaStream_t stream,
+                            int kv_shift = 0) {
     using namespace fa;
     const bool p16 = (v_mn & 2) != 0;  // V planes hold IEEE fp16 hi / lo: probabilities as one fp16 plane (kernel variant P16)
     v_mn &= 1;
@@ -661,7 +666,9 @@ static int attention_launch(int mode, const void* q_hi, const void* q_lo, const 
     a.scale_log2 = scale * 1.4426950408889634f;
     a.out_f32 = out_f32; a.out_hi = (__nv_bfloat16*)out_hi; a.out_lo = (__nv_bfloat16*)out_lo; a.out_ld = out_ld;
     a.v_mn = v_mn;
+    if (kv_shift < 0 || kv_shift >= B || (kv_shift && mode != 0)) return PRAM_ERR_ARG;
     a.nk_counts = nk_counts;
+    a.kv_shift = kv_shift * heads;
     a.pred = g_pram_pred;
     a.pdl_early = g_pram_pdl >= 2;
     a.lse_out = lse_out; a.lse_in = lse_in; a.ld_lse = ld_lse; a.colsum = colsum; a.ld_colsum = ld_colsum;
@@ -693,6 +700,17 @@ PRAM_API int pram_attention_tc(const void* q_hi, const void* q_lo, const void* k
                                int v_mn, const int* nk_counts, cudaStream_t stream) {
     return attention_launch(0, q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo, B, heads, Nq, Nk, nk_pad, scale, out_f32, out_hi, out_lo,
                             out_ld, split, p_swap, v_mn, nk_counts, nullptr, nullptr, 0, nullptr, 0, stream);
+}
+
+// same with rotated key / value batches: query batch element b attends to the keys / values (and nk_counts) of batch element
+// (b + kv_shift) mod B.  B = 2 x pairs, kv_shift = pairs, q = k = [set 0 | set 1]: both directions of the GML cross attention
+// (nets/gml.py:175-181) in ONE launch -- 2048 work items fill 296 CTA slots 6.9 times instead of 2 x 3.5 (rounded up to 2 x 4).
+PRAM_API int pram_attention_tc_shift(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const void* vt_hi,
+                                     const void* vt_lo, int B, int heads, int Nq, int Nk, int nk_pad, float scale,
+                                     float* out_f32, void* out_hi, void* out_lo, int out_ld, int split, int p_swap,
+                                     int v_mn, const int* nk_counts, int kv_shift, cudaStream_t stream) {
+    return attention_launch(0, q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo, B, heads, Nq, Nk, nk_pad, scale, out_f32, out_hi, out_lo,
+                            out_ld, split, p_swap, v_mn, nk_counts, nullptr, nullptr, 0, nullptr, 0, stream, kv_shift);
 }
 
 // same, additionally writing the log2-domain log-sum-exp of every query row to lse_out [B*heads][ld_lse]

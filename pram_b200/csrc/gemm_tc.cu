@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
         const int g2 = lane >> 2, col2 = (lane & 3) * 8;   // pass-2 mapping
         // one-pass epilogue (chunk loop below) needs 16-byte accesses everywhere: checked once per kernel
         auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-        const bool fast_ok = !p.l2norm && al16(biasp) && (!p.out_f32 || (al16(p.out_f32) && (p.ld_f32 & 3) == 0)) &&
+        const bool fast_ok = al16(biasp) && (!p.out_f32 || (al16(p.out_f32) && (p.ld_f32 & 3) == 0)) &&
                              (!resp || (al16(resp) && (p.res_ld & 3) == 0)) &&
                              (resp || !p.res_hi || (al16(p.res_hi) && al16(p.res_lo) && (p.res_ld & 7) == 0));
         int as = 0; uint32_t aphase = 0;
@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                 }
                 if (fast_ok && full32) {
                     // ---- ONE pass in the 16-byte-store mapping (4 lanes per row, 8 columns per lane): bias, residual, ReLU, fp32 /
-                    // split-bf16 / phase-split / fp16 stores.  Covers every layer of the networks except ragged N and the L2 norm;
+                    // split-bf16 / phase-split / fp16 stores.  Covers every layer of the networks except ragged N;
                     // the generic two-pass loop below costs ~3x the instructions per chunk (ncu: the 1x1 ResBlock convolutions
                     // were bound by the issue of their own epilogue, short-scoreboard chains on the staging tile).
                     uint4 rcur[MODE == 1 ? 8 : 1];
@@ -658,6 +658,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                         if (p.relu) {
 #pragma unroll
                             for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+                        }
+                        if (p.l2norm) {
+                            const float d = __int_as_float(lds32(eq_inv + 4 * row));
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) f[k] = f[k] / d;
                         }
                         if (pixr < 0) continue;
                         if (p.out_f32) {

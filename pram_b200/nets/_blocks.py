@@ -22,6 +22,8 @@ D = 256
 # one fused tcgen05 kernel for proj -> mlp.0 -> LayerNorm + GELU -> mlp.3 (+ residual) (csrc/mlp_block_tc.cu);
 # PRAM_FUSED_BLOCK=0 keeps the four separate launches (A/B timing, bisecting)
 FUSED_BLOCK = os.environ.get('PRAM_FUSED_BLOCK', '1') != '0'
+# PRAM_MERGE_SETS=0: one attention launch per token set / direction as before (A/B timing, bisecting)
+MERGE_SETS = os.environ.get('PRAM_MERGE_SETS', '1') != '0'
 # AdaGML's per-token mean attention on the tensor cores (attention_tc statistics + pram_attention_colsum_tc);
 # PRAM_COLMEAN_TC=0 falls back to the fp32 CUDA-core attention kernel for those blocks (A/B, bisecting)
 COLMEAN_TC = os.environ.get('PRAM_COLMEAN_TC', '1') != '0'
@@ -228,6 +230,17 @@ def _no_counts_here(counts):
         raise _lib.PramError('per-frame keypoint counts (padded batches) are only supported on the tensor-core attention path')
 
 
+def _mergeable(segments, colmeans, counts) -> bool:
+    """Both token sets in ONE attention launch: two adjacent segments of the same shape, no mean-attention output, and
+    (for padded batches) the concatenated counts supplied as ``counts[2]`` ([2 B] int32 = counts of set 0, then of set 1)."""
+    if not MERGE_SETS or colmeans is not None or len(segments) != 2:
+        return False
+    (o0, b0, n0), (o1, b1, n1) = segments
+    if b0 != b1 or n0 != n1 or o1 != o0 + b0 * n0:
+        return False
+    return counts is None or (len(counts) > 2 and counts[2] is not None)
+
+
 def self_block(ws: Workspace, pk: Dict[str, torch.Tensor], segments: Sequence[Tuple[int, int, int]],
                cos: torch.Tensor, sin: torch.Tensor, colmeans: Optional[List[torch.Tensor]] = None,
                counts: Optional[Sequence[Optional[torch.Tensor]]] = None):
@@ -247,6 +260,15 @@ def self_block(ws: Workspace, pk: Dict[str, torch.Tensor], segments: Sequence[Tu
                'seg_split': seg_split, 'seg_n0': segments[0][2], 'seg_n1': segments[-1][2], 'v_f16': ws.p16}
         ops.linear_tc(ws.x_bf, 2 * D, T, D, pk['qkv.tc'], 3 * D, pk['qkv.b'], split=ws.split, bn=256, qkv=qkv)
         ctx, ctx_ld = ws.ctx_out()
+        if _mergeable(segments, colmeans, counts):
+            # two equally shaped, adjacent segments are one batch of 2 B elements: one launch (2048 work items at the bench
+            # shape fill the 296 CTA slots 6.9 times; two launches of 1024 are 3.5 waves each, rounded up to 4)
+            off, b, n = segments[0]
+            ops.attention_tc(ops.split_rows(ws.q_bf, off), ops.split_rows(ws.k_bf, off), ops.split_rows(ws.v_bf, off), 2 * b, HEADS,
+                             n, n, n, HDIM ** -0.5, None, ops.split_rows(ctx, off), ctx_ld, ws.split, v_mn=True, v_f16=ws.p16,
+                             nk_counts=None if counts is None else counts[2])
+            _finish_block(ws, pk)
+            return
         for si, (off, b, n) in enumerate(segments):
             q, k = ops.split_rows(ws.q_bf, off), ops.split_rows(ws.k_bf, off)
             cnt = None if counts is None else counts[si]
@@ -281,13 +303,20 @@ def cross_block(ws: Workspace, pk: Dict[str, torch.Tensor], seg0: Tuple[int, int
     ws.ctx_in_bf = use_tc
     if not use_tc:
         _no_counts_here(counts)
-    c0, c1 = (None, None) if counts is None else counts
+    c0, c1 = (None, None) if counts is None else (counts[0], counts[1])
     if use_tc:
         fused = {'mode': 2, 'scale': sc, 'q': ws.q_bf, 'v': ws.v_bf, 'seg_split': o1, 'seg_n0': m, 'seg_n1': n, 'v_f16': ws.p16}
         ops.linear_tc(ws.x_bf, 2 * D, T, D, pk['qkv.tc'], 2 * D, pk['qkv.b'], split=ws.split, bn=256, qkv=fused)
         q0, q1 = ops.split_rows(ws.q_bf, o0), ops.split_rows(ws.q_bf, o1)
         v0, v1 = ops.split_rows(ws.v_bf, o0), ops.split_rows(ws.v_bf, o1)
         ctx, ctx_ld = ws.ctx_out()
+        if _mergeable((seg0, seg1), colmeans, counts):
+            # both directions in one launch over [set 0 | set 1]: query element i attends to the keys / values (and key
+            # counts) of element (i + B) mod 2B, i.e. set 0 -> set 1 and set 1 -> set 0 (pram_attention_tc_shift)
+            ops.attention_tc(q0, q0, v0, 2 * b, HEADS, m, n, n, 1.0, None, ops.split_rows(ctx, o0), ctx_ld, ws.split, v_mn=True,
+                             v_f16=ws.p16, nk_counts=None if counts is None else counts[2], kv_shift=b)
+            _finish_block(ws, pk)
+            return
         want = colmeans is not None
         lse, colsum = ws.stats(b, m, n) if want else (None, None)
         ops.attention_tc(q0, q1, v1, b, HEADS, m, n, n, 1.0, None, ops.split_rows(ctx, o0), ctx_ld, ws.split, v_mn=True, v_f16=ws.p16,

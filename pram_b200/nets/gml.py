@@ -179,6 +179,9 @@ class GML(nn.Module):
         # takes no part in attention or in the Sinkhorn normalisation and comes back unmatched
         cnt = [self._counts(data.get('num_keypoints0'), b, d0.device), self._counts(data.get('num_keypoints1'), b, d0.device)]
         counts = cnt if (cnt[0] is not None or cnt[1] is not None) else None
+        if counts is not None and m == n:  # [2B] counts of [set 0 | set 1]: both sets go through ONE attention launch per block
+            full = lambda c, k: c if c is not None else torch.full((b,), k, device=d0.device, dtype=torch.int32)
+            counts = [cnt[0], cnt[1], torch.cat([full(cnt[0], m), full(cnt[1], n)])]
         for i in range(self.n_layers):
             B.self_block(ws, pk['self'][i], (seg0, seg1), cos, sin, counts=counts)
             B.cross_block(ws, pk['cross'][i], seg0, seg1, counts=counts)

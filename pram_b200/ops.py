@@ -498,7 +498,7 @@ def lse_ld(n: int) -> int:
 
 def attention_tc(q: Split, k: Split, vt: Split, b: int, heads: int, nq: int, nk: int, nk_pad: int, scale: float,
                  out_f32: Optional[Tensor], out_bf: Optional[Split], out_ld: int, split: int, v_mn: bool = False,
-                 nk_counts: Optional[Tensor] = None, lse_out: Optional[Tensor] = None, v_f16: bool = False):
+                 nk_counts: Optional[Tensor] = None, lse_out: Optional[Tensor] = None, v_f16: bool = False, kv_shift: int = 0):
     """``vt`` is V^T [b*heads, 64, nk_pad] (v_mn=False) or V itself [b*heads, nk, 64] (v_mn=True).  ``nk_counts`` [b] int32:
     keys >= nk_counts[i] of batch element i are padding and receive no attention.  ``lse_out`` [b*heads, lse_ld(nq)] fp32
     (optional) receives the log2-domain log-sum-exp of every query row (input of ``attention_colsum_tc``).  ``v_f16``: the V
@@ -507,7 +507,10 @@ def attention_tc(q: Split, k: Split, vt: Split, b: int, heads: int, nq: int, nk:
             float(scale), ptr(out_f32), ptr(out_bf.hi) if out_bf is not None else None,
             ptr(out_bf.lo) if (out_bf is not None and out_bf.lo is not None) else None, out_ld, split, ATT_KV_TILE,
             int(v_mn) | (2 if v_f16 else 0), ptr(nk_counts))
-    if lse_out is None:
+    if kv_shift:  # query batch element i attends to keys / values / nk_counts of element (i + kv_shift) mod b
+        assert lse_out is None
+        call('pram_attention_tc_shift', *args, int(kv_shift), stream_ptr())
+    elif lse_out is None:
         call('pram_attention_tc', *args, stream_ptr())
     else:
         call('pram_attention_tc_lse', *args, ptr(lse_out), lse_out.shape[-1], stream_ptr())

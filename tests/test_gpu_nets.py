@@ -211,6 +211,44 @@ def test_gml_random_weights_batched_vs_oracle(lib, dev, precision):
         net({'descriptors0': d0.to(dev), 'descriptors1': d1.to(dev), 'keypoints0': k0.to(dev), 'keypoints1': k1.to(dev)})
 
 
+def test_gml_both_sets_in_one_attention_launch(lib, dev):
+    """m == n: self attention of both sets and both directions of the cross attention run as ONE launch each over
+    [set 0 | set 1] (rotated key / value batches, pram_attention_tc_shift).  Must equal the per-set launches bit for bit, with
+    and without per-pair keypoint counts, and stay inside the oracle tolerance."""
+    from pram_b200.nets import _blocks as BL
+    from pram_b200.nets.gml import GML
+    sd = RL.random_gml_state(seed=7)
+    net = GML({})
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).set_precision('bf16x3')
+    g = torch.Generator().manual_seed(1)
+    b, m = 3, 200
+    d0 = torch.nn.functional.normalize(torch.randn(b, m, 128, generator=g), dim=-1)
+    d1 = torch.nn.functional.normalize(torch.randn(b, m, 128, generator=g), dim=-1)
+    d1[:, :120] = d0[:, 40:160] + 0.01 * torch.randn(b, 120, 128, generator=g)
+    k0 = torch.rand(b, m, 2, generator=g) * torch.tensor([640., 480.])
+    k1 = torch.rand(b, m, 2, generator=g) * torch.tensor([640., 480.])
+    k1[:, :120] = k0[:, 40:160]
+    data = {'descriptors0': d0.to(dev), 'descriptors1': d1.to(dev), 'keypoints0': k0.to(dev), 'keypoints1': k1.to(dev),
+            'image_shape0': (1, 3, 640, 480), 'image_shape1': (1, 3, 640, 480)}
+    saved = BL.MERGE_SETS
+    try:
+        for extra in ({}, {'num_keypoints0': torch.tensor([200, 150, 97]), 'num_keypoints1': torch.tensor([180, 200, 64])},
+                      {'num_keypoints1': torch.tensor([33, 200, 199])}):
+            res = {}
+            for merge in (False, True):
+                BL.MERGE_SETS = merge
+                res[merge] = net({**data, **extra})
+                torch.cuda.synchronize()
+            for k_ in ('matches0', 'matches1', 'matching_scores0', 'matching_scores1'):
+                assert torch.equal(res[False][k_], res[True][k_]), (k_, list(extra))
+        ref = O.gml_forward(sd, {k_: (v.cpu() if torch.is_tensor(v) else v) for k_, v in data.items()})
+        out = net(data)
+        assert torch.allclose(out['matching_scores0'].cpu(), ref['matching_scores0'], atol=2e-3)
+    finally:
+        BL.MERGE_SETS = saved
+
+
 def _adagml_case():
     g = torch.Generator().manual_seed(0)
     m = n = 400
