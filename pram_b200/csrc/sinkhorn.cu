@@ -14,10 +14,11 @@
 // memory), so results are bit-reproducible run to run.  u, v, r, c never touch HBM.
 // Same algebra and eps placement as the reference (probability domain, eps inside the divisor).
 #include "common.cuh"
+#include <stdlib.h>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-constexpr int SK_MAXG = 8;
+constexpr int SK_MAXG = 16;  // 16 = non-portable cluster size (opt-in per kernel); used when few problems leave most SMs idle
 
 template <int NV, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
@@ -247,6 +248,7 @@ static int launch_sinkhorn(const float* dist, int B, int M, int N, const float* 
     const int rows_per = (M + 1 + G - 1) / G;
     size_t smem = sizeof(float) * (2 * (size_t)ldp + rows_per);
     PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (G > 8) PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(G, B, 1);
     cfg.blockDim = dim3(WARPS * 32, 1, 1);
@@ -284,8 +286,12 @@ PRAM_API int pram_sinkhorn_match(const float* dist, int B, int M, int N, const f
         // 20-iteration pass); a single problem keeps the portable maximum of 8 CTAs
         static int sms = 0;
         if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-        G = SK_MAXG;
-        while (G > 1 && (long long)B * G > sms) G >>= 1;
+        // (16-CTA clusters for up to 4 problems: a single 1024 x 1024 problem is bound by the latency of its row sweeps,
+        // 8 rows per warp and sweep with 8 CTAs; PRAM_SINKHORN_MAXG=8 keeps the portable size)
+        static int maxg = 0;
+        if (!maxg) { const char* e = getenv("PRAM_SINKHORN_MAXG"); maxg = e ? atoi(e) : SK_MAXG; if (maxg < 1 || maxg > SK_MAXG) maxg = SK_MAXG; }
+        G = maxg;
+        while (G > 1 && ((long long)B * G > sms || (G > 8 && B > 4))) G >>= 1;
     }
     if (G > SK_MAXG || (G & (G - 1))) return PRAM_ERR_ARG;
     const int ldp = (N + 1 + 3) / 4 * 4;
