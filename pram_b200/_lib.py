@@ -13,7 +13,8 @@ from pathlib import Path
 import torch
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / 'csrc' / 'libpram_b200.so'
+# PRAM_LIB: another build of the same library (A/B timing of a compile-time variant); default = the in-tree build
+LIB_PATH = Path(os.environ['PRAM_LIB']) if os.environ.get('PRAM_LIB') else _HERE / 'csrc' / 'libpram_b200.so'
 
 _P = C.c_void_p
 _I = C.c_int

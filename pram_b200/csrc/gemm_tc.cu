@@ -487,6 +487,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                     }
                 }
             }
+            // bias of the first chunk, loaded before the accumulator wait; every chunk then loads the NEXT chunk's bias while it
+            // works (ncu: the first FADD of a chunk waited for this load -- the top stall of the qkv GEMM, 10 % of its samples)
+            float4 bn0 = make_float4(0.f, 0.f, 0.f, 0.f), bn1 = bn0;
+            auto load_bias = [&](int nb) {
+                bn0 = make_float4(0.f, 0.f, 0.f, 0.f); bn1 = bn0;
+                if (biasp && (MODE == 2 || fast_ok) && nb + 32 <= p.N) {
+                    bn0 = __ldg(reinterpret_cast<const float4*>(biasp + nb + col2));
+                    bn1 = __ldg(reinterpret_cast<const float4*>(biasp + nb + col2 + 4));
+                }
+            };
+            load_bias(n0 + half * 32);
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
@@ -550,11 +561,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                             sts128(trow + (uint32_t)((j4 ^ (lane & 7)) << 4), make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
                                                                                   __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])));
                     }
-                    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                    if (biasp) {
-                        b0 = __ldg(reinterpret_cast<const float4*>(biasp + nb + col2));
-                        b1 = __ldg(reinterpret_cast<const float4*>(biasp + nb + col2 + 4));
-                    }
+                    const float4 b0 = bn0, b1 = bn1;
+                    if (c + 64 < BN) load_bias(nb + 64);
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -627,11 +635,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(
                         for (int i = 0; i < 8; ++i) rcur[i] = rv[i];
                         if (c + 64 < BN && nb + 64 + 32 <= p.N) load_res_fast(nb + 64, rv);  // next chunk's residual stays in flight
                     }
-                    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                    if (biasp) {
-                        b0 = __ldg(reinterpret_cast<const float4*>(biasp + nb + col2));
-                        b1 = __ldg(reinterpret_cast<const float4*>(biasp + nb + col2 + 4));
-                    }
+                    const float4 b0 = bn0, b1 = bn1;
+                    if (c + 64 < BN) load_bias(nb + 64);
                     const bool want_planes = p.out_hi || p.ps_hi;
                     __syncwarp();
 #pragma unroll

@@ -189,6 +189,38 @@ __device__ __forceinline__ float gelu_fast(float y) {
     const float ex = ex2_approx((y * -0.72134752044448170368f) * y);   // exp(-y^2 / 2)
     return fmaf(-fabsf(y), pl * ex, fmaxf(y, 0.f));
 }
+// ---- packed fp32 (FFMA2 / FMUL2 / FADD2: two lanes per instruction, sm_100) ---------------------------------------------
+// The LayerNorm + GELU pass is bound by the issue of its own fp32 arithmetic (20 instructions per element); the packed
+// forms halve every FFMA / FMUL / FADD of it.  Each lane is rounded exactly like the scalar instruction, and negating the
+// polynomial's constants instead of |y| is exact too (round-to-nearest is symmetric), so the results are those of gelu_fast.
+#ifndef PRAM_MLP_PACKED
+#define PRAM_MLP_PACKED 1
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f32x2 pk2u(uint32_t a, uint32_t b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// GELU of two values (same formula and constants as gelu_fast)
+__device__ __forceinline__ void gelu_fast2(f32x2 y, float& o0, float& o1) {
+    const f32x2 ay = y & 0x7fffffff7fffffffull;
+    float t0, t1;
+    upk2(fma2(ay, pk2(0.3275911f * 0.70710678118654752440f, 0.3275911f * 0.70710678118654752440f), pk2(1.f, 1.f)), t0, t1);
+    const f32x2 t = pk2(rcp_approx(t0), rcp_approx(t1));
+    f32x2 pl = fma2(pk2(-0.5f * 1.061405429f, -0.5f * 1.061405429f), t, pk2(-0.5f * -1.453152027f, -0.5f * -1.453152027f));
+    pl = fma2(pl, t, pk2(-0.5f * 1.421413741f, -0.5f * 1.421413741f));
+    pl = fma2(pl, t, pk2(-0.5f * -0.284496736f, -0.5f * -0.284496736f));
+    pl = fma2(pl, t, pk2(-0.5f * 0.254829592f, -0.5f * 0.254829592f));
+    pl = mul2(pl, t);                                                   // -(0.5 P(t))
+    float e0, e1;
+    upk2(mul2(mul2(y, pk2(-0.72134752044448170368f, -0.72134752044448170368f)), y), e0, e1);
+    const f32x2 ex = pk2(ex2_approx(e0), ex2_approx(e1));             // exp(-y^2 / 2)
+    float y0, y1;
+    upk2(y, y0, y1);
+    upk2(fma2(ay, mul2(pl, ex), pk2(fmaxf(y0, 0.f), fmaxf(y1, 0.f))), o0, o1);
+}
 // erf by Abramowitz-Stegun 7.1.26 (abs error <= 1.5e-7), same routine as the split-bf16 LayerNorm kernel (nn_simt.cu)
 __device__ __forceinline__ float erf_as(float x) {
     const float z = fabsf(x);
@@ -436,12 +468,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
                     const float4 b = *reinterpret_cast<const float4*>(&tb.b1[c0 + 4 * i]);
                     const float4 g = *reinterpret_cast<const float4*>(&tb.g[c0 + 4 * i]);
                     const float4 be = *reinterpret_cast<const float4*>(&tb.be[c0 + 4 * i]);
+#if PRAM_MLP_PACKED
+                    float y[4];
+                    {
+                        const f32x2 nm = pk2(-mean, -mean), rs = pk2(rstd, rstd);
+                        const f32x2 ya = fma2(add2(pk2u(v[4 * i], v[4 * i + 1]), add2(pk2(b.x, b.y), nm)), mul2(rs, pk2(g.x, g.y)), pk2(be.x, be.y));
+                        const f32x2 yb = fma2(add2(pk2u(v[4 * i + 2], v[4 * i + 3]), add2(pk2(b.z, b.w), nm)), mul2(rs, pk2(g.z, g.w)), pk2(be.z, be.w));
+                        gelu_fast2(ya, y[0], y[1]);
+                        gelu_fast2(yb, y[2], y[3]);
+                    }
+#else
                     float y[4] = {fmaf(__uint_as_float(v[4 * i]) + (b.x - mean), rstd * g.x, be.x),
                                   fmaf(__uint_as_float(v[4 * i + 1]) + (b.y - mean), rstd * g.y, be.y),
                                   fmaf(__uint_as_float(v[4 * i + 2]) + (b.z - mean), rstd * g.z, be.z),
                                   fmaf(__uint_as_float(v[4 * i + 3]) + (b.w - mean), rstd * g.w, be.w)};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) y[k] = gelu_fast(y[k]);
+#endif
                     split2(y[0], y[1], hi[2 * i], lo[2 * i]);
                     split2(y[2], y[3], hi[2 * i + 1], lo[2 * i + 1]);
                 }
