@@ -546,19 +546,19 @@ def roofline_probe(pipe, frames_dev, dev):
     ach = flops / (ms * 1e-3) / 1e12
     mma_mult = 3 if prec == 'bf16x3' else 1
     # DRAM traffic of the same launch from the committed `ncu --set full` capture (profiles/), B=32 bf16x3 only
-    traffic = None
-    prof = ROOT / 'profiles' / 'r01_ncu_full_conv3b_attention_v6_summary.csv'
-    if prof.exists() and B == 32 and (H, W) == (480, 640) and prec == 'bf16x3':
-        import csv
-        rows = list(csv.reader(open(prof)))
-        hdr = rows[0]
-        for r in rows[2:]:
-            if 'gemm_tc_kernel' in r[0]:
-                traffic = (float(r[hdr.index('dram__bytes_read.sum')]) + float(r[hdr.index('dram__bytes_write.sum')])) * 1e6
+    traffic, traffic_src = None, None
+    for name in ('r02b_conv3b_ncu_full.json', 'r02_conv3b_traffic.json'):   # newest capture of this launch first
+        prof = ROOT / 'profiles' / name
+        if prof.exists() and B == 32 and (H, W) == (480, 640) and prec == 'bf16x3':
+            try:
+                d = json.loads(prof.read_text())
+                traffic, traffic_src = float(d['dram_bytes']), f'profiles/{name}'
                 break
+            except (ValueError, KeyError):   # an unreadable summary must not take the bench down: traffic stays null
+                continue
     return {'bound': 'tensor', 'kernel': f'conv3x3 256->256 @120x160 (conv3b), precision {prec}', 'achieved': ach,
             'tensor_flops_issued_per_algorithmic_flop': mma_mult, 'peak': peak,
-            'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': traffic, 'traffic_unit': 'bytes/launch (dram read+write, ncu)',
+            'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': traffic, 'traffic_unit': 'bytes/launch (dram read+write, ncu --set full)', 'traffic_source': traffic_src,
             'algorithmic_bytes': 2.0 * B * (H // 4) * (W // 4) * 256 * 2 * (2 if prec == 'bf16x3' else 1) + 9 * 256 * 256 * 2 * (2 if prec == 'bf16x3' else 1),
             'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst)' if peaks else 'fallback 1.59 PFLOP/s'}
 

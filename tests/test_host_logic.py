@@ -235,3 +235,17 @@ def test_bench_workloads_and_step_bound():
         assert bench.METRIC == 'localization frames/sec (640x480, 1024 kpts)'
     finally:
         bench.H, bench.W, bench.KPTS, bench.NCLASS, bench.FOCAL, bench.MAX_ERROR, bench.METRIC = saved
+
+
+def test_committed_profile_summaries_parse():
+    """bench.py reads its roofline traffic figure from profiles/*.json; every committed summary must be valid JSON (an empty
+    file once took the multi-GPU bench down) and the conv3b capture must carry the DRAM byte count."""
+    import json
+    from pathlib import Path
+    prof = Path(__file__).resolve().parents[1] / 'profiles'
+    files = sorted(prof.glob('*.json'))
+    assert files
+    for f in files:
+        json.loads(f.read_text())
+    d = json.loads((prof / 'r02b_conv3b_ncu_full.json').read_text())
+    assert d['dram_bytes'] > 1e9 and 'gemm_tc_kernel' in d['kernel']
