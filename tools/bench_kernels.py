@@ -86,6 +86,21 @@ conv_case('conv3x3 256->256 @120x160 (conv3b)', 120, 160, 256, 256, 3)
 conv_case('conv3x3 128->128 @240x320 (conv2a-like)', 240, 320, 128, 128, 3)
 conv_case('conv1x1 256->256 @120x160 (conv4.x.conv1/3)', 120, 160, 256, 256, 1)
 
+xr_ = ops.split_bf16(torch.randn(B, 120, 160, 256, device=dev), True)
+rr_ = ops.split_bf16(torch.randn(B, 120, 160, 256, device=dev), True)
+wr_ = ops.split_bf16(torch.randn(1, 256, 256, device=dev) * 0.05, True)
+br_ = torch.randn(256, device=dev)
+report('gemm_tc_kernel conv1x1 256->256 + residual planes + ReLU @120x160 (conv4.x.conv3)',
+       timeit(lambda: ops.conv_tc(xr_, wr_, br_, 1, 1, True, 3, res_bf=rr_)), nbytes=B * 120 * 160 * 256 * 12, bound='hbm',
+       note='reads A hi/lo + residual hi/lo, writes hi/lo: 12 B per output element')
+x16_ = ops.as_f16_plane(torch.randn(B, 120, 160, 256, device=dev))
+wd_ = ops.Split((torch.randn(1, 128, 256, device=dev) * 0.05).half().view(torch.bfloat16), None)
+bd_ = torch.randn(128, device=dev)
+report('gemm_tc_kernel conv1x1 256->128 fp16 + L2 norm @120x160 (convDb)',
+       timeit(lambda: ops.conv_tc(x16_, wd_, bd_, 1, 1, False, 1, want_f32=True, want_bf=False, l2norm=True, f16=True)),
+       nbytes=B * 120 * 160 * (256 * 2 + 128 * 4), bound='hbm')
+del xr_, rr_, x16_
+
 # ---- linear layers at transformer shapes -------------------------------------------------------------------
 def lin_case(name, rows_, k, n):
     a = ops.split_bf16(torch.randn(rows_, k, device=dev), True)
@@ -135,7 +150,7 @@ nn_ = torch.empty((B,), device=dev, dtype=torch.int32)
 
 def select_only():
     call('pram_select_keypoints', ptr(cand), cap, ptr(counts[0]), ptr(counts[1]), ptr(score), B, H, W, 0.0025, 0.005, 128, K, 4,
-         ptr(kp), ptr(sc), ptr(nn_), K, stream_ptr())
+         0, 0, ptr(kp), ptr(sc), ptr(nn_), K, None, stream_ptr())
 
 
 nms_only()
