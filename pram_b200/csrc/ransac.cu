@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(FIN_THREADS) ransac_finalize_kernel(
     __shared__ rs::Pose pose, trial;
     __shared__ double red[32];
     __shared__ double scratch[28 * 8];
-    __shared__ int s_best_cnt, s_ok;
+    __shared__ int s_best_cnt, s_ok, s_stop;
     __shared__ double s_lambda, s_cost;
     for (int i = threadIdx.x; i < n_out; i += FIN_THREADS) inlier_mask[(long long)b * n_out + i] = 0;
     if (threadIdx.x == 0) {
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(FIN_THREADS) ransac_finalize_kernel(
     for (int phase = 0; phase < 2; ++phase) {
         const bool robust = (phase == 1);
         const int iters = robust ? final_iters : lo_iters;
-        if (threadIdx.x == 0) { ref = pose; cur = pose; s_lambda = 1e-4; }
+        if (threadIdx.x == 0) { ref = pose; cur = pose; s_lambda = 1e-4; s_stop = 0; }
         __syncthreads();
         for (int it = 0; it < iters; ++it) {
             double acc[28];  // 21 upper-triangular H entries, 6 gradient entries, cost
@@ -463,9 +463,17 @@ __global__ void __launch_bounds__(FIN_THREADS) ransac_finalize_kernel(
                         for (int cc = 0; cc < 3; ++cc)
                             trial.R[r * 3 + cc] = dR[r * 3] * cur.R[cc] + dR[r * 3 + 1] * cur.R[3 + cc] + dR[r * 3 + 2] * cur.R[6 + cc];
                     trial.t[0] = cur.t[0] + d[3]; trial.t[1] = cur.t[1] + d[4]; trial.t[2] = cur.t[2] + d[5];
+                    // converged: the step is below what float64 resolves on a pose of unit scale (rotation in radians, translation
+                    // in scene units); the remaining iterations of the budget would only re-evaluate the same pose.  A typical
+                    // phase stops after 3 - 6 of its 10 / 20 iterations (each one is two block-wide float64 reductions).
+                    double dm = 0;
+                    for (int r = 0; r < 6; ++r) dm = fmax(dm, fabs(d[r]));
+                    const double scale = 1.0 + fmax(fabs(cur.t[0]), fmax(fabs(cur.t[1]), fabs(cur.t[2])));
+                    if (dm < 1e-13 * scale) s_stop = 1;
                 }
             }
             __syncthreads();
+            if (s_stop) break;   // block-uniform (shared flag read after the barrier)
             // cost of the trial pose on the same fixed set
             double ev[1] = {0};
             for (int i = threadIdx.x; i < m; i += FIN_THREADS) {
