@@ -298,9 +298,16 @@ PRAM_API int pram_sinkhorn_match(const float* dist, int B, int M, int N, const f
     int* idx0 = iws;
     int* idx1 = iws + (long long)B * M;
     const int nv = (ldp + 127) / 128;
-    if (nv <= 9)
-        return launch_sinkhorn<9, 16>(dist, B, M, N, bin_score, iters, threshold, pws, ldp, matches0, matches1,
-                                      mscores0, mscores1, idx0, idx1, fws, G, m_counts, n_counts, stream);
+    if (nv <= 9) {
+        int rc = launch_sinkhorn<9, 16>(dist, B, M, N, bin_score, iters, threshold, pws, ldp, matches0, matches1,
+                                        mscores0, mscores1, idx0, idx1, fws, G, m_counts, n_counts, stream);
+        if (rc != PRAM_OK && G > 8 && cluster <= 0) {  // the opt-in 16-CTA cluster could not be placed on this part: portable size
+            cudaGetLastError();
+            rc = launch_sinkhorn<9, 16>(dist, B, M, N, bin_score, iters, threshold, pws, ldp, matches0, matches1,
+                                        mscores0, mscores1, idx0, idx1, fws, 8, m_counts, n_counts, stream);
+        }
+        return rc;
+    }
     if (nv <= 17)
         return launch_sinkhorn<17, 8>(dist, B, M, N, bin_score, iters, threshold, pws, ldp, matches0, matches1,
                                        mscores0, mscores1, idx0, idx1, fws, G, m_counts, n_counts, stream);

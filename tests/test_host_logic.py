@@ -249,3 +249,25 @@ def test_committed_profile_summaries_parse():
         json.loads(f.read_text())
     d = json.loads((prof / 'r02b_conv3b_ncu_full.json').read_text())
     assert d['dram_bytes'] > 1e9 and 'gemm_tc_kernel' in d['kernel']
+
+
+def test_attention_launch_merging_rule():
+    """nets/_blocks._mergeable: both token sets of a GML block share one attention launch only when the two segments are
+    adjacent, equally shaped, no mean-attention output is requested, and padded batches bring the concatenated counts."""
+    import torch
+    from pram_b200.nets import _blocks as BL
+    seg = ((0, 4, 100), (400, 4, 100))
+    assert BL._mergeable(seg, None, None)
+    assert not BL._mergeable(seg, [torch.zeros(1)], None)                      # AdaGML asks for the per-key attention mass
+    assert not BL._mergeable(((0, 4, 100), (400, 4, 90)), None, None)           # M != N
+    assert not BL._mergeable(((0, 4, 100), (512, 4, 100)), None, None)          # not adjacent
+    assert not BL._mergeable(((0, 4, 100),), None, None)                        # SegNetViT: one segment
+    c = torch.full((4,), 100, dtype=torch.int32)
+    assert not BL._mergeable(seg, None, [c, c])                                 # counts without the concatenated form
+    assert BL._mergeable(seg, None, [c, None, torch.cat([c, c])])
+    saved = BL.MERGE_SETS
+    try:
+        BL.MERGE_SETS = False
+        assert not BL._mergeable(seg, None, None)
+    finally:
+        BL.MERGE_SETS = saved
