@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
     const int rank = (int)cluster.block_rank();
     const int b = blockIdx.y;
     const int rows_per = (MR + G - 1) / G;
+    float* part_s = u_s + ((rows_per + 3) & ~3);   // [WARPS][ldp] per-warp column partials of one sweep
     const int r0 = min(rank * rows_per, MR), r1 = min(r0 + rows_per, MR);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float bin = *bin_ptr;
@@ -139,20 +140,23 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
                 cp[k].z += pv.z * ui; cp[k].w += pv.w * ui;
             }
         }
-        // fixed-order reduction of the per-warp partials into col_s
-        for (int w = 0; w < WARPS; ++w) {
-            if (warp == w) {
+        // fixed-order reduction of the per-warp partials into col_s: every warp parks its partials, then each thread adds the
+        // WARPS values of its four columns in warp order -- the same order (and bits) as the former one-warp-at-a-time
+        // accumulation, with one block barrier instead of WARPS of them
 #pragma unroll
-                for (int k = 0; k < NV; ++k) {
-                    int j = k * 128 + lane * 4;
-                    if (j < ldp) {
-                        float4* d = reinterpret_cast<float4*>(col_s + j);
-                        if (w == 0) *d = cp[k];
-                        else { float4 o = *d; o.x += cp[k].x; o.y += cp[k].y; o.z += cp[k].z; o.w += cp[k].w; *d = o; }
-                    }
-                }
+        for (int k = 0; k < NV; ++k) {
+            const int j = k * 128 + lane * 4;
+            if (j < ldp) *reinterpret_cast<float4*>(part_s + (size_t)warp * ldp + j) = cp[k];
+        }
+        __syncthreads();
+        for (int j = threadIdx.x * 4; j < ldp; j += WARPS * 32 * 4) {
+            float4 a = *reinterpret_cast<const float4*>(part_s + j);
+#pragma unroll
+            for (int w = 1; w < WARPS; ++w) {
+                const float4 o = *reinterpret_cast<const float4*>(part_s + (size_t)w * ldp + j);
+                a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
             }
-            __syncthreads();
+            *reinterpret_cast<float4*>(col_s + j) = a;
         }
         cluster.sync();
         // rank-ordered reduction of this rank's column chunk over all CTAs, then broadcast v
@@ -246,7 +250,7 @@ static int launch_sinkhorn(const float* dist, int B, int M, int N, const float* 
                            int* idx0, int* idx1, float* max0, int G, const int* mc, const int* nc, cudaStream_t stream) {
     auto kern = sinkhorn_match_kernel<NV, WARPS>;
     const int rows_per = (M + 1 + G - 1) / G;
-    size_t smem = sizeof(float) * (2 * (size_t)ldp + rows_per);
+    size_t smem = sizeof(float) * (2 * (size_t)ldp + ((rows_per + 3) & ~3) + (size_t)WARPS * ldp);
     PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (G > 8) PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
