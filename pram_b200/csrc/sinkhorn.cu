@@ -204,18 +204,47 @@ __global__ void __launch_bounds__(WARPS * 32) sinkhorn_match_kernel(
     }
     __threadfence();
     cluster.sync();
-    // ---- column arg-max over i < M for this rank's columns j < N ----
+    // ---- column arg-max over i < mb for this rank's columns j < N ----
+    // The rank's columns are taken in blocks of 32 float4 groups (128 columns): lane = group, warp = a band of rows, four
+    // running maxima per thread from 16-byte loads; the bands meet in shared memory and are merged in row order with a
+    // strict comparison, so the first maximal row wins exactly as in a top-to-bottom scan.  (One thread per column walking
+    // all rows -- 1024 dependent-latency loads on half the threads -- was a 45 us serial tail of every launch.)
     {
-        const int cols_per = (N + G - 1) / G;
-        const int c0 = rank * cols_per, c1 = min(c0 + cols_per, N);
-        for (int j = c0 + threadIdx.x; j < c1; j += WARPS * 32) {
-            float best = -1.f;
-            int bi = 0;
-            for (int i = 0; i < mb; ++i) {
-                float pv = P[(long long)i * ldp + j];
-                if (pv > best) { best = pv; bi = i; }
+        const int ngroups = (N + 3) / 4;                       // float4 groups that hold columns j < N
+        const int gper = (ngroups + G - 1) / G;
+        const int g0 = rank * gper, g1 = min(g0 + gper, ngroups);
+        const int rows_pw = (mb + WARPS - 1) / WARPS;
+        const int ra = min(warp * rows_pw, mb), rb = min(ra + rows_pw, mb);
+        float* sb = part_s;                                     // [WARPS][128] best values
+        int* si = reinterpret_cast<int*>(part_s + WARPS * 128);  // [WARPS][128] their rows   (8 KB + 8 KB <= WARPS * ldp floats)
+        for (int gb = g0; gb < g1; gb += 32) {
+            const int g = gb + lane;
+            float best[4] = {-1.f, -1.f, -1.f, -1.f};
+            int bi[4] = {0, 0, 0, 0};
+            if (g < g1) {
+                const float* col = P + 4 * g;
+                for (int i = ra; i < rb; ++i) {
+                    const float4 pv = *reinterpret_cast<const float4*>(col + (long long)i * ldp);
+                    if (pv.x > best[0]) { best[0] = pv.x; bi[0] = i; }
+                    if (pv.y > best[1]) { best[1] = pv.y; bi[1] = i; }
+                    if (pv.z > best[2]) { best[2] = pv.z; bi[2] = i; }
+                    if (pv.w > best[3]) { best[3] = pv.w; bi[3] = i; }
+                }
             }
-            idx1_ws[(long long)b * N + j] = bi;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { sb[warp * 128 + lane * 4 + q] = best[q]; si[warp * 128 + lane * 4 + q] = bi[q]; }
+            __syncthreads();
+            if (threadIdx.x < 128) {
+                const int j = 4 * gb + threadIdx.x;
+                float bbest = -1.f;
+                int bbi = 0;
+                for (int w = 0; w < WARPS; ++w) {
+                    const float v = sb[w * 128 + threadIdx.x];
+                    if (v > bbest) { bbest = v; bbi = si[w * 128 + threadIdx.x]; }
+                }
+                if (j < N && 4 * gb + threadIdx.x < 4 * g1) idx1_ws[(long long)b * N + j] = bbi;
+            }
+            __syncthreads();
         }
     }
     __threadfence();
@@ -250,7 +279,9 @@ static int launch_sinkhorn(const float* dist, int B, int M, int N, const float* 
                            int* idx0, int* idx1, float* max0, int G, const int* mc, const int* nc, cudaStream_t stream) {
     auto kern = sinkhorn_match_kernel<NV, WARPS>;
     const int rows_per = (M + 1 + G - 1) / G;
-    size_t smem = sizeof(float) * (2 * (size_t)ldp + ((rows_per + 3) & ~3) + (size_t)WARPS * ldp);
+    // v | column partials | u | per-warp partials of a sweep, re-used by the column arg-max (2 x WARPS x 128 words)
+    const size_t part = (size_t)WARPS * ((size_t)ldp > 256 ? (size_t)ldp : 256);
+    size_t smem = sizeof(float) * (2 * (size_t)ldp + ((rows_per + 3) & ~3) + part);
     PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (G > 8) PRAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
