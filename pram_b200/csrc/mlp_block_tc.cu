@@ -166,6 +166,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void sts_u4(uint32_t a, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
@@ -235,7 +240,7 @@ __device__ __forceinline__ float erf_as(float x) {
 
 // barrier block layout (uint64 each)
 enum : int { B_FULLA = 0, B_EMPTYA = 2, B_HFULL = 4, B_SLOTF = 5, B_SLOTE = 9, B_W3F = 13, B_W3E = 16, B_ACCF = 19, B_ACCE = 20,
-             B_H1FULL = 21, B_COUNT = 22 };
+             B_H1FULL = 21, B_CDONE = 22, B_COUNT = 23 };
 
 template <int SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
@@ -265,6 +270,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
         for (int s = 0; s < NSTAGE_3; ++s) { mbar_init(&bars[B_W3F + s], 1); mbar_init(&bars[B_W3E + s], 1); }
         mbar_init(&bars[B_ACCF], 1);
         mbar_init(&bars[B_ACCE], EPI_WARPS);
+        mbar_init(&bars[B_CDONE], EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -313,6 +319,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
                         if (SPLIT == 3) tma_prefetch_2d(&map_a_lo, kb * BK, nrow0);
                     }
                 }
+                // the last W3 stage doubles as the staging area of the previous tile's phase C (2 KB per epilogue warp)
+                mbar_wait(&bars[B_CDONE], (it & 1) ^ 1, 13);
                 for (int s = 0; s < 2 * KB2; ++s) {   // 16 half k-blocks of W3, all 256 output rows each
                     mbar_wait(&bars[B_W3E + s3], ph3 ^ 1, 3);
                     const uint32_t st = sbase + W3_OFF + s3 * STAGE_3;
@@ -513,35 +521,99 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
             // residual: fp32 rows when given, else x = hi + lo of this tile's own A rows (just streamed by phase A, L2-hot):
             // the activation stream then lives in HBM as its two bf16 planes only -- 1 KB per token written per block
             // instead of 3 KB moved (fp32 read + fp32 write + planes), which was the DRAM burst that stalled all SMs at once
+            // Global accesses of phase C go through a 2 KB staging tile per warp ([32 rows][32 columns] of one bf16 plane,
+            // 16-byte pieces XOR-swizzled by the row pair): the thread-per-row accesses of the first version touched 32
+            // different 128-byte lines per instruction (1024 L1 wavefronts per warp and tile, which is what bounded the phase:
+            // 21k cycles, exposed on the last tile of a CTA and slowing the next tile's first GEMM otherwise); four lanes per row
+            // move whole 64-byte segments, 8 lines per instruction.  The staging bytes are the last W3 stage, idle between the
+            // second GEMM of this tile and the W3 stream of the next one (B_CDONE orders the two).
+            const uint32_t stg = sbase + W3_OFF + (NSTAGE_3 - 1) * STAGE_3 + (uint32_t)e * 2048u;
+            auto swz = [](int row, int piece) { return (uint32_t)(row * 64 + ((piece ^ ((row >> 1) & 3)) << 4)); };
+            const int crow = lane >> 2, cpiece = lane & 3;                      // coalesced mapping: row = 8 t + crow
+            const long long tile_row0 = (long long)tile * BM + q * 32;
+            // one plane tile (columns n0 .. n0 + 31 of this warp's 32 rows) -> this lane's row as 16 words
+            auto load_plane = [&](const __nv_bfloat16* plane, int n0, uint32_t (&w)[16]) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int row = t * 8 + crow;
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (tile_row0 + row < p.T) v = __ldg(reinterpret_cast<const uint4*>(plane + (tile_row0 + row) * p.lda + n0 + cpiece * 8));
+                    sts_u4(stg + swz(row, cpiece), v);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int pc = 0; pc < 4; ++pc) {
+                    const uint4 v = lds_u4(stg + swz(lane, pc));
+                    w[4 * pc] = v.x; w[4 * pc + 1] = v.y; w[4 * pc + 2] = v.z; w[4 * pc + 3] = v.w;
+                }
+                __syncwarp();
+            };
+            // this lane's row of one output plane (16 words = 32 bf16) -> global, through the staging tile
+            auto store_plane = [&](__nv_bfloat16* plane, int n0, const uint4 (&w)[4]) {
+#pragma unroll
+                for (int pc = 0; pc < 4; ++pc) sts_u4(stg + swz(lane, pc), w[pc]);
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int row = t * 8 + crow;
+                    const uint4 v = lds_u4(stg + swz(row, cpiece));
+                    if (tile_row0 + row < p.T) *reinterpret_cast<uint4*>(plane + (tile_row0 + row) * p.ld_bf + n0 + cpiece * 8) = v;
+                }
+                __syncwarp();
+            };
             auto load_res = [&](int n0, float4 (&rv)[8]) {
+                if (p.res) {   // fp32 residual rows (AdaGML keeps the fp32 stream): thread-per-row loads as before
+                    if (!row_ok) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) rv[i] = __ldg(reinterpret_cast<const float4*>(p.res + grow * p.res_ld + n0) + i);
+                    }
+                    return;
+                }
+                uint32_t h[16], l[16];
+                load_plane(p.xa_hi, n0, h);
+                if (SPLIT == 3) load_plane(p.xa_lo, n0, l);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t h0 = h[2 * i], h1 = h[2 * i + 1];
+                    const uint32_t l0 = (SPLIT == 3) ? l[2 * i] : 0u, l1 = (SPLIT == 3) ? l[2 * i + 1] : 0u;
+                    rv[i] = make_float4(__uint_as_float(h0 << 16) + __uint_as_float(l0 << 16),
+                                        __uint_as_float(h0 & 0xffff0000u) + __uint_as_float(l0 & 0xffff0000u),
+                                        __uint_as_float(h1 << 16) + __uint_as_float(l1 << 16),
+                                        __uint_as_float(h1 & 0xffff0000u) + __uint_as_float(l1 & 0xffff0000u));
+                }
+            };
+            // first chunk's residual BEFORE the accumulator wait (the warps idle through the tail of the second GEMM anyway) --
+            // thread-per-row loads, because the staging bytes are a W3 stage the MMA may still be reading until B_ACCF
+            auto load_res_direct = [&](int n0, float4 (&rv)[8]) {
+                if (p.res) { load_res(n0, rv); return; }
                 if (!row_ok) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                } else if (p.res) {
+                    return;
+                }
+                const uint4* ph = reinterpret_cast<const uint4*>(p.xa_hi + grow * p.lda + n0);
+                const uint4* pl = reinterpret_cast<const uint4*>(p.xa_lo + grow * p.lda + n0);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) rv[i] = __ldg(reinterpret_cast<const float4*>(p.res + grow * p.res_ld + n0) + i);
-                } else {
-                    const uint4* ph = reinterpret_cast<const uint4*>(p.xa_hi + grow * p.lda + n0);
-                    const uint4* pl = reinterpret_cast<const uint4*>(p.xa_lo + grow * p.lda + n0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint4 h = __ldg(ph + i);
-                        uint4 l = make_uint4(0u, 0u, 0u, 0u);
-                        if (SPLIT == 3) l = __ldg(pl + i);
-                        rv[2 * i] = make_float4(__uint_as_float(h.x << 16) + __uint_as_float(l.x << 16),
-                                                __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u),
-                                                __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16),
-                                                __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u));
-                        rv[2 * i + 1] = make_float4(__uint_as_float(h.z << 16) + __uint_as_float(l.z << 16),
-                                                    __uint_as_float(h.z & 0xffff0000u) + __uint_as_float(l.z & 0xffff0000u),
-                                                    __uint_as_float(h.w << 16) + __uint_as_float(l.w << 16),
-                                                    __uint_as_float(h.w & 0xffff0000u) + __uint_as_float(l.w & 0xffff0000u));
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 h = __ldg(ph + i);
+                    uint4 l = make_uint4(0u, 0u, 0u, 0u);
+                    if (SPLIT == 3) l = __ldg(pl + i);
+                    rv[2 * i] = make_float4(__uint_as_float(h.x << 16) + __uint_as_float(l.x << 16),
+                                            __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u),
+                                            __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16),
+                                            __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u));
+                    rv[2 * i + 1] = make_float4(__uint_as_float(h.z << 16) + __uint_as_float(l.z << 16),
+                                                __uint_as_float(h.z & 0xffff0000u) + __uint_as_float(l.z & 0xffff0000u),
+                                                __uint_as_float(h.w << 16) + __uint_as_float(l.w << 16),
+                                                __uint_as_float(h.w & 0xffff0000u) + __uint_as_float(l.w & 0xffff0000u));
                 }
             };
             if (e == 0 && lane == 0) stamp(p, it, 3);
             float4 rv[8];
-            load_res(part * 64, rv);  // independent of the accumulator: overlaps the tail of the second GEMM
+            load_res_direct(part * 64, rv);
             mbar_wait(&bars[B_ACCF], it & 1, 11);
             tc_fence_after();
             if (e == 0 && lane == 0) stamp(p, it, 4);
@@ -557,31 +629,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
                     if (lane == 0) mbar_arrive(&bars[B_ACCE]);
                     load_res(n0, rv);
                 }
-                if (row_ok) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float f0 = __uint_as_float(v[4 * i]) + tb.b3[n0 + 4 * i] + rv[i].x;
-                        const float f1 = __uint_as_float(v[4 * i + 1]) + tb.b3[n0 + 4 * i + 1] + rv[i].y;
-                        const float f2 = __uint_as_float(v[4 * i + 2]) + tb.b3[n0 + 4 * i + 2] + rv[i].z;
-                        const float f3 = __uint_as_float(v[4 * i + 3]) + tb.b3[n0 + 4 * i + 3] + rv[i].w;
-                        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + n0 + 4 * i) = make_float4(f0, f1, f2, f3);
-                        split2(f0, f1, v[4 * i], v[4 * i + 2]);       // re-use v: [4i] = hi01, [4i+1] = hi23, [4i+2] = lo01, [4i+3] = lo23
-                        uint32_t h23, l23;
-                        split2(f2, f3, h23, l23);
-                        v[4 * i + 1] = h23; v[4 * i + 3] = l23;
-                    }
-                    if (p.out_hi) {
+                for (int i = 0; i < 8; ++i) {
+                    const float f0 = __uint_as_float(v[4 * i]) + tb.b3[n0 + 4 * i] + rv[i].x;
+                    const float f1 = __uint_as_float(v[4 * i + 1]) + tb.b3[n0 + 4 * i + 1] + rv[i].y;
+                    const float f2 = __uint_as_float(v[4 * i + 2]) + tb.b3[n0 + 4 * i + 2] + rv[i].z;
+                    const float f3 = __uint_as_float(v[4 * i + 3]) + tb.b3[n0 + 4 * i + 3] + rv[i].w;
+                    if (p.out_f32 && row_ok) *reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + n0 + 4 * i) = make_float4(f0, f1, f2, f3);
+                    split2(f0, f1, v[4 * i], v[4 * i + 2]);       // re-use v: [4i] = hi01, [4i+1] = hi23, [4i+2] = lo01, [4i+3] = lo23
+                    uint32_t h23, l23;
+                    split2(f2, f3, h23, l23);
+                    v[4 * i + 1] = h23; v[4 * i + 3] = l23;
+                }
+                if (p.out_hi) {   // warp-uniform
+                    uint4 w[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            *reinterpret_cast<uint4*>(p.out_hi + grow * p.ld_bf + n0 + 8 * i) =
-                                make_uint4(v[8 * i], v[8 * i + 1], v[8 * i + 4], v[8 * i + 5]);
-                            if (SPLIT == 3 && p.out_lo)
-                                *reinterpret_cast<uint4*>(p.out_lo + grow * p.ld_bf + n0 + 8 * i) =
-                                    make_uint4(v[8 * i + 2], v[8 * i + 3], v[8 * i + 6], v[8 * i + 7]);
-                        }
+                    for (int i = 0; i < 4; ++i) w[i] = make_uint4(v[8 * i], v[8 * i + 1], v[8 * i + 4], v[8 * i + 5]);
+                    store_plane(p.out_hi, n0, w);
+                    if (SPLIT == 3 && p.out_lo) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) w[i] = make_uint4(v[8 * i + 2], v[8 * i + 3], v[8 * i + 6], v[8 * i + 7]);
+                        store_plane(p.out_lo, n0, w);
                     }
                 }
             }
+            // phase C no longer touches the staging tile: the producer may stream the next tile's W3 into that stage
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_CDONE]);
             if (e == 0 && lane == 0) stamp(p, it, 5);
         }
     }
