@@ -953,9 +953,18 @@ PRAM_API int pram_gemm_tc(const pram_tc_args* a, cudaStream_t stream) {
     }
     int bn = a->bn;
     if (bn == 0) bn = (a->N > 128) ? 256 : (a->N > 64 ? 128 : 64);
-    if (a->l2norm && a->N > bn) return PRAM_ERR_UNSUPPORTED;
     const int TW = 1 << a->tw_log2, TH = BM >> a->tw_log2;
     if (TW > 256 || TH < 1) return PRAM_ERR_ARG;
+    if (a->bn == 0 && bn == 256 && !a->qkv_mode && !a->l2norm) {
+        // Wave quantisation of small problems: one 640x480 frame has 150 output tiles per 256-wide layer at 1/4 resolution --
+        // two waves on 148 SMs, the second one with 2 tiles.  Half-width tiles (0.55 of the cost: half the MMAs, the same
+        // activation tile) come out ahead whenever they need fewer weighted waves; large batches keep the 256-wide tile.
+        const long long mt = (long long)a->B * ((a->Wo + TW - 1) / TW) * ((a->Ho + TH - 1) / TH);
+        const long long w256 = (mt * ((a->N + 255) / 256) + g_num_sms - 1) / g_num_sms;
+        const long long w128 = (mt * ((a->N + 127) / 128) + g_num_sms - 1) / g_num_sms;
+        if (0.55 * (double)w128 < (double)w256 && w256 <= 8) bn = 128;
+    }
+    if (a->l2norm && a->N > bn) return PRAM_ERR_UNSUPPORTED;
 
     // 2-CTA clusters with a multicast weight tile: shared weights (no per-batch weight planes), at least one full
     // wave of tiles, and a weight tile whose halves are whole swizzle atoms
