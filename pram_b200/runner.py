@@ -179,18 +179,28 @@ class LocalizationPipeline:
         syncs with the host).  Returns the number of library kernels inside one replay."""
         from . import _lib
         self._static_in = images.clone()
-        side = torch.cuda.Stream(device=self.dev)
-        side.wait_stream(torch.cuda.current_stream(self.dev))
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                self.localize(self._static_in, smap)
-        torch.cuda.current_stream(self.dev).wait_stream(side)
-        torch.cuda.synchronize(self.dev)
-        self._graph = torch.cuda.CUDAGraph()
-        n0 = _lib.launch_count()
-        with torch.cuda.graph(self._graph):
-            self._static_out = self.localize(self._static_in, smap)
-        self.graph_launches = _lib.launch_count() - n0
+        # small batches are bound by the latency of ~150 dependent launches: let every persistent kernel release its
+        # successor as soon as its own CTAs are resident (programmatic dependent launch, early trigger; baked into the
+        # captured nodes).  At batch 32 the early trigger costs 0.6 %, so it stays off there (DESIGN.md section 11).
+        lib = _lib.load()
+        pdl_saved = lib.pram_get_pdl()
+        if pdl_saved == 1 and images.shape[0] <= 4:
+            lib.pram_set_pdl(2)
+        try:
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.localize(self._static_in, smap)
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            torch.cuda.synchronize(self.dev)
+            self._graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(self._graph):
+                self._static_out = self.localize(self._static_in, smap)
+            self.graph_launches = _lib.launch_count() - n0
+        finally:
+            lib.pram_set_pdl(pdl_saved)
         return self.graph_launches
 
     def replay(self, images: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
