@@ -1,5 +1,5 @@
 """Sinkhorn + mutual matches alone: B pairs of 1024 x 1024, 20 iterations, CUDA events, L2 flushed between repetitions.
-    PRAM_SINKHORN_KEEP8=k python tools/bench_sinkhorn.py [B]"""
+    python tools/bench_sinkhorn.py [B]            (PRAM_SINKHORN_MAXG=8 keeps the portable cluster size)"""
 import json
 import os
 import sys
@@ -26,5 +26,5 @@ for r in range(12):
     if r >= 3:
         ts.append(e0.elapsed_time(e1))
 ts.sort()
-print(json.dumps({'B': B, 'keep8': os.environ.get('PRAM_SINKHORN_KEEP8', 'auto'), 'ms': round(ts[len(ts) // 2], 4),
+print(json.dumps({'B': B, 'maxg': os.environ.get('PRAM_SINKHORN_MAXG', 'auto'), 'ms': round(ts[len(ts) // 2], 4),
                   'checksum': int(out[0].sum().item())}))
