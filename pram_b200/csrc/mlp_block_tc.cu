@@ -452,6 +452,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_block_kernel(
                         }
                     }
                 }
+                // The scratch lives in ring slot 3, which the previous tile's conversion pass wrote last (k-block 7).  Those writes
+                // are already ordered before this point through SLOTF -> MMA -> tcgen05.commit(ACCF) -> every warp's ACCF wait
+                // in phase C, but that chain runs through the async proxy, which compute-sanitizer's racecheck cannot follow
+                // (it reported the pair); one named barrier per tile (~100 cycles of ~60k) makes the order explicit.
+                asm volatile("bar.sync 5, 512;" ::: "memory");
                 sts_f32(red + 4 * (part * 128 + r), s1);
                 sts_f32(red + 4 * (512 + part * 128 + r), s2);
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
